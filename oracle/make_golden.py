@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.pt by running the UNMODIFIED reference
+modules (via oracle/ref_shim.py) in the build container.  Run: ``python -m oracle.make_golden``.
+
+Weights are NOT stored (9.5 M floats): every case records the ``init_params`` seed; the
+reference modules are loaded with exactly those tensors through ``load_state_dict``.  Stored:
+inputs' seeds/shapes, loss, scores, alphas, encoder output, bias gradients in full, and for
+the big weight gradients their sum / abs-sum / first 256 values — plus a 3-step Adam loss
+trajectory.  The GPU box has no /root/reference: tests read only these files.
+"""
+import os
+import sys
+
+import torch
+
+from oracle import ref_model as rm
+from oracle import ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # name: B, H, W, V, tmin, tmax, train(dropout), positional
+    "tiny_eval": dict(B=2, H=32, W=64, V=40, tmin=3, tmax=6, train=False, positional=True, pseed=11, dseed=21),
+    "tiny_train": dict(B=3, H=32, W=80, V=40, tmin=3, tmax=7, train=True, positional=True, pseed=12, dseed=22),
+    "tiny_nopos": dict(B=2, H=48, W=64, V=37, tmin=2, tmax=5, train=False, positional=False, pseed=13, dseed=23),
+    "cfg1": dict(B=4, H=64, W=256, V=100, tmin=8, tmax=32, train=False, positional=True, pseed=14, dseed=24),
+}
+
+
+def summarize(g):
+    out = {}
+    for k, v in g.items():
+        v = v.detach()
+        if v.numel() <= 4096:
+            out[k] = v.clone()
+        else:
+            out[k] = dict(sum=v.double().sum().item(), abssum=v.double().abs().sum().item(),
+                          head=v.reshape(-1)[:256].clone(), shape=tuple(v.shape))
+    return out
+
+
+def dropout_masks(seed, B, T, D, p=0.5):
+    """Reproduces nn.Dropout's CPU draws of the reference forward (seq2seq_torch.py:316): after
+    manual_seed(seed) the only RNG consumers are the T dropout calls on [B, D]."""
+    torch.manual_seed(seed)
+    return torch.stack([torch.nn.functional.dropout(torch.ones(B, D), p, True) for _ in range(T)], dim=1)
+
+
+def run_case(name, c):
+    pe, pd = rm.init_params(c["V"], seed=c["pseed"])
+    enc, dec = ref_shim.build_reference_models(c["V"], positional_embeddings=c["positional"])
+    enc.load_state_dict(pe)
+    dec.load_state_dict(pd)
+    img, formula = rm.synthetic_batch(c["B"], c["H"], c["W"], c["V"], c["tmin"], c["tmax"], seed=c["dseed"])
+    T = formula.shape[1] - 1
+    enc.train(c["train"])
+    dec.train(c["train"])
+    rec = dict(case=c, torch=torch.__version__)
+    mask_seed = 1000 + c["dseed"]
+    oe = torch.optim.Adam(enc.parameters(), lr=1e-3)          # img2seq_torch.py:86-87
+    od = torch.optim.Adam(dec.parameters(), lr=1e-3)
+    traj = []
+    for step in range(3):
+        torch.manual_seed(mask_seed + step)
+        loss, scores, alphas = ref_shim.ref_get_loss(enc, dec, img, formula)
+        od.zero_grad()
+        oe.zero_grad()
+        loss.backward()
+        if step == 0:
+            rec["loss"] = loss.item()
+            rec["scores"] = scores.detach().clone()
+            rec["alphas"] = alphas.detach().clone()
+            rec["enc_out"] = enc(img).detach().clone()
+            rec["grad_enc"] = summarize({k: v.grad for k, v in enc.named_parameters()})
+            rec["grad_dec"] = summarize({k: v.grad for k, v in dec.named_parameters()})
+        od.step()
+        oe.step()
+        traj.append(-loss.item())                              # getLoss returns -loss (:172)
+    rec["get_loss_trajectory"] = traj
+    rec["mask_seed"] = mask_seed
+    rec["params_after_3_steps"] = summarize({**{"enc." + k: v for k, v in enc.state_dict().items()},
+                                             **{"dec." + k: v for k, v in dec.state_dict().items()}})
+    # self-check: restatement reproduces it bit for bit right now
+    mask = dropout_masks(mask_seed, c["B"], T, 512) if c["train"] else None
+    l2, aux = rm.get_loss(pe, pd, img, formula, dropout_mask=mask, positional=c["positional"])
+    assert abs(l2.item() - rec["loss"]) == 0.0, (name, l2.item(), rec["loss"])
+    assert (aux["scores"] - rec["scores"]).abs().max().item() == 0.0
+    torch.save(rec, os.path.join(OUT, name + ".pt"))
+    print(name, "loss", rec["loss"], "traj", traj, "T", T,
+          "bytes", os.path.getsize(os.path.join(OUT, name + ".pt")))
+
+
+def main():
+    if not ref_shim.reference_available():
+        sys.exit("reference tree not available; golden files can only be regenerated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    for name, c in CASES.items():
+        run_case(name, c)
+
+
+if __name__ == "__main__":
+    main()
