@@ -1,0 +1,134 @@
+"""Helpers for bench.py: synthetic workload, per-kernel roofline probes (CUDA events on the launching
+stream), launch counting, and the CPU baseline leg (the only place outside tests/ that runs oracle/)."""
+import ctypes
+import os
+import time
+
+import torch
+
+
+def tc_ready():
+    from latex_ocr_b200 import _lib
+    return bool(_lib.lib().lo_tc_available())
+
+
+def synthetic_batch(B, H, W, V, T, seed):
+    """white (255) background with 10 % random ink; targets of length U{20..T}, then END,
+    PAD up to T+1 columns (model/utils/text.py:157-162).  ids 0..V-4 tokens, V-2 PAD, V-1 END."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.full((B, 1, H, W), 255.0)
+    ink = torch.rand((B, 1, H, W), generator=g) < 0.10
+    img = torch.where(ink, torch.randint(0, 255, (B, 1, H, W), generator=g).float(), img)
+    lens = torch.randint(min(20, T), T + 1, (B,), generator=g)
+    lens[0] = T
+    formula = torch.full((B, T + 1), V - 2, dtype=torch.long)
+    for b in range(B):
+        n = int(lens[b])
+        formula[b, :n] = torch.randint(0, V - 3, (n,), generator=g)
+        formula[b, n] = V - 1
+    return img, formula
+
+
+def launches_per_step(model, img_dev, formula_dev):
+    """Kernels launched by ONE train step (counted on an eager replay of the same step body)."""
+    from latex_ocr_b200 import _lib
+    N, L = formula_dev.shape
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    mask = model.decoder.make_dropout_mask(N, L - 1)
+    model._step_body(img_dev.float(), formula_dev, [L - 1] * N, mask)
+    torch.cuda.synchronize()
+    return _lib.launch_count() - n0
+
+
+def _time_ms(fn, iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def kernel_probes(model, c, pk):
+    """Roofline objects for the two kernels the north star names:
+       attention step kernel — HBM bound: algorithmic bytes = B*R*(A+C)*bpe + B*R*4 per launch
+       conv stack fwd+bwd   — tensor bound: 56.0 GFLOP per image (fwd + dgrad + wgrad)."""
+    from latex_ocr_b200 import _lib
+    L = _lib.lib()
+    dec, enc = model.decoder, model.encoder
+    B, T = c["B"], c["T"]
+    key = [k for k in dec._ws if k[0] == B and k[1] == T][0]
+    R = key[2]
+    ws = dec._ws[key]
+    t, a = ws["t"], ws["args"]
+    bpe = 2 if dec.precision == "bf16" else 4
+    A = C = 512
+    O1 = A + C + 4 * 512
+    enc_ws = enc._ws[(B, c["H"], c["W"])]
+    enc_out = enc_ws["out"].view(B, R, C)
+    st = _lib.stream_ptr()
+    dt = _lib.LO_BF16 if bpe == 2 else _lib.LO_F32
+
+    def att_steps():
+        for s in range(T):
+            o1 = t["out1"][s]
+            _lib.check(L.lo_attention_forward(_lib.ptr(t["att1"]), _lib.ptr(enc_out), dt, _lib.ptr(o1), O1, a.w_full,
+                                              ctypes.c_void_p(t["alphas"].data_ptr() + s * R * 4), T * R, _lib.ptr(t["ctx"][s]),
+                                              None, 0, None, B, R, A, C, _lib.ptr(t["work"]), st))
+
+    ms_att = _time_ms(att_steps, 3) / T
+    att_bytes = B * R * (A + C) * bpe + B * R * 4
+    att = {"kernel": "attention_fwd_kernel (score+softmax+context, one decode step)", "bound": "hbm",
+           "achieved": att_bytes / (ms_att * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "traffic": None,
+           "us_per_launch": ms_att * 1e3, "algorithmic_bytes": att_bytes, "peak_source": pk["src"]}
+    att["frac"] = att["achieved"] / att["peak"]
+
+    img = enc_ws["img"]
+    denc = t["denc"].view(B, enc_ws["out"].shape[1], enc_ws["out"].shape[2], C)
+
+    def conv_all():
+        enc.forward_raw(img, need_grad=True)
+        enc.backward_raw(tuple(img.shape), denc)
+
+    ms_conv = _time_ms(conv_all, 3)
+    flops = B * 56.0e9
+    conv = {"kernel": "conv stack fwd+dgrad+wgrad (6 layers, incl. pools/ReLU masks)", "bound": "tensor",
+            "achieved": flops / (ms_conv * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "traffic": None,
+            "ms": ms_conv, "algorithmic_flops": flops, "peak_source": pk["src"] + " (sustained cuBLAS bf16)"}
+    conv["frac"] = conv["achieved"] / conv["peak"]
+
+    def dec_all():
+        _lib.check(L.lo_decoder_forward(ctypes.byref(a), 1, st))
+        _lib.check(L.lo_decoder_backward(ctypes.byref(a), st))
+
+    ms_dec = _time_ms(dec_all, 2)
+    extra = {"decoder_fwd_bwd_ms": ms_dec, "encoder_fwd_bwd_ms": ms_conv, "attention_fwd_us_per_step": ms_att * 1e3}
+    dominant = conv if ms_conv >= T * ms_att * 2 else att
+    return {"dominant": dominant, "all": {"attention": att, "conv": conv, "phases": extra}}
+
+
+def cpu_baseline(c):
+    """The reference's CPU algorithm (oracle port, executed un-hoisted like the reference) on this box's
+    host cores, on a bounded sample of the workload."""
+    from oracle import ref_model as rm
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sb = int(os.environ.get("LO_REF_SAMPLE_B", "4"))
+    pe, pd = rm.init_params(c["V"], seed=0)
+    img, formula = rm.synthetic_batch(sb, c["H"], c["W"], c["V"], c["T"], c["T"], seed=1234)
+    state = {}
+    t0 = time.perf_counter()
+    rm.train_step(pe, pd, img, formula, state, hoist=False)        # warm-up (also bounds the sample)
+    warm = time.perf_counter() - t0
+    n = 2 if warm < 12 else 1
+    t0 = time.perf_counter()
+    for _ in range(n):
+        rm.train_step(pe, pd, img, formula, state, hoist=False)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": sb / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "%d of %d images per step (cfg2 shapes), %d timed step(s) after 1 warm-up, torch %s CPU fp32, %.2f s/step"
+                      % (sb, c["B"], n, torch.__version__, dt)}

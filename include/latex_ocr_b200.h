@@ -1,0 +1,206 @@
+/*
+ * latex_ocr_b200 — C ABI of the B200-native (sm_100a) im2latex hot path.
+ *
+ * The reference (LinXueyuanStdio/LaTeX_OCR) has no FFI: its boundary is the Python class surface
+ * (SURVEY.md §8-b).  Each entry point below replaces the library call(s) the reference makes at the
+ * cited lines; the Python mirror in latex_ocr_b200/ (EncoderCNN, Attention, DecoderWithAttention,
+ * Img2SeqModel) reaches them through ctypes.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*); no allocation, no synchronisation,
+ *     no host-visible global state -> every call is CUDA-graph capturable;
+ *   - return 0 on success, negative LO_E* otherwise (never throws); lo_last_error() gives the text;
+ *   - dtype arguments are LO_F32 or LO_BF16 and name the STORAGE type of the "big" tensors
+ *     (feature maps, conv/linear weight shadows, encoder_out, att1).  Small per-step state is fp32.
+ *     Accumulation is always fp32.
+ */
+#ifndef LATEX_OCR_B200_H
+#define LATEX_OCR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LO_F32 0
+#define LO_BF16 1
+
+#define LO_OK 0
+#define LO_EINVAL (-1)   /* bad argument / unsupported shape */
+#define LO_ECUDA (-2)    /* a CUDA runtime call or launch failed */
+#define LO_ENOTSUP (-3)  /* path not available on this device (needs sm_100) */
+
+#define LO_IMPL_SIMT 0   /* CUDA-core kernels (fp32 or bf16 storage) — the tight-parity path */
+#define LO_IMPL_TC 1     /* tcgen05 + TMA kernels (bf16 storage only) */
+
+int lo_version(void);
+const char* lo_last_error(void);
+/* number of kernels launched through this library since load (bench.py's gpu_launches) */
+int64_t lo_launch_count(void);
+/* 1 if the tcgen05/TMA kernels are built in and the current device is sm_100 */
+int lo_tc_available(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic strided (batched) GEMM:  C[b][m][n] (+)= sum_k A[b][m*sam + k*sak] * B[b][k*sbk + n*sbn] (+ bias[n]) (ReLU)
+ * Replaces nn.Linear / torch.mm call sites: seq2seq_torch.py:172-176, :223-227 and their autograd.
+ * dtA/dtB/dtC in {LO_F32, LO_BF16}; supported combos: (f,f,f) (f,bf,f) (bf,bf,bf) (bf,bf,f).
+ * impl=LO_IMPL_TC requires bf16 A and B, sak==1, sbk==1 (both K-major), K%64==0, 16B-aligned rows.
+ */
+int lo_gemm(const void* A, int dtA, const void* B, int dtB, void* C, int dtC,
+            int M, int N, int K,
+            int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc,
+            int batch, int64_t sA, int64_t sB, int64_t sC,
+            const float* bias, int accumulate, int relu, int impl, void* stream);
+
+/* column sums: out[n] (+)= sum_m X[m*ld + n]  (bias gradients) ; X fp32 or bf16 */
+int lo_colsum(const void* X, int dt, float* out, int M, int N, int64_t ld, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder.  Feature maps are NHWC; conv weights are [Cout][3][3][Cin] ("KRSC", K-major for the
+ * implicit GEMM); replaces nn.Conv2d/nn.ReLU/nn.MaxPool2d at seq2seq_torch.py:35-56 and
+ * convolution_backward (autograd of img2seq_torch.py:165).
+ */
+/* conv1 (Cin=1) + bias + ReLU + 2x2/2 max-pool fused; img fp32 [N][H][W] raw 0..255
+ * (img2seq_torch.py:115-117); out [N][H/2][W/2][64] */
+int lo_conv1_pool_forward(const float* img, const float* w, const float* bias, void* out, int dt,
+                          int N, int H, int W, void* stream);
+/* conv1 weight/bias gradient from the POOLED output gradient; recomputes conv1 to find the
+ * ReLU mask and pool argmax (first maximum in window scan order, as PyTorch) */
+int lo_conv1_pool_wgrad(const float* img, const float* w, const float* bias, const void* dpool, int dt,
+                        float* dw, float* db, int N, int H, int W, void* stream);
+/* y = [relu](conv3x3(x, w, pad) + bias) [* (mask > 0)] ; x [N][H][W][Cin], y [N][H+2pad-2][W+2pad-2][Cout];
+ * pad in {0,1,2}.  mask (optional, same shape/dtype as y) implements the ReLU backward when this
+ * call computes a data gradient.  bias may be NULL. */
+int lo_conv3x3(const void* x, const void* w, const float* bias, const void* mask, void* y, int dt,
+               int N, int H, int W, int Cin, int Cout, int pad, int relu, int impl, void* stream);
+/* dw[Cout][3][3][Cin] = sum x (*) dy ; db[Cout] = sum dy ; x [N][H][W][Cin], dy [N][Ho][Wo][Cout] */
+int lo_conv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, int dt,
+                     int N, int H, int W, int Cin, int Cout, int pad, int impl, void* stream);
+/* wt[Cin][3][3][Cout] = w[Cout][2-r][2-s][Cin]  (weights of the data-gradient convolution) */
+int lo_conv_weight_flip(const void* w, void* wt, int dt, int Cin, int Cout, void* stream);
+/* floor-mode max-pool kh x kw, stride = kernel (nn.MaxPool2d seq2seq_torch.py:37,42,49,52) */
+int lo_maxpool_forward(const void* x, void* y, int dt, int N, int H, int W, int C, int kh, int kw, void* stream);
+/* dx = route dy to the first maximum of each window, times (x > 0) (x is a ReLU output) */
+int lo_maxpool_backward(const void* x, const void* y, const void* dy, void* dx, int dt,
+                        int N, int H, int W, int C, int kh, int kw, void* stream);
+/* out = y + timing_signal (seq2seq_torch.py:115-157); table fp32 [H][W][C] built once by the host */
+int lo_add_table(const void* y, const float* table, void* out, int dt, int N, int64_t HWC, void* stream);
+/* dY6 = denc (fp32) * (y6 > 0), cast to dt */
+int lo_relu_mask_cast(const float* g, const void* y, void* out, int dt, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention (single step): Attention.forward seq2seq_torch.py:178-192 with att1 hoisted.
+ * att1,enc [B][R][A|C] (dt) ; att2 [B][A] fp32 (= decoder_att(h)) ; wf [A] fp32 (full_att.weight; its bias
+ * cancels in the softmax) ; alpha out fp32 [B][alpha_stride>=R] ; ctx out fp32 [B][C].
+ * gate_pre (optional) [B][gate_stride]: if given, gate = sigmoid(gate_pre) is written back in place and
+ * gctx [B][C] = gate*ctx (seq2seq_torch.py:311-312).  work: lo_attention_workspace_bytes(B, C) bytes.
+ */
+int64_t lo_attention_workspace_bytes(int B, int C);
+int lo_attention_forward(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
+                         const float* wf, float* alpha, int64_t alpha_stride, float* ctx,
+                         float* gate_pre, int64_t gate_stride, float* gctx,
+                         int B, int R, int A, int C, void* work, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole teacher-forced decoder: DecoderWithAttention.forward seq2seq_torch.py:267-320 (+ the loss of
+ * img2seq_torch.py:147-159) and its hand-derived backward.  One struct carries every buffer; the
+ * Python side (latex_ocr_b200/decoder.py) parses THIS header to build the ctypes mirror.
+ * Shapes: B rows (already sorted by length), T steps, R regions, C=enc dim, A=att dim, D=decoder dim,
+ * E=embed dim, V=vocab.  "f32" fields are float*, "big" fields are `dt` storage.
+ */
+typedef struct lo_decoder_args {
+  int32_t B, T, R, C, A, D, E, V;
+  int32_t dt;              /* storage of enc/att1/weight shadows */
+  int32_t impl;            /* LO_IMPL_SIMT | LO_IMPL_TC for the hoisted GEMMs */
+  int32_t has_dropout;     /* 0: eval ; 1: multiply h by dropout_mask before fc */
+  int32_t reserved0;
+  float alpha_c;           /* doubly-stochastic regulariser weight (img2seq_torch.py:157) */
+  float reserved1;
+  const int32_t* bt_host;  /* HOST int[T]: rows active at step t (seq2seq_torch.py:308); non-increasing */
+  const int64_t* caps;     /* [B][caps_stride] token ids (sorted rows) */
+  int64_t caps_stride;
+  /* inputs */
+  const void* enc;         /* big [B][R][C] */
+  /* parameters: weight shadows in `dt`, biases fp32.  Wcat1 = [decoder_att; f_beta; weight_hh] rows
+   * (contiguous [A+C+4D][D]), bcat1 likewise.  w_ih is [4D][E+C]. */
+  const void* w_enc_att; const float* b_enc_att;   /* [A][C] */
+  const void* wcat1; const float* bcat1;           /* [A+C+4D][D] */
+  const float* w_full;                             /* [A] fp32 */
+  const void* emb;                                 /* [V][E] */
+  const void* w_ih; const float* b_ih;             /* [4D][E+C] */
+  const void* w_init; const float* b_init;         /* [2D][C]: init_h rows then init_c rows */
+  const void* w_fc; const float* b_fc;             /* [V][D] */
+  /* transposed shadows for the backward per-step GEMMs (built by lo_decoder_pack_bwd_weights) */
+  void* wbwd1;             /* [C+D][4D]: rows 0..C-1 = w_ih[:,E+j]^T, rows C.. = w_hh[:,j]^T */
+  void* wbwd2;             /* [D][A+C]: [n][k] = k<A ? w_dec_att[k][n] : w_f_beta[k-A][n] */
+  /* forward state (f32 unless noted) */
+  void* att1;              /* big [B][R][A] */
+  float* ptab;             /* [V][4D] = emb @ w_ih[:, :E]^T + b_ih */
+  float* mean;             /* [B][C] */
+  float* hall;             /* [T+1][B][D] */
+  float* call;             /* [T+1][B][D] */
+  float* out1;             /* [T][B][A+C+4D]: att2 | gate (sigmoid applied) | h@w_hh^T+b_hh */
+  float* alphas;           /* [B][T][R] */
+  float* ctx;              /* [T][B][C] */
+  float* gctx;             /* [T][B][C] */
+  float* gates;            /* [T][B][4D] post-activation i,f,g,o */
+  float* gtmp;             /* [B][4D] scratch */
+  const float* dropout_mask; /* [B][T][D] multipliers or NULL */
+  float* hd;               /* [B][T][D] h after dropout */
+  float* logits;           /* [B][T][V]  (== predictions) */
+  /* loss */
+  float* row_loss;         /* [B*T] */
+  float* loss;             /* [4]: total, ce, reg, n_valid */
+  /* backward state */
+  float* dlogits;          /* [B][T][V] */
+  float* dhd;              /* [B][T][D] */
+  float* dreg;             /* [B][R] gradient of the regulariser w.r.t. alpha (same for every t) */
+  const float* dalpha_ext; /* optional external d loss/d alphas [B][T][R] (generic autograd mode); overrides dreg */
+  float* sreg;             /* [B][T] */
+  float* dcat;             /* [T][B][A+C+4D]: datt2 | dgate_pre | dgates_pre */
+  float* dxh;              /* [B][C+D] scratch: dgctx | dh_prev */
+  float* dc;               /* [2][B][D] ping-pong dc */
+  float* dctx;             /* [T][B][C] */
+  float* de;               /* [B][T][R] */
+  float* dptab;            /* [V][4D] */
+  void* datt1;             /* big [B][R][A] */
+  float* denc;             /* f32 [B][R][C]  (output: gradient w.r.t. encoder_out) */
+  float* dinit;            /* [B][2D] = dh0 | dc0 */
+  float* dmean;            /* [B][C] */
+  /* parameter gradients (fp32, reference layouts) */
+  float* g_w_enc_att; float* g_b_enc_att;
+  float* g_wcat1; float* g_bcat1;
+  float* g_w_full; float* g_b_full;
+  float* g_emb;
+  float* g_w_ih; float* g_b_ih;
+  float* g_w_init; float* g_b_init;
+  float* g_w_fc; float* g_b_fc;
+  void* work;              /* lo_attention_workspace_bytes(B, max(A,C)) */
+} lo_decoder_args;
+
+/* sizeof(lo_decoder_args) as compiled into the library (the ctypes mirror checks it) */
+int64_t lo_sizeof_decoder_args(void);
+/* forward through all T steps + logits ; if with_loss, also CE + regulariser into loss[] */
+int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream);
+/* backward of loss[0]; fills every g_* and denc.  Requires lo_decoder_forward(with_loss=1) state. */
+int lo_decoder_backward(const lo_decoder_args* a, void* stream);
+int lo_decoder_pack_bwd_weights(const lo_decoder_args* a, void* stream);
+
+/* greedy decode on the same step kernels (decode loop semantics of dynamic_decode.py:17-74 +
+ * greedy_decoder_cell.py:46-66): tokens out [B][max_steps] int64, first input token = start_id */
+int lo_decoder_greedy(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps,
+                      int64_t* tokens, int32_t* finished, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser: torch.optim.Adam defaults (img2seq_torch.py:86-87, :168-170) on one flat buffer.
+ * state_dev: float[2] = {step (as float), lr}; step is incremented on the device so the call is
+ * graph-replayable.  shadow (optional) receives the bf16 copy of the updated parameters.
+ */
+int lo_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n,
+                 float* state_dev, float beta1, float beta2, float eps, float grad_scale, void* stream);
+int lo_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATEX_OCR_B200_H */

@@ -1,0 +1,139 @@
+// Shared device/host helpers for the latex_ocr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/latex_ocr_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+namespace lo {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+extern char g_err[512];
+extern int64_t g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+#define LO_CHECK_ARG(cond, what)                                                        \
+  do {                                                                                  \
+    if (!(cond)) return lo::fail(LO_EINVAL, "%s: invalid argument: " what " (line %ld)", __func__, __LINE__); \
+  } while (0)
+
+#define LO_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return lo::fail(LO_ECUDA, "%s: CUDA error %ld at line %ld", cudaGetErrorString(e__), (long)e__, __LINE__); \
+  } while (0)
+
+// call after every <<<>>> launch
+#define LO_LAUNCH_OK()                                                                  \
+  do {                                                                                  \
+    lo::g_launches++;                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess)                                                             \
+      return lo::fail(LO_ECUDA, "%s: launch failed (%ld) at line %ld", cudaGetErrorString(e__), (long)e__, __LINE__); \
+  } while (0)
+
+#define LO_TRY(call)                                                                    \
+  do {                                                                                  \
+    int r__ = (call);                                                                   \
+    if (r__ != LO_OK) return r__;                                                       \
+  } while (0)
+
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---- dtype helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+// value as it will be read back after a store to T (used so fwd masks == bwd masks)
+__device__ __forceinline__ float roundto(float v, const float*) { return v; }
+__device__ __forceinline__ float roundto(float v, const bf16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// 8 consecutive elements -> 8 floats (16-byte aligned for bf16, 32-byte for float)
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float* v) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// host-side dtype dispatch: calls f(T*) with T = float or bf16
+#define LO_DISPATCH_DT(dt, T, ...)                   \
+  do {                                               \
+    if ((dt) == LO_F32) { typedef float T; __VA_ARGS__; } \
+    else if ((dt) == LO_BF16) { typedef bf16 T; __VA_ARGS__; } \
+    else return lo::fail(LO_EINVAL, "%s: bad dtype %ld", __func__, (long)(dt)); \
+  } while (0)
+
+// ---- internal launchers shared between translation units ---------------------------------------
+struct GemmDesc {
+  int M, N, K;
+  int64_t sam, sak, sbk, sbn, ldc;
+  int batch;
+  int64_t sA, sB, sC;
+  const float* bias;
+  int accumulate, relu;
+};
+int gemm(const void* A, int dtA, const void* B, int dtB, void* C, int dtC, const GemmDesc& d, int impl, cudaStream_t st);
+// C[M][N] (+)= A[M][K] * W[N][K]^T + bias  (row-major, K contiguous)
+int gemm_nt(const void* A, int dtA, int64_t lda, const void* W, int dtW, int64_t ldw, void* C, int dtC, int64_t ldc,
+            int M, int N, int K, const float* bias, int accumulate, int relu, int impl, cudaStream_t st);
+// C[M][N] (+)= A[K][M]^T * B[K][N]   (weight gradients)
+int gemm_tn(const void* A, int dtA, int64_t lda, const void* B, int dtB, int64_t ldb, void* C, int dtC, int64_t ldc,
+            int M, int N, int K, int accumulate, int impl, cudaStream_t st);
+// C[M][N] (+)= A[M][K] * B[K][N]
+int gemm_nn(const void* A, int dtA, int64_t lda, const void* B, int dtB, int64_t ldb, void* C, int dtC, int64_t ldc,
+            int M, int N, int K, int accumulate, int impl, cudaStream_t st);
+int colsum(const void* X, int dt, float* out, int M, int N, int64_t ld, int accumulate, cudaStream_t st);
+
+// tcgen05 paths (lo_tc.cu)
+bool tc_available();
+int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc,
+               int M, int N, int K, const float* bias, int accumulate, int relu, cudaStream_t st);
+int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask, bf16* y,
+               int N, int H, int W, int Cin, int Cout, int pad, int relu, cudaStream_t st);
+
+}  // namespace lo

@@ -1,0 +1,919 @@
+// Attention-LSTM decoder of the torch flavour (DecoderWithAttention, seq2seq_torch.py:195-320) with the
+// loss of img2seq_torch.py:147-159: forward over T teacher-forced steps, hand-derived backward.
+//
+// Schedule: everything that does not depend on the recurrence is hoisted out of the
+// time loop (att1 = encoder_att(enc), the embedding->gate projection table, logits, every weight
+// gradient, d att1 and d enc).  Inside the loop each step reads enc and att1 exactly ONCE in forward
+// and ONCE in backward (the HBM roofline of SURVEY.md §8-d) and runs two skinny GEMMs.
+#include "lo_common.cuh"
+
+namespace lo {
+
+#define LO_ATT_THREADS 256
+#define LO_ATT_WARPS 8
+#define LO_ATT_MAXSPLIT 16
+
+static inline int att_splits(int B) {
+  int s = (444 + B - 1) / B;
+  if (s < 1) s = 1;
+  if (s > LO_ATT_MAXSPLIT) s = LO_ATT_MAXSPLIT;
+  return s;
+}
+
+__device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
+
+// ------------------------------------------------------------------------------------------------
+// K5: attention forward for one step.  grid (nsplit, B), 256 threads.  Each warp streams rows of
+// att1 and enc (16 B per lane per load), keeps an online-softmax state (m, l, acc[C/32]) in registers;
+// CTA combine in smem, cross-CTA combine by the last CTA to finish (threadfence + ticket).
+// NV = A/256 = C/256 vectors of 8 elements per lane.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(LO_ATT_THREADS) attention_fwd_kernel(
+    const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
+    const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
+    float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, int R, int nsplit,
+    int* __restrict__ counters, float* __restrict__ partials) {
+  constexpr int CH = NV * 256;   // A == C == CH
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rps = (R + nsplit - 1) / nsplit;
+  const int r0 = sp * rps, r1 = min(R, r0 + rps);
+  float a2[NV * 8], wv[NV * 8], acc[NV * 8];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
+    ld8(wf + (j * 32 + lane) * 8, wv + j * 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[j * 8 + i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  const T* a1b = att1 + (int64_t)b * R * CH;
+  const T* eb = enc + (int64_t)b * R * CH;
+  float* alb = alpha + (int64_t)b * alpha_stride;
+  for (int r = r0 + wid; r < r1; r += 2 * LO_ATT_WARPS) {
+    const int rb = r + LO_ATT_WARPS;
+    const bool two = rb < r1;
+    float v0[NV * 8], v1[NV * 8], u0[NV * 8], u1[NV * 8];
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      ld8(a1b + (int64_t)r * CH + (j * 32 + lane) * 8, v0 + j * 8);
+      ld8(eb + (int64_t)r * CH + (j * 32 + lane) * 8, u0 + j * 8);
+    }
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+        ld8(a1b + (int64_t)rb * CH + (j * 32 + lane) * 8, v1 + j * 8);
+        ld8(eb + (int64_t)rb * CH + (j * 32 + lane) * 8, u1 + j * 8);
+      }
+    }
+    float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; i++) {
+      e0 = fmaf(wv[i], fmaxf(v0[i] + a2[i], 0.f), e0);
+      if (two) e1 = fmaf(wv[i], fmaxf(v1[i] + a2[i], 0.f), e1);
+    }
+    e0 = warp_sum(e0);
+    e1 = warp_sum(e1);
+    if (lane == 0) {
+      alb[r] = e0;
+      if (two) alb[rb] = e1;
+    }
+    const float mn = two ? fmaxf(m, fmaxf(e0, e1)) : fmaxf(m, e0);
+    const float sc = expf(m - mn);     // m = -inf on the first row -> 0
+    const float p0 = expf(e0 - mn);
+    const float p1 = two ? expf(e1 - mn) : 0.f;
+    l = l * sc + p0 + p1;
+#pragma unroll
+    for (int i = 0; i < NV * 8; i++) {
+      float t = acc[i] * sc;
+      t = fmaf(p0, u0[i], t);
+      if (two) t = fmaf(p1, u1[i], t);
+      acc[i] = t;
+    }
+    m = mn;
+  }
+  // ---- CTA combine
+  __shared__ float s_m[LO_ATT_WARPS], s_l[LO_ATT_WARPS];
+  __shared__ float s_acc[LO_ATT_WARPS][CH];
+  __shared__ float s_scale[LO_ATT_MAXSPLIT];
+  __shared__ float s_ML[2];
+  __shared__ int s_last;
+  if (lane == 0) { s_m[wid] = m; s_l[wid] = l; }
+#pragma unroll
+  for (int j = 0; j < NV; j++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) s_acc[wid][(j * 32 + lane) * 8 + i] = acc[j * 8 + i];
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < LO_ATT_WARPS; w++) M = fmaxf(M, s_m[w]);
+  float L = 0.f;
+  float wsc[LO_ATT_WARPS];
+#pragma unroll
+  for (int w = 0; w < LO_ATT_WARPS; w++) {
+    wsc[w] = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - M);
+    L += s_l[w] * wsc[w];
+  }
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += LO_ATT_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < LO_ATT_WARPS; w++) t = fmaf(s_acc[w][c], wsc[w], t);
+    part[2 + c] = t;
+  }
+  if (threadIdx.x == 0) { part[0] = M; part[1] = L; }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + b, 1);
+    s_last = (ticket == nsplit - 1);
+    if (s_last) counters[b] = 0;   // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last CTA of this batch row: global combine, write ctx (+gate), normalise alpha
+  const float* pb = partials + (int64_t)b * nsplit * (CH + 2);
+  if (threadIdx.x == 0) {
+    float Mg = -INFINITY;
+    for (int s = 0; s < nsplit; s++) Mg = fmaxf(Mg, ldcg_f(pb + (int64_t)s * (CH + 2)));
+    float Lg = 0.f;
+    for (int s = 0; s < nsplit; s++) {
+      const float ms = ldcg_f(pb + (int64_t)s * (CH + 2));
+      const float scl = (ms == -INFINITY) ? 0.f : expf(ms - Mg);
+      s_scale[s] = scl;
+      Lg += ldcg_f(pb + (int64_t)s * (CH + 2) + 1) * scl;
+    }
+    s_ML[0] = Mg;
+    s_ML[1] = 1.0f / Lg;
+  }
+  __syncthreads();
+  const float Mg = s_ML[0], invL = s_ML[1];
+  for (int c = threadIdx.x; c < CH; c += LO_ATT_THREADS) {
+    float t = 0.f;
+    for (int s = 0; s < nsplit; s++) t = fmaf(ldcg_f(pb + (int64_t)s * (CH + 2) + 2 + c), s_scale[s], t);
+    t *= invL;
+    ctx[(int64_t)b * CH + c] = t;
+    if (gate_pre) {
+      const float g = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
+      gate_pre[(int64_t)b * gate_stride + c] = g;
+      gctx[(int64_t)b * CH + c] = g * t;
+    }
+  }
+  for (int r = threadIdx.x; r < R; r += LO_ATT_THREADS) alb[r] = expf(ldcg_f(alb + r) - Mg) * invL;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: attention backward for one step (same streaming structure; reads enc and att1 once).
+//   dctx = dgctx*gate ; dgp = dgctx*ctx*gate*(1-gate) ; s = <dctx,ctx> + sreg
+//   dalpha_r = <dctx, enc_r> + dreg_r ; de_r = alpha_r (dalpha_r - s) ; datt2_a = wf_a sum_r de_r [att1_ra + att2_a > 0]
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(LO_ATT_THREADS) attention_bwd_kernel(
+    const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, const float* __restrict__ gate,
+    int64_t o1_stride, const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride,
+    const float* __restrict__ ctx, const float* __restrict__ dgctx, int64_t dg_stride, const float* __restrict__ dreg,
+    int64_t dreg_stride, const float* __restrict__ sreg, int64_t sreg_stride, float* __restrict__ de, float* __restrict__ datt2,
+    float* __restrict__ dgp, int64_t dcat_stride, float* __restrict__ dctx_out, int R, int nsplit,
+    int* __restrict__ counters, float* __restrict__ partials) {
+  constexpr int CH = NV * 256;
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rps = (R + nsplit - 1) / nsplit;
+  const int r0 = sp * rps, r1 = min(R, r0 + rps);
+  float a2[NV * 8], dc[NV * 8], macc[NV * 8];
+  float sdot = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const int c0 = (j * 32 + lane) * 8;
+    float g[8], cx[8], dg[8];
+    ld8(att2 + (int64_t)b * o1_stride + c0, a2 + j * 8);
+    ld8(gate + (int64_t)b * o1_stride + c0, g);
+    ld8(ctx + (int64_t)b * CH + c0, cx);
+    ld8(dgctx + (int64_t)b * dg_stride + c0, dg);
+    float gp[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      dc[j * 8 + i] = dg[i] * g[i];
+      sdot = fmaf(dc[j * 8 + i], cx[i], sdot);
+      gp[i] = dg[i] * cx[i] * g[i] * (1.f - g[i]);
+      macc[j * 8 + i] = 0.f;
+    }
+    if (sp == 0 && wid == 0) {
+      st8(dgp + (int64_t)b * dcat_stride + c0, gp);
+      st8(dctx_out + (int64_t)b * CH + c0, dc + j * 8);
+    }
+  }
+  const float s = warp_sum(sdot) + sreg[(int64_t)b * sreg_stride];
+  const T* a1b = att1 + (int64_t)b * R * CH;
+  const T* eb = enc + (int64_t)b * R * CH;
+  const float* alb = alpha + (int64_t)b * alpha_stride;
+  float* deb = de + (int64_t)b * alpha_stride;
+  const float* drb = dreg + (int64_t)b * dreg_stride;
+  for (int r = r0 + wid; r < r1; r += 2 * LO_ATT_WARPS) {
+    const int rb = r + LO_ATT_WARPS;
+    const bool two = rb < r1;
+    float v0[NV * 8], v1[NV * 8], u0[NV * 8], u1[NV * 8];
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      ld8(eb + (int64_t)r * CH + (j * 32 + lane) * 8, u0 + j * 8);
+      ld8(a1b + (int64_t)r * CH + (j * 32 + lane) * 8, v0 + j * 8);
+    }
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+        ld8(eb + (int64_t)rb * CH + (j * 32 + lane) * 8, u1 + j * 8);
+        ld8(a1b + (int64_t)rb * CH + (j * 32 + lane) * 8, v1 + j * 8);
+      }
+    }
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; i++) {
+      d0 = fmaf(dc[i], u0[i], d0);
+      if (two) d1 = fmaf(dc[i], u1[i], d1);
+    }
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    const float de0 = alb[r] * (d0 + drb[r] - s);
+    const float de1 = two ? alb[rb] * (d1 + drb[rb] - s) : 0.f;
+    if (lane == 0) {
+      deb[r] = de0;
+      if (two) deb[rb] = de1;
+    }
+#pragma unroll
+    for (int i = 0; i < NV * 8; i++) {
+      macc[i] += (v0[i] + a2[i] > 0.f) ? de0 : 0.f;
+      if (two) macc[i] += (v1[i] + a2[i] > 0.f) ? de1 : 0.f;
+    }
+  }
+  __shared__ float s_acc[LO_ATT_WARPS][CH];
+  __shared__ int s_last;
+#pragma unroll
+  for (int j = 0; j < NV; j++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) s_acc[wid][(j * 32 + lane) * 8 + i] = macc[j * 8 + i];
+  __syncthreads();
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += LO_ATT_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < LO_ATT_WARPS; w++) t += s_acc[w][c];
+    part[2 + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + b, 1);
+    s_last = (ticket == nsplit - 1);
+    if (s_last) counters[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = partials + (int64_t)b * nsplit * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += LO_ATT_THREADS) {
+    float t = 0.f;
+    for (int sidx = 0; sidx < nsplit; sidx++) t += ldcg_f(pb + (int64_t)sidx * (CH + 2) + 2 + c);
+    datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hoisted d att1 / d w_full: ONE sweep over att1 after the time loop.
+//   datt1[b,r,a] = wf[a] * sum_t de[b,t,r] * [att1[b,r,a] + att2[t,b,a] > 0]
+//   dwf[a]      += sum_{b,r,t} de[b,t,r] * relu(att1[b,r,a] + att2[t,b,a])
+// grid (A/64, ceil(R/32), B), 128 threads, thread tile 4(r) x 4(a), time chunks of 32 staged in smem.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, const float* __restrict__ out1,
+                                                     int64_t o1_row, int64_t o1_step, const float* __restrict__ de,
+                                                     const float* __restrict__ wf, T* __restrict__ datt1,
+                                                     float* __restrict__ dwf, int Tn, int R, int A) {
+  constexpr int TT = 32;
+  __shared__ __align__(16) float s_a2[TT][64];
+  __shared__ __align__(16) float s_de[TT][32];
+  __shared__ float s_w[8][64];
+  const int b = blockIdx.z, r0 = blockIdx.y * 32, a0 = blockIdx.x * 64;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;   // a = a0 + tx*4.., r = r0 + ty*4..
+  float x[4][4], acc[4][4], wacc[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    wacc[i] = 0.f;
+    const int r = r0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      acc[i][j] = 0.f;
+      x[i][j] = (r < R) ? ldf(att1 + ((int64_t)b * R + r) * A + a0 + tx * 4 + j) : -INFINITY;
+    }
+  }
+  for (int t0 = 0; t0 < Tn; t0 += TT) {
+    for (int i = threadIdx.x; i < TT * 64; i += 128) {
+      const int tt = i / 64, a = i % 64;
+      s_a2[tt][a] = (t0 + tt < Tn) ? out1[(int64_t)(t0 + tt) * o1_step + (int64_t)b * o1_row + a0 + a] : 0.f;
+    }
+    for (int i = threadIdx.x; i < TT * 32; i += 128) {
+      const int tt = i / 32, r = i % 32;
+      s_de[tt][r] = (t0 + tt < Tn && r0 + r < R) ? de[((int64_t)b * Tn + t0 + tt) * R + r0 + r] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int tt = 0; tt < TT; tt++) {
+      const float4 q = *reinterpret_cast<const float4*>(&s_a2[tt][tx * 4]);
+      const float4 d4 = *reinterpret_cast<const float4*>(&s_de[tt][ty * 4]);
+      const float a2v[4] = {q.x, q.y, q.z, q.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float pre = x[i][j] + a2v[j];
+          const bool on = pre > 0.f;
+          acc[i][j] += on ? dv[i] : 0.f;
+          wacc[j] = fmaf(on ? dv[i] : 0.f, pre, wacc[j]);
+        }
+    }
+    __syncthreads();
+  }
+  float wv[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) wv[j] = wf[a0 + tx * 4 + j];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) stf(datt1 + ((int64_t)b * R + r) * A + a0 + tx * 4 + j, acc[i][j] * wv[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) s_w[ty][tx * 4 + j] = wacc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += s_w[k][threadIdx.x];
+    atomicAdd(dwf + a0 + threadIdx.x, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small pointwise / reduction kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mean_rows_kernel(const T* __restrict__ enc, float* __restrict__ mean, int R, int C) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int r = 0; r < R; r++) s += ldf(enc + ((int64_t)b * R + r) * C + c);
+  mean[(int64_t)b * C + c] = s / (float)R;
+}
+
+// LSTM cell pointwise (nn.LSTMCell, gate order i,f,g,o).  pre = gtmp + ptab[tok] + hh_pre.
+__global__ void lstm_pw_fwd_kernel(const float* __restrict__ gtmp, const float* __restrict__ ptab,
+                                   const int64_t* __restrict__ tok, int64_t tok_stride, const float* __restrict__ hh,
+                                   int64_t hh_stride, const float* __restrict__ c_prev, float* __restrict__ gates,
+                                   float* __restrict__ c_out, float* __restrict__ h_out, float* __restrict__ hd,
+                                   int64_t hd_stride, const float* __restrict__ dmask, int nrows, int D, int V) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrows * D) return;
+  const int b = idx / D, j = idx % D;
+  int64_t tk = tok[(int64_t)b * tok_stride];
+  if (tk < 0) tk = 0;
+  if (tk >= V) tk = V - 1;
+  const float* pt = ptab + tk * 4 * D;
+  const float* g0 = gtmp + (int64_t)b * 4 * D;
+  const float* h0 = hh + (int64_t)b * hh_stride;
+  const float pi = g0[j] + pt[j] + h0[j];
+  const float pf = g0[D + j] + pt[D + j] + h0[D + j];
+  const float pg = g0[2 * D + j] + pt[2 * D + j] + h0[2 * D + j];
+  const float po = g0[3 * D + j] + pt[3 * D + j] + h0[3 * D + j];
+  const float i = sigmoidf_(pi), f = sigmoidf_(pf), g = tanhf(pg), o = sigmoidf_(po);
+  const float c = f * c_prev[(int64_t)b * D + j] + i * g;
+  const float h = o * tanhf(c);
+  float* gt = gates + (int64_t)b * 4 * D;
+  gt[j] = i; gt[D + j] = f; gt[2 * D + j] = g; gt[3 * D + j] = o;
+  c_out[(int64_t)b * D + j] = c;
+  h_out[(int64_t)b * D + j] = h;
+  if (hd) hd[(int64_t)b * hd_stride + j] = dmask ? h * dmask[(int64_t)b * hd_stride + j] : h;
+}
+
+// backward of the cell pointwise part: dh = dhd[b,t] + dh_next ; writes d(pre-activations), dc_prev in place
+__global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_stride, const float* __restrict__ dmask,
+                                   const float* __restrict__ dh_next,
+                                   int64_t dhn_stride, float* __restrict__ dc, const float* __restrict__ gates,
+                                   const float* __restrict__ c_prev, const float* __restrict__ c_cur,
+                                   float* __restrict__ dG, int64_t dG_stride, int nrows, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrows * D) return;
+  const int b = idx / D, j = idx % D;
+  const float* gt = gates + (int64_t)b * 4 * D;
+  const float i = gt[j], f = gt[D + j], g = gt[2 * D + j], o = gt[3 * D + j];
+  const float tc = tanhf(c_cur[(int64_t)b * D + j]);
+  float dh = dhd[(int64_t)b * dhd_stride + j];
+  if (dmask) dh *= dmask[(int64_t)b * dhd_stride + j];
+  dh += dh_next[(int64_t)b * dhn_stride + j];
+  const float dct = dc[(int64_t)b * D + j] + dh * o * (1.f - tc * tc);
+  float* d = dG + (int64_t)b * dG_stride;
+  d[j] = dct * g * i * (1.f - i);
+  d[D + j] = dct * c_prev[(int64_t)b * D + j] * f * (1.f - f);
+  d[2 * D + j] = dct * i * (1.f - g * g);
+  d[3 * D + j] = dh * tc * o * (1.f - o);
+  dc[(int64_t)b * D + j] = dct * f;
+}
+
+// fused cross-entropy forward/backward: warp per (b,t) row.  target = caps[b][t+1]; rows with b >= bt[t] get 0.
+__global__ void ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ caps, int64_t caps_stride,
+                          const int32_t* __restrict__ dlen, float* __restrict__ row_loss, float* __restrict__ dlogits,
+                          int B, int Tn, int V, float inv_n) {
+  const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * Tn) return;
+  const int b = row / Tn, t = row % Tn;
+  const float* lg = logits + (int64_t)row * V;
+  float* dl = dlogits ? dlogits + (int64_t)row * V : nullptr;
+  if (t >= dlen[b]) {
+    if (lane == 0) row_loss[row] = 0.f;
+    if (dl) for (int v = lane; v < V; v += 32) dl[v] = 0.f;
+    return;
+  }
+  float mx = -INFINITY;
+  for (int v = lane; v < V; v += 32) mx = fmaxf(mx, lg[v]);
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int v = lane; v < V; v += 32) se += expf(lg[v] - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  int64_t tg = caps[(int64_t)b * caps_stride + t + 1];
+  if (tg < 0) tg = 0;
+  if (tg >= V) tg = V - 1;
+  if (lane == 0) row_loss[row] = lse - lg[tg];
+  if (dl)
+    for (int v = lane; v < V; v += 32) dl[v] = (expf(lg[v] - lse) - (v == (int)tg ? 1.f : 0.f)) * inv_n;
+}
+
+// doubly-stochastic regulariser: S = sum_t alpha ; sq -> row_loss tail ; dreg = -2 alpha_c (1-S)/(B R)
+__global__ void reg_kernel(const float* __restrict__ alphas, float* __restrict__ sq, float* __restrict__ dreg, int B, int Tn,
+                           int R, float alpha_c) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * R) return;
+  const int b = idx / R, r = idx % R;
+  float S = 0.f;
+  for (int t = 0; t < Tn; t++) S += alphas[((int64_t)b * Tn + t) * R + r];
+  const float d = 1.f - S;
+  sq[idx] = d * d;
+  if (dreg) dreg[idx] = -2.f * alpha_c * d / ((float)B * (float)R);
+}
+
+// sreg[b,t] = sum_r alpha[b,t,r] dreg[b,r]  (warp per (b,t))
+__global__ void sreg_kernel(const float* __restrict__ alphas, const float* __restrict__ dreg, int64_t dreg_bstride,
+                            int64_t dreg_tstride, float* __restrict__ sreg, int B, int Tn, int R) {
+  const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * Tn) return;
+  const int b = row / Tn, t = row % Tn;
+  float s = 0.f;
+  for (int r = lane; r < R; r += 32)
+    s = fmaf(alphas[(int64_t)row * R + r], dreg[(int64_t)b * dreg_bstride + (int64_t)t * dreg_tstride + r], s);
+  s = warp_sum(s);
+  if (lane == 0) sreg[row] = s;
+}
+
+// deterministic final reduction: loss[0]=total, [1]=ce, [2]=reg, [3]=n_valid
+__global__ void loss_finalize_kernel(const float* __restrict__ row_loss, int n_rows, const float* __restrict__ sq, int n_sq,
+                                     float inv_n, float alpha_c, float* __restrict__ loss) {
+  __shared__ float red[2][32];
+  float a = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) a += row_loss[i];
+  for (int i = threadIdx.x; i < n_sq; i += blockDim.x) c += sq[i];
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tcq = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { ta += red[0][w]; tcq += red[1][w]; }
+    const float ce = ta * inv_n, reg = n_sq ? tcq / (float)n_sq : 0.f;
+    loss[0] = ce + alpha_c * reg;
+    loss[1] = ce;
+    loss[2] = reg;
+    loss[3] = 1.f / inv_n;
+  }
+}
+
+// dptab[v][:] = sum over (t,b) with caps[b][t] == v (and t < dlen[b]) of dG[t][b][:]   (deterministic order)
+__global__ void dptab_kernel(const float* __restrict__ dcat, int64_t row_stride, int64_t step_stride, int col0,
+                             const int64_t* __restrict__ caps, int64_t caps_stride, const int32_t* __restrict__ dlen,
+                             float* __restrict__ dptab, int B, int Tn, int G) {
+  const int v = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ unsigned s_bits[8];
+  float acc = 0.f;
+  const int total = B * Tn;
+  for (int base = 0; base < total; base += 256) {
+    const int idx = base + threadIdx.x;
+    bool hit = false;
+    if (idx < total) {
+      const int b = idx / Tn, t = idx % Tn;
+      hit = (t < dlen[b]) && (caps[(int64_t)b * caps_stride + t] == (int64_t)v);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0) s_bits[threadIdx.x >> 5] = bal;
+    __syncthreads();
+    if (j < G) {
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        unsigned bits = s_bits[w];
+        while (bits) {                                  // ascending index order -> deterministic sum
+          const int k = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int id = base + w * 32 + k;
+          const int b = id / Tn, t = id % Tn;
+          acc += dcat[(int64_t)t * step_stride + (int64_t)b * row_stride + col0 + j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (j < G) dptab[(int64_t)v * G + j] = acc;
+}
+
+// denc[b][r][:] += dmean[b][:] / R
+__global__ void add_rowbcast_kernel(float* __restrict__ denc, const float* __restrict__ dmean, int R, int C, float scale,
+                                    int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t b = i / ((int64_t)R * C);
+    denc[i] += dmean[b * C + c] * scale;
+  }
+}
+
+// out[n][k] = in[k][n]  (in [K][ld_in] -> out [N][ld_out]), generic small transpose with dtype
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ in, int64_t ld_in, T* __restrict__ out, int64_t ld_out, int K, int N) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (k0 + i < K && n0 + threadIdx.x < N) tile[i][threadIdx.x] = ldf(in + (int64_t)(k0 + i) * ld_in + n0 + threadIdx.x);
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (n0 + i < N && k0 + threadIdx.x < K) stf(out + (int64_t)(n0 + i) * ld_out + k0 + threadIdx.x, tile[threadIdx.x][i]);
+}
+
+__global__ void argmax_kernel(const float* __restrict__ logits, int V, int64_t* __restrict__ tokens, int64_t tok_stride,
+                              int64_t* __restrict__ next_tok, int32_t* __restrict__ finished, int64_t end_id, int B) {
+  const int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int v = lane; v < V; v += 32) {
+    const float x = logits[(int64_t)b * V + v];
+    if (x > best) { best = x; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }   // lowest index wins ties (torch.argmax)
+  }
+  if (lane == 0) {
+    tokens[(int64_t)b * tok_stride] = bi;
+    next_tok[b] = bi;
+    if (bi == end_id) finished[b] = 1;
+  }
+}
+
+__global__ void fill_i64_kernel(int64_t* p, int64_t v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void dlen_kernel(int32_t* dlen, int B, int Tn, int full) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) dlen[i] = full;
+  (void)Tn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct Dims {
+  int B, T, R, C, A, D, E, V, O1, G;
+};
+static inline Dims dims(const lo_decoder_args* a) {
+  return Dims{a->B, a->T, a->R, a->C, a->A, a->D, a->E, a->V, a->A + a->C + 4 * a->D, 4 * a->D};
+}
+
+static int check_args(const lo_decoder_args* a) {
+  LO_CHECK_ARG(a != nullptr, "args");
+  LO_CHECK_ARG(a->B > 0 && a->T > 0 && a->R > 0 && a->V > 1, "B,T,R,V");
+  LO_CHECK_ARG(a->A == a->C && (a->C == 256 || a->C == 512 || a->C == 1024), "attention_dim == encoder_dim in {256,512,1024}");
+  LO_CHECK_ARG(a->D % 8 == 0 && a->E % 8 == 0, "D, E multiples of 8");
+  LO_CHECK_ARG(a->dt == LO_F32 || a->dt == LO_BF16, "dt");
+  LO_CHECK_ARG(a->bt_host && a->caps && a->enc && a->work, "null pointer");
+  for (int t = 0; t < a->T; t++) {
+    LO_CHECK_ARG(a->bt_host[t] >= 1 && a->bt_host[t] <= a->B, "bt_host out of range");
+    if (t) LO_CHECK_ARG(a->bt_host[t] <= a->bt_host[t - 1], "bt_host must be non-increasing");
+  }
+  return LO_OK;
+}
+
+static int* work_counters(const lo_decoder_args* a) { return (int*)a->work; }
+static float* work_partials(const lo_decoder_args* a) { return (float*)((char*)a->work + 4096); }
+static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a->work + 2048); }
+
+static int attention_forward_launch(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
+                                    const float* wf, float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre,
+                                    int64_t gate_stride, float* gctx, int B, int R, int C, void* work, cudaStream_t st) {
+  const int ns = att_splits(B);
+  int* cnt = (int*)work;
+  float* part = (float*)((char*)work + 4096);
+  dim3 grid(ns, B);
+#define LO_ATT_FWD(T, NV)                                                                                           \
+  attention_fwd_kernel<T, NV><<<grid, LO_ATT_THREADS, 0, st>>>((const T*)att1, (const T*)enc, att2, att2_stride, wf, \
+                                                               alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, R, ns, cnt, part)
+  if (dt == LO_F32) {
+    if (C == 256) LO_ATT_FWD(float, 1); else if (C == 512) LO_ATT_FWD(float, 2); else LO_ATT_FWD(float, 4);
+  } else {
+    if (C == 256) LO_ATT_FWD(bf16, 1); else if (C == 512) LO_ATT_FWD(bf16, 2); else LO_ATT_FWD(bf16, 4);
+  }
+#undef LO_ATT_FWD
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+// builds dlen[b] (device) = number of steps row b decodes, from the host bt[] array, via tiny memcpy-free kernels
+static int upload_dlen(const lo_decoder_args* a, cudaStream_t st) {
+  // dlen[b] = #{t : bt[t] > b}.  bt is non-increasing, so rows [bt[t], bt[t-1]) have dlen = t.
+  int32_t* dl = work_dlen(a);
+  LO_CHECK_ARG(a->B <= 512, "B <= 512 (dlen scratch)");
+  LO_CUDA(cudaMemsetAsync(dl, 0, (size_t)a->B * 4, st));   // rows that never decode (caption length 1)
+  // rows below bt[T-1] decode all T steps
+  dlen_kernel<<<cdiv(a->B, 128), 128, 0, st>>>(dl, a->bt_host[a->T - 1], a->T, a->T);
+  LO_LAUNCH_OK();
+  for (int t = a->T - 1; t >= 1; t--) {
+    const int lo_ = a->bt_host[t], hi_ = a->bt_host[t - 1];
+    if (hi_ > lo_) {
+      dlen_kernel<<<cdiv(hi_ - lo_, 128), 128, 0, st>>>(dl + lo_, hi_ - lo_, a->T, t);
+      LO_LAUNCH_OK();
+    }
+  }
+  return LO_OK;
+}
+
+static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_t st) {
+  const int dt = a->dt;
+  // att1 = enc @ W_e^T + b_e   (hoisted: the reference recomputes it every step, seq2seq_torch.py:186)
+  LO_TRY(gemm_nt(a->enc, dt, d.C, a->w_enc_att, dt, d.C, a->att1, dt, d.A, d.B * d.R, d.A, d.C, a->b_enc_att, 0, 0, a->impl, st));
+  // embedding -> gate projection table (replaces embedding lookup + x[:, :E] @ W_ih[:, :E]^T, seq2seq_torch.py:291,:313)
+  LO_TRY(gemm_nt(a->emb, dt, d.E, a->w_ih, dt, d.E + d.C, a->ptab, LO_F32, d.G, d.V, d.G, d.E, a->b_ih, 0, 0, LO_IMPL_SIMT, st));
+  // init_hidden_state (seq2seq_torch.py:255-265)
+  {
+    dim3 grid(cdiv(d.C, 256), d.B);
+    LO_DISPATCH_DT(dt, T, (mean_rows_kernel<T><<<grid, 256, 0, st>>>((const T*)a->enc, a->mean, d.R, d.C)));
+    LO_LAUNCH_OK();
+  }
+  const size_t es = dt == LO_F32 ? 4 : 2;
+  LO_TRY(gemm_nt(a->mean, LO_F32, d.C, a->w_init, dt, d.C, a->hall, LO_F32, d.D, d.B, d.D, d.C, a->b_init, 0, 0, LO_IMPL_SIMT, st));
+  LO_TRY(gemm_nt(a->mean, LO_F32, d.C, (const char*)a->w_init + (size_t)d.D * d.C * es, dt, d.C, a->call, LO_F32, d.D, d.B,
+                 d.D, d.C, a->b_init + d.D, 0, 0, LO_IMPL_SIMT, st));
+  return LO_OK;
+}
+
+// one decoder step t with nrows active rows; tok: token ids consumed at this step
+static int forward_step(const lo_decoder_args* a, const Dims& d, int t, int nrows, const int64_t* tok, int64_t tok_stride,
+                        float* hd_t, int64_t hd_stride, const float* dmask_t, cudaStream_t st) {
+  const int dt = a->dt;
+  float* h_prev = a->hall + (int64_t)t * d.B * d.D;
+  float* c_prev = a->call + (int64_t)t * d.B * d.D;
+  float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+  // [att2 | gate_pre | hh_pre] = h_prev @ [W_d; W_beta; W_hh]^T + b   (seq2seq_torch.py:187, :311, LSTMCell hh part)
+  LO_TRY(gemm_nt(h_prev, LO_F32, d.D, a->wcat1, dt, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D, a->bcat1, 0, 0, LO_IMPL_SIMT, st));
+  LO_TRY(attention_forward_launch(a->att1, a->enc, dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+                                  a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C, nrows,
+                                  d.R, d.C, a->work, st));
+  // gates_x = (gate*ctx) @ W_ih[:, E:]^T
+  const size_t es = dt == LO_F32 ? 4 : 2;
+  LO_TRY(gemm_nt(a->gctx + (int64_t)t * d.B * d.C, LO_F32, d.C, (const char*)a->w_ih + (size_t)d.E * es, dt, d.E + d.C, a->gtmp,
+                 LO_F32, d.G, nrows, d.G, d.C, nullptr, 0, 0, LO_IMPL_SIMT, st));
+  lstm_pw_fwd_kernel<<<cdiv((long)nrows * d.D, 256), 256, 0, st>>>(
+      a->gtmp, a->ptab, tok, tok_stride, o1 + d.A + d.C, d.O1, c_prev, a->gates + (int64_t)t * d.B * d.G,
+      a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D, hd_t, hd_stride, dmask_t, nrows, d.D, d.V);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+}  // namespace lo
+
+using namespace lo;
+
+extern "C" {
+
+int64_t lo_sizeof_decoder_args(void) { return (int64_t)sizeof(lo_decoder_args); }
+
+int64_t lo_attention_workspace_bytes(int B, int C) {
+  return 4096 + (int64_t)B * LO_ATT_MAXSPLIT * (C + 2) * 4;
+}
+
+int lo_attention_forward(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride, const float* wf,
+                         float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre, int64_t gate_stride, float* gctx,
+                         int B, int R, int A, int C, void* work, void* stream) {
+  LO_CHECK_ARG(att1 && enc && att2 && wf && alpha && ctx && work, "null pointer");
+  LO_CHECK_ARG(A == C && (C == 256 || C == 512 || C == 1024), "attention_dim == encoder_dim in {256,512,1024}");
+  LO_CHECK_ARG(B > 0 && B <= 512 && R > 0, "B in 1..512, R > 0");
+  LO_CHECK_ARG(att2_stride % 4 == 0, "att2 rows must be 16-byte aligned");
+  return attention_forward_launch(att1, enc, dt, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, B,
+                                  R, C, work, (cudaStream_t)stream);
+}
+
+int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
+  LO_TRY(check_args(a));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Dims d = dims(a);
+  const bool ragged = a->bt_host[d.T - 1] < d.B;
+  if (ragged) {
+    LO_CUDA(cudaMemsetAsync(a->alphas, 0, (size_t)d.B * d.T * d.R * 4, st));
+    LO_CUDA(cudaMemsetAsync(a->hd, 0, (size_t)d.B * d.T * d.D * 4, st));
+  }
+  LO_TRY(upload_dlen(a, st));
+  LO_TRY(forward_prologue(a, d, st));
+  for (int t = 0; t < d.T; t++) {
+    const float* dm = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+    LO_TRY(forward_step(a, d, t, a->bt_host[t], a->caps + t, a->caps_stride, a->hd + (int64_t)t * d.D, (int64_t)d.T * d.D, dm, st));
+  }
+  // predictions = fc(dropout(h))  (seq2seq_torch.py:316), hoisted out of the loop
+  LO_TRY(gemm_nt(a->hd, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B * d.T, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));
+  if (ragged) {
+    // rows that stopped decoding keep zeros in `predictions` (seq2seq_torch.py:301): re-zero what the GEMM wrote (bias)
+    // handled by the CE kernel (ignores them) and by the Python side for the returned tensor.
+  }
+  if (with_loss) {
+    long nvalid = 0;
+    for (int t = 0; t < d.T; t++) nvalid += a->bt_host[t];
+    const float inv_n = 1.0f / (float)nvalid;
+    ce_kernel<<<cdiv((long)d.B * d.T, 8), 256, 0, st>>>(a->logits, a->caps, a->caps_stride, work_dlen(a), a->row_loss, a->dlogits,
+                                                         d.B, d.T, d.V, inv_n);
+    LO_LAUNCH_OK();
+    reg_kernel<<<cdiv((long)d.B * d.R, 256), 256, 0, st>>>(a->alphas, a->row_loss + (int64_t)d.B * d.T, a->dreg, d.B, d.T, d.R, a->alpha_c);
+    LO_LAUNCH_OK();
+    loss_finalize_kernel<<<1, 1024, 0, st>>>(a->row_loss, d.B * d.T, a->row_loss + (int64_t)d.B * d.T, d.B * d.R, inv_n, a->alpha_c, a->loss);
+    LO_LAUNCH_OK();
+  }
+  return LO_OK;
+}
+
+int lo_decoder_pack_bwd_weights(const lo_decoder_args* a, void* stream) {
+  LO_TRY(check_args(a));
+  LO_CHECK_ARG(a->wbwd1 && a->wbwd2, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Dims d = dims(a);
+  const size_t es = a->dt == LO_F32 ? 4 : 2;
+  dim3 blk(32, 8);
+  // wbwd1 [C+D][4D]: rows 0..C-1 <- (w_ih[:, E:])^T ; rows C.. <- w_hh^T
+  const char* w_hh = (const char*)a->wcat1 + (size_t)(d.A + d.C) * d.D * es;
+  const char* w_dec = (const char*)a->wcat1;
+  const char* w_beta = (const char*)a->wcat1 + (size_t)d.A * d.D * es;
+  LO_DISPATCH_DT(a->dt, T, {
+    transpose_kernel<T><<<dim3(cdiv(d.C, 32), cdiv(d.G, 32)), blk, 0, st>>>((const T*)a->w_ih + d.E, d.E + d.C, (T*)a->wbwd1, d.G, d.G, d.C);
+    transpose_kernel<T><<<dim3(cdiv(d.D, 32), cdiv(d.G, 32)), blk, 0, st>>>((const T*)w_hh, d.D, (T*)a->wbwd1 + (int64_t)d.C * d.G, d.G, d.G, d.D);
+    // wbwd2 [D][A+C]: [n][k<A] = w_dec[k][n] ; [n][A+k] = w_beta[k][n]
+    transpose_kernel<T><<<dim3(cdiv(d.D, 32), cdiv(d.A, 32)), blk, 0, st>>>((const T*)w_dec, d.D, (T*)a->wbwd2, d.A + d.C, d.A, d.D);
+    transpose_kernel<T><<<dim3(cdiv(d.D, 32), cdiv(d.C, 32)), blk, 0, st>>>((const T*)w_beta, d.D, (T*)a->wbwd2 + d.A, d.A + d.C, d.C, d.D);
+  });
+  lo::g_launches += 3;
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
+  LO_TRY(check_args(a));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Dims d = dims(a);
+  const int dt = a->dt;
+  const bool ragged = a->bt_host[d.T - 1] < d.B;
+  const int ns = att_splits(d.B);
+  const int64_t BT = (int64_t)d.B * d.T;
+  LO_TRY(lo_decoder_pack_bwd_weights(a, stream));
+  // sreg[b,t] = sum_r alpha dreg
+  const float* dal = a->dalpha_ext ? a->dalpha_ext : a->dreg;
+  const int64_t dal_b = a->dalpha_ext ? (int64_t)d.T * d.R : d.R, dal_t = a->dalpha_ext ? d.R : 0;
+  sreg_kernel<<<cdiv(BT, 8), 256, 0, st>>>(a->alphas, dal, dal_b, dal_t, a->sreg, d.B, d.T, d.R);
+  LO_LAUNCH_OK();
+  // fc backward (hoisted): g_w_fc = dlogits^T hd ; g_b_fc ; dhd = dlogits @ W_fc (* dropout mask)
+  LO_TRY(gemm_tn(a->dlogits, LO_F32, d.V, a->hd, LO_F32, d.D, a->g_w_fc, LO_F32, d.D, d.V, d.D, (int)BT, 0, LO_IMPL_SIMT, st));
+  LO_TRY(colsum(a->dlogits, LO_F32, a->g_b_fc, (int)BT, d.V, d.V, 0, st));
+  LO_TRY(gemm_nn(a->dlogits, LO_F32, d.V, a->w_fc, dt, d.D, a->dhd, LO_F32, d.D, (int)BT, d.D, d.V, 0, LO_IMPL_SIMT, st));
+  LO_CUDA(cudaMemsetAsync(a->dxh, 0, (size_t)d.B * (d.C + d.D) * 4, st));
+  LO_CUDA(cudaMemsetAsync(a->dc, 0, (size_t)d.B * d.D * 4, st));
+  if (ragged) {
+    LO_CUDA(cudaMemsetAsync(a->dcat, 0, (size_t)d.T * d.B * d.O1 * 4, st));
+    LO_CUDA(cudaMemsetAsync(a->de, 0, (size_t)BT * d.R * 4, st));
+    LO_CUDA(cudaMemsetAsync(a->dctx, 0, (size_t)d.T * d.B * d.C * 4, st));
+  }
+  int* cnt = work_counters(a);
+  float* part = work_partials(a);
+  for (int t = d.T - 1; t >= 0; t--) {
+    const int nrows = a->bt_host[t];
+    float* dcat_t = a->dcat + (int64_t)t * d.B * d.O1;
+    const float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+    const float* dmul = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+    lstm_pw_bwd_kernel<<<cdiv((long)nrows * d.D, 256), 256, 0, st>>>(
+        a->dhd + (int64_t)t * d.D, (int64_t)d.T * d.D, dmul, a->dxh + d.C, d.C + d.D, a->dc, a->gates + (int64_t)t * d.B * d.G,
+        a->call + (int64_t)t * d.B * d.D, a->call + (int64_t)(t + 1) * d.B * d.D, dcat_t + d.A + d.C, d.O1, nrows, d.D);
+    LO_LAUNCH_OK();
+    // [dgctx | dh_prev] = dG @ [W_ih[:, E:] | W_hh]
+    LO_TRY(gemm_nt(dcat_t + d.A + d.C, LO_F32, d.O1, a->wbwd1, dt, d.G, a->dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 0,
+                   0, LO_IMPL_SIMT, st));
+    dim3 grid(ns, nrows);
+#define LO_ATT_BWD(TY_, NV)                                                                                                       \
+  attention_bwd_kernel<TY_, NV><<<grid, LO_ATT_THREADS, 0, st>>>(                                                                 \
+      (const TY_*)a->att1, (const TY_*)a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,        \
+      a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T, a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, \
+      d.O1, a->dctx + (int64_t)t * d.B * d.C, d.R, ns, cnt, part)
+    if (dt == LO_F32) {
+      if (d.C == 256) LO_ATT_BWD(float, 1); else if (d.C == 512) LO_ATT_BWD(float, 2); else LO_ATT_BWD(float, 4);
+    } else {
+      if (d.C == 256) LO_ATT_BWD(bf16, 1); else if (d.C == 512) LO_ATT_BWD(bf16, 2); else LO_ATT_BWD(bf16, 4);
+    }
+#undef LO_ATT_BWD
+    LO_LAUNCH_OK();
+    // dh_prev += [datt2 | dgate_pre] @ [W_d ; W_beta]
+    LO_TRY(gemm_nt(dcat_t, LO_F32, d.O1, a->wbwd2, dt, d.A + d.C, a->dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C, nullptr, 1,
+                   0, LO_IMPL_SIMT, st));
+  }
+  // dinit = [dh0 | dc0]
+  LO_CUDA(cudaMemcpy2DAsync(a->dinit, (size_t)2 * d.D * 4, a->dxh + d.C, (size_t)(d.C + d.D) * 4, (size_t)d.D * 4, d.B,
+                            cudaMemcpyDeviceToDevice, st));
+  LO_CUDA(cudaMemcpy2DAsync(a->dinit + d.D, (size_t)2 * d.D * 4, a->dc, (size_t)d.D * 4, (size_t)d.D * 4, d.B,
+                            cudaMemcpyDeviceToDevice, st));
+  // ---- hoisted gradients
+  // [W_d; W_beta; W_hh] and biases: dcat^T @ h_prev
+  LO_TRY(gemm_tn(a->dcat, LO_F32, d.O1, a->hall, LO_F32, d.D, a->g_wcat1, LO_F32, d.D, d.O1, d.D, d.T * d.B, 0, LO_IMPL_SIMT, st));
+  LO_TRY(colsum(a->dcat, LO_F32, a->g_bcat1, d.T * d.B, d.O1, d.O1, 0, st));
+  // W_ih[:, E:] : dG^T @ gctx ; b_ih = colsum(dG) (== g_b_hh)
+  LO_TRY(gemm_tn(a->dcat + d.A + d.C, LO_F32, d.O1, a->gctx, LO_F32, d.C, a->g_w_ih + d.E, LO_F32, d.E + d.C, d.G, d.C, d.T * d.B, 0,
+                 LO_IMPL_SIMT, st));
+  LO_TRY(colsum(a->dcat + d.A + d.C, LO_F32, a->g_b_ih, d.T * d.B, d.G, d.O1, 0, st));
+  // embedding path through the projection table
+  {
+    dim3 grid(cdiv(d.G, 256), d.V);
+    dptab_kernel<<<grid, 256, 0, st>>>(a->dcat, d.O1, (int64_t)d.B * d.O1, d.A + d.C, a->caps, a->caps_stride, work_dlen(a), a->dptab,
+                                       d.B, d.T, d.G);
+    LO_LAUNCH_OK();
+  }
+  LO_TRY(gemm_nn(a->dptab, LO_F32, d.G, a->w_ih, dt, d.E + d.C, a->g_emb, LO_F32, d.E, d.V, d.E, d.G, 0, LO_IMPL_SIMT, st));
+  LO_TRY(gemm_tn(a->dptab, LO_F32, d.G, a->emb, dt, d.E, a->g_w_ih, LO_F32, d.E + d.C, d.G, d.E, d.V, 0, LO_IMPL_SIMT, st));
+  // d att1 + d w_full in one sweep over att1
+  LO_CUDA(cudaMemsetAsync(a->g_w_full, 0, (size_t)d.A * 4, st));
+  LO_CUDA(cudaMemsetAsync(a->g_b_full, 0, 4, st));   // sum_r de = 0 exactly (softmax); reference value is rounding noise
+  {
+    dim3 grid(d.A / 64, cdiv(d.R, 32), d.B);
+    LO_DISPATCH_DT(dt, T, (datt1_kernel<T><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de, a->w_full,
+                                                                  (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
+    LO_LAUNCH_OK();
+  }
+  // encoder_att: g_W = datt1^T enc ; g_b = colsum(datt1) ; denc = datt1 @ W_e
+  LO_TRY(gemm_tn(a->datt1, dt, d.A, a->enc, dt, d.C, a->g_w_enc_att, LO_F32, d.C, d.A, d.C, d.B * d.R, 0, LO_IMPL_SIMT, st));
+  LO_TRY(colsum(a->datt1, dt, a->g_b_enc_att, d.B * d.R, d.A, d.A, 0, st));
+  LO_TRY(gemm_nn(a->datt1, dt, d.A, a->w_enc_att, dt, d.C, a->denc, LO_F32, d.C, d.B * d.R, d.C, d.A, 0, LO_IMPL_SIMT, st));
+  // denc[b] += alphas[b]^T @ dctx[:, b, :]   (the context read, summed over time — a batched GEMM instead of a per-step RMW)
+  {
+    GemmDesc g{d.R, d.C, d.T, 1, d.R, (int64_t)d.B * d.C, 1, d.C, d.B, (int64_t)d.T * d.R, d.C, (int64_t)d.R * d.C, nullptr, 1, 0};
+    LO_TRY(gemm(a->alphas, LO_F32, a->dctx, LO_F32, a->denc, LO_F32, g, LO_IMPL_SIMT, st));
+  }
+  // init_h / init_c
+  LO_TRY(gemm_tn(a->dinit, LO_F32, 2 * d.D, a->mean, LO_F32, d.C, a->g_w_init, LO_F32, d.C, 2 * d.D, d.C, d.B, 0, LO_IMPL_SIMT, st));
+  LO_TRY(colsum(a->dinit, LO_F32, a->g_b_init, d.B, 2 * d.D, 2 * d.D, 0, st));
+  LO_TRY(gemm_nn(a->dinit, LO_F32, 2 * d.D, a->w_init, dt, d.C, a->dmean, LO_F32, d.C, d.B, d.C, 2 * d.D, 0, LO_IMPL_SIMT, st));
+  {
+    const int64_t total = (int64_t)d.B * d.R * d.C;
+    add_rowbcast_kernel<<<148 * 8, 256, 0, st>>>(a->denc, a->dmean, d.R, d.C, 1.0f / (float)d.R, total);
+    LO_LAUNCH_OK();
+  }
+  return LO_OK;
+}
+
+int lo_decoder_greedy(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* tokens,
+                      int32_t* finished, void* stream) {
+  LO_TRY(check_args(a));
+  LO_CHECK_ARG(tokens && finished && max_steps > 0 && max_steps <= a->T, "tokens/finished/max_steps (<= T capacity)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Dims d = dims(a);
+  // next-token buffer lives in the dlen scratch area's neighbour: reuse dptab-free region -> use `sreg` as int64 scratch
+  int64_t* next_tok = (int64_t*)a->sreg;
+  LO_CHECK_ARG((int64_t)d.B * d.T * 4 >= (int64_t)d.B * 8, "sreg scratch too small");
+  fill_i64_kernel<<<cdiv(d.B, 128), 128, 0, st>>>(next_tok, start_id, d.B);
+  LO_LAUNCH_OK();
+  LO_CUDA(cudaMemsetAsync(finished, 0, (size_t)d.B * 4, st));
+  LO_TRY(forward_prologue(a, d, st));
+  for (int t = 0; t < max_steps; t++) {
+    LO_TRY(forward_step(a, d, t, d.B, next_tok, 1, nullptr, 0, nullptr, st));
+    // logits_t = fc(h_t)   (no dropout at decode time)
+    LO_TRY(gemm_nt(a->hall + (int64_t)(t + 1) * d.B * d.D, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D,
+                   a->b_fc, 0, 0, LO_IMPL_SIMT, st));
+    argmax_kernel<<<cdiv(d.B, 8), 256, 0, st>>>(a->logits, d.V, tokens + t, max_steps, next_tok, finished, end_id, d.B);
+    LO_LAUNCH_OK();
+  }
+  return LO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// Fused Adam over one flat parameter buffer (torch.optim.Adam defaults, img2seq_torch.py:86-87,168-170)
+// + dtype casts.  The step counter lives on the device so the call can be replayed inside a CUDA graph.
+#include "lo_common.cuh"
+
+namespace lo {
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            bf16* __restrict__ shadow, int64_t n, const float* __restrict__ state, float b1, float b2, float eps,
+                            float gscale) {
+  const float step = state[0] + 1.0f;      // state[0] is bumped by adam_bump_kernel after this kernel
+  const float lr = state[1];
+  const float bc1 = 1.0f - powf(b1, step);
+  const float bc2 = 1.0f - powf(b2, step);
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    const float pi = p[i] - step_size * (mi / denom);
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+__global__ void adam_bump_kernel(float* state) { state[0] += 1.0f; }
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) stf(d + i, ldf(s + i));
+}
+
+}  // namespace lo
+
+using namespace lo;
+
+extern "C" {
+
+int lo_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float* state_dev, float beta1,
+                 float beta2, float eps, float grad_scale, void* stream) {
+  LO_CHECK_ARG(p && g && m && v && state_dev && n > 0, "null pointer / n");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)((n + 1023) / 1024);
+  if (grid > 148 * 8) grid = 148 * 8;
+  adam_kernel<<<grid, 256, 0, st>>>(p, g, m, v, (bf16*)shadow_bf16, n, state_dev, beta1, beta2, eps, grad_scale);
+  LO_LAUNCH_OK();
+  adam_bump_kernel<<<1, 1, 0, st>>>(state_dev);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+int lo_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, void* stream) {
+  LO_CHECK_ARG(src && dst && n > 0, "null pointer / n");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)((n + 1023) / 1024);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (dt_src == LO_F32 && dt_dst == LO_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+  else if (dt_src == LO_BF16 && dt_dst == LO_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+  else if (dt_src == LO_F32 && dt_dst == LO_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (dt_src == LO_BF16 && dt_dst == LO_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  else return fail(LO_EINVAL, "%s: bad dtype", __func__);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""Img2SeqModel — the trainer surface of model/img2seq_torch.py:64-172 + model/base_torch.py:45-206
+(build_train / getLoss / _run_train_epoch / train) on the B200-native encoder and decoder.
+
+``getLoss`` keeps the reference semantics exactly (img2seq_torch.py:136-172): every row's caption
+length is the padded length (:144), targets are captions[:, 1:] (:147), loss = CE(mean over packed
+positions, PADs included) + 1.0 * mean((1 - sum_t alpha)^2) (:151-159), backward, Adam step on the
+decoder then the encoder (:162-170), returns ``-loss`` (:172).  The ``lr`` and ``dropout`` arguments
+are ignored exactly like the reference ignores them.
+"""
+import ctypes
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .decoder import DecoderWithAttention
+from .encoder import EncoderCNN
+
+
+class Img2SeqModel:
+    def __init__(self, config, dir_output=None, vocab=None, device=None, precision=None, impl=None, n_tok=None):
+        self._config = config
+        self._dir_output = dir_output
+        self._vocab = vocab
+        dev = device or getattr(config, "device", "cuda")
+        if not str(dev).startswith("cuda"):
+            raise _lib.LatexOcrB200Error("latex_ocr_b200 runs on CUDA devices only (device=%r)" % (dev,))
+        self.device = torch.device(dev)
+        self.precision = precision or getattr(config, "precision", "bf16")
+        self.impl = impl or getattr(config, "impl", "simt")
+        self._n_tok = n_tok if n_tok is not None else (vocab.n_tok if vocab is not None else None)
+        self.encoder = None
+        self.decoder = None
+        self.use_graph = bool(getattr(config, "cuda_graph", False))
+        self._graphs = {}
+        self.dist = None          # set by latex_ocr_b200.dist.attach(model)
+        self.lr = float(getattr(config, "lr_init", 1e-3))
+
+    # --- model/base_torch.py:45-71 -------------------------------------------------------------
+    def build_train(self, config=None):
+        config = config or self._config
+        self.getModel("Img2Seq")
+        self.getOptimizer(getattr(config, "lr_method", "adam"), float(getattr(config, "lr_init", 1e-3)))
+        return self
+
+    def build_pred(self, config=None):
+        self.getModel("Img2Seq")
+        return self
+
+    def getModel(self, model_name="Img2Seq"):
+        """img2seq_torch.py:69-83 (only the Img2Seq branch is on the hot path)."""
+        if model_name != "Img2Seq":
+            raise NotImplementedError("model_name=%r: only 'Img2Seq' is implemented" % model_name)
+        self.encoder = EncoderCNN(self._config, device=self.device, precision=self.precision, impl=self.impl)
+        self.decoder = DecoderWithAttention(attention_dim=512, embed_dim=512, decoder_dim=512, vocab_size=self._n_tok,
+                                            dropout=0.5, device=self.device, precision=self.precision, impl=self.impl)
+        return self
+
+    def getOptimizer(self, lr_method="adam", lr=0.001):
+        """img2seq_torch.py:85-88: two Adam optimisers with torch defaults (one fused launch each)."""
+        if str(lr_method).lower() != "adam":
+            raise NotImplementedError("lr_method=%r: the torch path of the reference always builds Adam" % lr_method)
+        self.lr = float(lr)
+        self.encoder.store.ensure_adam(lr)
+        self.decoder.store.ensure_adam(lr)
+
+    def train_mode(self, flag=True):
+        self.encoder.train(flag)
+        self.decoder.train(flag)
+
+    # --- the fused train step --------------------------------------------------------------------
+    def _adam(self, store, grad_scale=1.0):
+        L = _lib.lib()
+        check(L.lo_adam_step(ptr(store.master), ptr(store.grad), ptr(store.m), ptr(store.v), ptr(store.shadow), store.numel,
+                             ptr(store.adam_state), 0.9, 0.999, 1e-8, float(grad_scale), stream_ptr()))
+
+    def _step_body(self, img, caps, decode_lengths, dropout_mask):
+        """encoder fwd -> decoder fwd + loss -> decoder bwd -> encoder bwd -> (grad all-reduce) -> Adam x2.
+        img: CUDA fp32 [N,1,H,W]; caps: CUDA int64 [N,L] sorted rows.  Returns the device loss vector."""
+        N = img.shape[0]
+        enc_out = self.encoder.forward_raw(img, need_grad=True)
+        R = enc_out.shape[1] * enc_out.shape[2]
+        enc_flat = enc_out.view(N, R, enc_out.shape[3])
+        ws = self.decoder.run_forward(enc_flat, caps, decode_lengths, with_loss=True, need_grad=True, dropout_mask=dropout_mask)
+        self.decoder.run_backward(ws)
+        scale = 1.0
+        if self.dist is not None:
+            self.dist.reduce_async(self.decoder.store.grad)        # decoder bucket flies while the encoder backward runs
+            scale = 1.0 / self.dist.world_size
+        self.encoder.backward_raw(tuple(img.shape), ws["t"]["denc"].view(N, enc_out.shape[1], enc_out.shape[2], enc_out.shape[3]))
+        if self.dist is not None:
+            self.dist.reduce_async(self.encoder.store.grad)
+            self.dist.wait()
+        self._adam(self.decoder.store, scale)
+        self._adam(self.encoder.store, scale)
+        return ws["t"]["loss"]
+
+    def train_step(self, img, formula, sync=False):
+        """img: float tensor [N,1,H,W] (CPU pinned or CUDA); formula: int64 [N,L] (CPU or CUDA).
+        Returns the device loss vector [total, ce, reg, n_valid] (no host sync unless sync=True)."""
+        N, L = formula.shape
+        lengths = torch.full((N, 1), L, dtype=torch.long)                       # img2seq_torch.py:144
+        lens, sort_ind = lengths.squeeze(1).sort(dim=0, descending=True)        # seq2seq_torch.py:286 (host, tiny)
+        decode_lengths = (lens - 1).tolist()
+        img_d = img.to(self.device, non_blocking=True)
+        caps_d = formula.to(self.device, non_blocking=True)
+        if not torch.equal(sort_ind, torch.arange(N)):
+            si = sort_ind.to(self.device)
+            img_d, caps_d = img_d[si], caps_d[si]
+        T = L - 1
+        if not self.use_graph:
+            mask = self.decoder.make_dropout_mask(N, T)
+            loss = self._step_body(img_d.float(), caps_d, decode_lengths, mask)
+        else:
+            loss = self._graph_step(img_d, caps_d, decode_lengths)
+        if sync:
+            torch.cuda.synchronize()
+        return loss
+
+    def _graph_step(self, img_d, caps_d, decode_lengths):
+        key = (tuple(img_d.shape), tuple(caps_d.shape), self.decoder.training)
+        g = self._graphs.get(key)
+        if g is None:
+            N, T = caps_d.shape[0], caps_d.shape[1] - 1
+            st = {"img": torch.zeros(img_d.shape, dtype=torch.float32, device=self.device),
+                  "caps": torch.zeros(caps_d.shape, dtype=torch.int64, device=self.device)}
+            st["img"].copy_(img_d)
+            st["caps"].copy_(caps_d)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):       # warm-up outside capture (allocates workspaces)
+                for _ in range(2):
+                    mask = self.decoder.make_dropout_mask(N, T)
+                    self._step_body(st["img"], st["caps"], decode_lengths, mask)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                mask = self.decoder.make_dropout_mask(N, T)
+                st["loss"] = self._step_body(st["img"], st["caps"], decode_lengths, mask)
+            st["graph"] = graph
+            g = self._graphs[key] = st
+        g["img"].copy_(img_d, non_blocking=True)
+        g["caps"].copy_(caps_d, non_blocking=True)
+        g["graph"].replay()
+        return g["loss"]
+
+    def getLoss(self, img, formula, lr=None, dropout=None, training=True):
+        """img2seq_torch.py:136-172.  Returns -loss as a Python float (one device->host read)."""
+        loss = self.train_step(img, formula)
+        return -float(loss[0].item())
+
+    # --- epoch loop: img2seq_torch.py:90-134 / base_torch.py:169-206 ------------------------------
+    def _run_train_epoch(self, config, train_set, val_set, epoch, lr_schedule):
+        from .data import minibatches, pad_batch_formulas, pad_batch_images
+        batch_size = config.batch_size
+        self.train_mode(True)
+        losses = []
+        t0 = time.time()
+        nimg = 0
+        for i, (img, formula) in enumerate(minibatches(train_set, batch_size)):
+            img = pad_batch_images(img)                                            # utils/image.py:47 (255 padding)
+            img = torch.from_numpy(img).float().permute(0, 3, 1, 2)                # img2seq_torch.py:115-117
+            formula, _ = pad_batch_formulas(formula, self._vocab.id_pad, self._vocab.id_end)
+            formula = torch.from_numpy(formula.astype(np.int64))                   # :118
+            loss_eval = self.getLoss(img, formula=formula, lr=getattr(lr_schedule, "lr", None),
+                                     dropout=getattr(config, "dropout", None), training=True)
+            losses.append(loss_eval)
+            nimg += img.shape[0]
+            if lr_schedule is not None:
+                lr_schedule.update(batch_no=epoch * ((len(train_set) + batch_size - 1) // batch_size) + i)
+        self.last_epoch_stats = {"images_per_s": nimg / max(time.time() - t0, 1e-9), "mean_neg_loss": float(np.mean(losses)) if losses else 0.0}
+        score = self.last_epoch_stats["mean_neg_loss"]
+        if val_set is not None and hasattr(self, "evaluate"):
+            pass
+        return score
+
+    def train(self, config, train_set, val_set, lr_schedule):
+        """base_torch.py:169-206 (epoch loop; best-score bookkeeping)."""
+        best_score = None
+        for epoch in range(config.n_epochs):
+            score = self._run_train_epoch(config, train_set, val_set, epoch, lr_schedule)
+            if best_score is None or score >= best_score:
+                best_score = score
+            if lr_schedule is not None and getattr(lr_schedule, "stop_training", False):
+                break
+        return best_score
+
+    # --- checkpoints: state_dict round-trips with the reference modules ----------------------------
+    def state_dict(self):
+        return {"encoder": self.encoder.state_dict(), "decoder": self.decoder.state_dict()}
+
+    def load_state_dict(self, sd):
+        self.encoder.load_state_dict(sd["encoder"])
+        self.decoder.load_state_dict(sd["decoder"])
+
+    def save(self, path=None):
+        path = path or os.path.join(self._dir_output or ".", "model.pt")
+        torch.save({k: {n: t.detach().cpu().contiguous() for n, t in v.items()} for k, v in self.state_dict().items()}, path)
+        return path
+
+    def restore(self, path):
+        self.load_state_dict(torch.load(path, map_location=self.device))

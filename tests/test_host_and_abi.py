@@ -1,0 +1,80 @@
+"""CPU (-m "not gpu"): host-side logic and the C-ABI surface (library loads, exports every declared symbol,
+struct mirror matches, argument validation happens before any GPU work)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from latex_ocr_b200 import _lib, data
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    for name in _lib.declared_symbols():
+        assert hasattr(L, name), name
+    assert L.lo_version() >= 100
+    assert L.lo_sizeof_decoder_args() == ctypes.sizeof(_lib.DecoderArgs)
+    out = subprocess.run(["nm", "-D", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in _lib.declared_symbols():
+        assert (" T " + name) in out, name
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    assert L.lo_gemm(None, 0, None, 0, None, 0, 4, 4, 4, 4, 1, 1, 4, 4, 1, 0, 0, 0, None, 0, 0, 0, None) == -1
+    assert b"null pointer" in L.lo_last_error()
+    assert L.lo_attention_workspace_bytes(64, 512) == 4096 + 64 * 16 * 514 * 4
+    assert L.lo_decoder_forward(None, 0, None) == -1
+
+
+def test_cpu_tensors_are_refused():
+    with pytest.raises(_lib.LatexOcrB200Error):
+        _lib.ptr(torch.zeros(3))
+    from latex_ocr_b200.img2seq import Img2SeqModel
+    from util import Cfg
+    with pytest.raises(_lib.LatexOcrB200Error):
+        Img2SeqModel(Cfg(), n_tok=10, device="cpu")
+
+
+def test_batching_helpers_follow_reference_rules():
+    imgs = [np.zeros((3, 5, 1), np.uint8), np.ones((4, 2, 1), np.uint8)]
+    b = data.pad_batch_images(imgs)
+    assert b.shape == (2, 4, 5, 1) and b.dtype == np.uint8
+    assert b[0, 3, 0, 0] == 255 and b[1, 0, 4, 0] == 255 and b[1, 3, 1, 0] == 1
+    f, l = data.pad_batch_formulas([[1, 2, 3], [4]], id_pad=8, id_end=9)
+    assert f.tolist() == [[1, 2, 3, 9], [4, 9, 8, 8]] and l.tolist() == [4, 2]
+    got = list(data.minibatches(((i, -i) for i in range(5)), 2))
+    assert got == [([0, 1], [0, -1]), ([2, 3], [-2, -3]), ([4], [-4])]
+    assert list(data.minibatches(iter(()), 3)) == []
+    v = data.SimpleVocab(10)
+    assert (v.id_unk, v.id_pad, v.id_end) == (7, 8, 9)
+
+
+def test_flat_store_layout_cpu():
+    from latex_ocr_b200.decoder import decoder_specs
+    from latex_ocr_b200.params import FlatStore
+    S = FlatStore(decoder_specs(512, 512, 512, 500, 512), "cpu", bf16_shadow=True)
+    o = S.offsets
+    # the three per-step weights (and their biases) must be contiguous: one GEMM, one weight-gradient GEMM
+    a = o["attention.decoder_att.weight"]
+    b = o["f_beta.weight"]
+    c = o["decode_step.weight_hh"]
+    assert a[0] + a[1] == b[0] and b[0] + b[1] == c[0]
+    a, b, c = o["attention.decoder_att.bias"], o["f_beta.bias"], o["decode_step.bias_hh"]
+    assert a[0] + a[1] == b[0] and b[0] + b[1] == c[0]
+    assert o["init_h.weight"][0] + o["init_h.weight"][1] == o["init_c.weight"][0]
+    assert all(v[0] % 8 == 0 for v in o.values())
+    assert sum(v[1] for v in o.values()) == 4976117          # decoder parameter count at V=500
+    S.f32("fc.bias").fill_(1.5)
+    S.sync_shadow()
+    assert S.w("fc.bias").dtype == torch.bfloat16 and float(S.w("fc.bias")[3]) == 1.5
+
+
+def test_timing_signal_table_matches_oracle():
+    from latex_ocr_b200.encoder import timing_signal_table
+    from oracle import ref_model as rm
+    t = timing_signal_table(512, 6, 30, "cpu")
+    assert torch.equal(t, rm.timing_signal_nd(512, 6, 30).permute(1, 2, 0).contiguous())
