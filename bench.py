@@ -83,7 +83,8 @@ def run_reference(args, rank):
         return
     import torch
     from oracle import ref_model as rm
-    cores = os.cpu_count() or 1
+    import bench_support as bs
+    cores = bs.cpu_threads()
     torch.set_num_threads(cores)
     sample_b = int(os.environ.get("LO_REF_SAMPLE_B", "8"))
     c = CFG2
@@ -115,6 +116,13 @@ def run_reference(args, rank):
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
+
+
+def log(*a):
+    print("[bench %.1fs]" % (time.time() - T0), *a, file=sys.stderr, flush=True)
+
+
+T0 = time.time()
 
 
 def main():
@@ -174,10 +182,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log("model built; warm-up")
     # ---- device-resident timing ---------------------------------------------------------------------
     for _ in range(args.warmup):
         model.train_step(img_dev, formula_dev)
     barrier()
+    log("warm-up done; timing")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -193,6 +203,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches_eager = _lib.launch_count() - l0
     final_loss = float(loss[0].item())
+    log("device-resident: %.2f ms/step" % ms)
     # ---- end-to-end timing (pinned host inputs, H2D + loss D2H every step) -----------------------------
     for _ in range(2):
         model.getLoss(img_pin, formula_pin)
@@ -207,6 +218,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t[0].item(), t[1].item()
+    log("e2e: %.2f ms/step" % ms_e2e)
     per_step_launches = bs.launches_per_step(model, img_dev, formula_dev)
     if rank != 0:
         if world > 1:
@@ -216,6 +228,7 @@ def main():
     total_imgs = c["B"] * world
     value = total_imgs / (ms / 1e3)
     probes = bs.kernel_probes(model, c, pk)
+    log("probes done")
     out = {
         "metric": "formula-images/sec (train step, 128x512 px, seq<=150)", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",

@@ -111,11 +111,24 @@ def kernel_probes(model, c, pk):
     return {"dominant": dominant, "all": {"attention": att, "conv": conv, "phases": extra}}
 
 
+def cpu_threads():
+    """Threads for the CPU arm: every core the process may use (affinity and cgroup quota respected), capped by
+    LO_CPU_THREADS.  Oversubscribing a quota-limited container makes the OpenMP barriers of the 150-step loop crawl."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return max(1, min(n, int(os.environ.get("LO_CPU_THREADS", "64"))))
+
+
 def cpu_baseline(c):
     """The reference's CPU algorithm (oracle port, executed un-hoisted like the reference) on this box's
     host cores, on a bounded sample of the workload."""
     from oracle import ref_model as rm
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     sb = int(os.environ.get("LO_REF_SAMPLE_B", "4"))
     pe, pd = rm.init_params(c["V"], seed=0)

@@ -460,6 +460,11 @@ int lo_conv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, int dt
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
   const int64_t P = (int64_t)N * Ho * Wo;
   LO_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cout * 9 * Cin * sizeof(float), st));
+  if (impl == LO_IMPL_TC && dt == LO_BF16 && Cin % 64 == 0 && Cout % 128 == 0 && tc_available()) {
+    LO_TRY(tc_conv3x3_wgrad((const bf16*)x, (const bf16*)dy, dw, N, H, W, Cin, Cout, pad, st));
+    if (db) LO_TRY(colsum(dy, dt, db, (int)P, Cout, Cout, 0, st));
+    return LO_OK;
+  }
   const int tiles = 9 * cdiv(Cin, 64) * cdiv(Cout, 64);
   int splits = cdiv(148 * 4, tiles);
   const int maxs = (int)((P + 511) / 512);
@@ -469,7 +474,6 @@ int lo_conv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, int dt
   LO_DISPATCH_DT(dt, T, (conv3x3_wgrad_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, dw, N, H, W, Cin, Cout, pad, splits)));
   LO_LAUNCH_OK();
   if (db) LO_TRY(colsum(dy, dt, db, (int)P, Cout, Cout, 0, st));
-  (void)impl;
   return LO_OK;
 }
 

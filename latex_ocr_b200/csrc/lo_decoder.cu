@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
           const float pre = x[i][j] + a2v[j];
           const bool on = pre > 0.f;
           acc[i][j] += on ? dv[i] : 0.f;
-          wacc[j] = fmaf(on ? dv[i] : 0.f, pre, wacc[j]);
+          wacc[j] = fmaf(dv[i], on ? pre : 0.f, wacc[j]);   // (never 0 * -inf: padded rows carry pre = -inf)
         }
     }
     __syncthreads();

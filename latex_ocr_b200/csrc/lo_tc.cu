@@ -1,11 +1,589 @@
-// tcgen05 + TMA kernels (placeholder until the sm_100a GEMM/conv land in this file).
+// tcgen05 + TMA kernels (sm_100a): NHWC 3x3 implicit-GEMM convolution and the K-major "NT" GEMM.
+//
+//   D[128 x NT] (TMEM, fp32) += A[128 x 64] (smem, bf16, K-major, SWIZZLE_128B) * B[NT x 64]^T (smem, bf16, K-major)
+//
+// A tiles come from TMA: for the convolution a 4-D tiled map over the NHWC feature map {C, W, H, N} with box
+// {64, BW, BH, 1} (BW*BH = 128 output positions); tap (r,s) is just a coordinate shift and the halo / zero padding
+// falls out of TMA's out-of-bounds zero fill — no im2col buffer, no predicates.  B tiles are rows of the
+// [Cout][9*Cin] weight matrix.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU/mask -> global).  3-4 stage mbarrier ring, one output
+// tile per CTA, 2 CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
 #include "lo_common.cuh"
+
 namespace lo {
-bool tc_available() { return false; }
-int tc_gemm_nt(const bf16*, int64_t, const bf16*, int64_t, void*, int, int64_t, int, int, int, const float*, int, int, cudaStream_t) {
-  return fail(LO_ENOTSUP, "%s: not built", __func__);
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (strings follow cute/arch/{copy_sm90_tma,mma_sm100_umma,tmem_allocator_sm100}.hpp)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int tc_conv3x3(const bf16*, const bf16*, const float*, const bf16*, bf16*, int, int, int, int, int, int, int, cudaStream_t) {
-  return fail(LO_ENOTSUP, "%s: not built", __func__);
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends for a bounded time per call; a wait that never completes traps instead of hanging the GPU
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a protocol bug must fail loudly, not hang the box
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread i of the warp gets row (quadrant base + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
+// 1024 B apart (SBO), LBO unused for swizzled K-major (=1), version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address   bits [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset (16 B units) bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                           // version = 1         bits [46,48)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B        bits [61,64)
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+  // problem
+  int M, N, K;            // GEMM view: M rows (positions), N = Cout, K = 9*Cin (conv) or K (gemm)
+  int conv;               // 0: plain NT GEMM ; 1: 3x3 conv
+  int Ho, Wo, Cin, pad;   // conv geometry (output H, W)
+  int BW, BH, tiles_w, tiles_h;
+  // epilogue
+  const float* bias;
+  const bf16* mask;
+  void* out;
+  int64_t ldc;
+  int out_f32, accumulate, relu;
+};
+
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_THREADS = 192;
+
+template <int NT, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
+  static constexpr int B_BYTES = NT * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                   const __grid_constant__ CUtensorMap mapB, TcParams p) {
+  using SM = TcSmem<NT, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * NT;
+  const int mt = blockIdx.y;
+  const int KB = p.K / TC_BK;
+
+  // tile origin
+  int img = 0, h0 = 0, w0 = 0, m0 = mt * TC_BM;
+  if (p.conv) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    img = mt / per_img;
+    const int rem = mt % per_img;
+    h0 = (rem / p.tiles_w) * p.BH;
+    w0 = (rem % p.tiles_w) * p.BW;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const int cpb = p.conv ? p.Cin / TC_BK : 1;
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* sa = smem + s * SM::STAGE_BYTES;
+        uint8_t* sb = sa + SM::A_BYTES;
+        mbar_expect_tx(full_bar + s, SM::STAGE_BYTES);
+        if (p.conv) {
+          const int tap = kb / cpb, cb = kb % cpb;
+          const int r = tap / 3, q = tap % 3;
+          tma_load_4d(sa, &mapA, full_bar + s, cb * TC_BK, w0 + q - p.pad, h0 + r - p.pad, img);
+        } else {
+          tma_load_2d(sa, &mapA, full_bar + s, kb * TC_BK, m0);
+        }
+        tma_load_2d(sb, &mapB, full_bar + s, kb * TC_BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (one thread) =====
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, NT);
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint32_t sb = sa + SM::A_BYTES;
+        const uint64_t da = make_kmajor_sw128_desc(sa);
+        const uint64_t db = make_kmajor_sw128_desc(sb);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; k++) {
+          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the 16 B-unit address field
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);             // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warps 2..5 ; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;          // row inside the 128-row tile == TMEM lane
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    bool row_ok;
+    int64_t row_off;
+    if (p.conv) {
+      const int h = h0 + row / p.BW, w = w0 + row % p.BW;
+      row_ok = (h < p.Ho) && (w < p.Wo);
+      row_off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
+    } else {
+      row_ok = (m0 + row) < p.M;
+      row_off = (int64_t)(m0 + row) * p.ldc;
+    }
+#pragma unroll 1
+    for (int c = 0; c < NT; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective: no divergence around it
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const int n = n0 + c + g * 8;
+        if (n >= p.N) continue;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) f[i] += __ldg(p.bias + n + i);
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + n;
+          if (p.accumulate) {
+            float old[8];
+            ld8(o, old);
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] += old[i];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
+          }
+          st8(o, f);
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + row_off + n;
+          if (p.accumulate) {
+            float old[8];
+            ld8(o, old);
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] += old[i];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (p.mask) {
+            float mk[8];
+            ld8(p.mask + row_off + n, mk);
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = mk[i] > 0.f ? f[i] : 0.f;
+          }
+          st8(o, f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, NT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:  dW[co][tap][ci] += sum_p dY[p][co] * X[p + tap][ci]
+// GEMM view: M = co (128), N = ci (NT), K = output positions.  Both operands are "MN-major" (the channel index is
+// contiguous in NHWC), which UMMA takes directly: smem tile = [128 positions][64 channels] (one TMA box, SWIZZLE_128B),
+// descriptor LBO = distance between 64-channel boxes, SBO = 1024 B (8 positions), 16 positions (2048 B) per MMA.
+// grid: (co tiles * ci tiles, 9 taps, K splits); epilogue = fp32 atomics into dW (split-K partial sums).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // next 64-element block along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;                   // next 8 rows along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct WgParams {
+  int Cin, Cout, Ho, Wo, pad;
+  int BW, BH, tiles_w, tiles_h, kstages, per_split, ci_tiles;
+  float* dw;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY,
+                                                               const __grid_constant__ CUtensorMap mapX, WgParams p) {
+  constexpr int BOX = 128 * 64 * 2;                 // one [128 pos][64 ch] box
+  constexpr int A_BYTES = 2 * BOX, B_BYTES = (NT / 64) * BOX, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = (blockIdx.x / p.ci_tiles) * 128, ci0 = (blockIdx.x % p.ci_tiles) * NT;
+  const int tap = blockIdx.y, r = tap / 3, q = tap % 3;
+  const int ks0 = blockIdx.z * p.per_split;
+  const int ks1 = min(p.kstages, ks0 + p.per_split);
+  const int KS = ks1 - ks0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapDY);
+    tma_prefetch_desc(&mapX);
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (KS > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int per_img = p.tiles_w * p.tiles_h;
+        for (int i = 0; i < KS; i++) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          const int ks = ks0 + i;
+          const int img = ks / per_img, rem = ks % per_img;
+          const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          tma_load_4d(sa, &mapDY, full_bar + s, co0, w0, h0, img);
+          tma_load_4d(sa + BOX, &mapDY, full_bar + s, co0 + 64, w0, h0, img);
+#pragma unroll
+          for (int j = 0; j < NT / 64; j++)
+            tma_load_4d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, w0 + q - p.pad, h0 + r - p.pad, img);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NT) | (1u << 15) | (1u << 16);   // A and B MN-major
+        for (int i = 0; i < KS; i++) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const uint64_t da = make_mnmajor_sw128_desc(sa + k * 2048, BOX);
+            const uint64_t db = make_mnmajor_sw128_desc(sb + k * 2048, BOX);
+            umma_bf16(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);
+        }
+        umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    } else {
+      const int quad = warp & 3;
+      const int co = co0 + quad * 32 + lane;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < NT; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+        if (co < p.Cout) {
+          float* o = p.dw + ((int64_t)co * 9 + tap) * p.Cin + ci0 + c;
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (ci0 + c + j < p.Cin) atomicAdd(o + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, NT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_encode = nullptr;
+static int g_tc_state = -1;   // -1 unknown, 0 unavailable, 1 ok
+
+bool tc_available() {
+  if (g_tc_state >= 0) return g_tc_state == 1;
+  g_tc_state = 0;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) return false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+      qres != cudaDriverEntryPointSuccess)
+    return false;
+  g_encode = (PFN_tmapEncodeTiled)fn;
+  g_tc_state = 1;
+  return true;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LO_ECUDA, "%s: cuTensorMapEncodeTiled failed (%ld)", "tc", (long)r);
+  return LO_OK;
+}
+
+template <int NT, int STAGES>
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, cudaStream_t st) {
+  using SM = TcSmem<NT, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LO_CUDA(cudaFuncSetAttribute(tc_gemm_conv_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(p.N, NT), mtiles);
+  tc_gemm_conv_kernel<NT, STAGES><<<grid, TC_THREADS, SM::TOTAL, st>>>(mA, mB, p);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, cudaStream_t st) {
+  if (p.N <= 64) return launch_tc<64, 4>(mA, mB, p, mtiles, st);
+  return launch_tc<128, 3>(mA, mB, p, mtiles, st);
+}
+
+int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
+               const float* bias, int accumulate, int relu, cudaStream_t st) {
+  if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
+  LO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "K%64, N%8, ld%8");
+  LO_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0, "16-byte alignment");
+  CUtensorMap mA, mB;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t str[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t box[2] = {64, 128};
+    LO_TRY(make_map(&mA, A, 2, dims, str, box));
+  }
+  const int NT = N <= 64 ? 64 : 128;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t str[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)NT};
+    LO_TRY(make_map(&mB, W, 2, dims, str, box));
+  }
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.conv = 0;
+  p.bias = bias; p.mask = nullptr; p.out = C; p.ldc = ldc;
+  p.out_f32 = (dtC == LO_F32); p.accumulate = accumulate; p.relu = relu;
+  return launch_tc_any(mA, mB, p, cdiv(M, TC_BM), st);
+}
+
+int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask, bf16* y, int N, int H, int W, int Cin, int Cout,
+               int pad, int relu, cudaStream_t st) {
+  if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
+  LO_CHECK_ARG(Cin % 64 == 0 && Cout % 8 == 0, "Cin%64==0, Cout%8==0");
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  int BW = 128;
+  while (BW > 8 && BW / 2 >= Wo) BW /= 2;     // smallest power of two >= Wo (capped at 128)
+  const int BH = 128 / BW;
+  CUtensorMap mA, mB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+    LO_TRY(make_map(&mA, x, 4, dims, str, box));
+  }
+  const int NT = Cout <= 64 ? 64 : 128;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
+    cuuint64_t str[1] = {(cuuint64_t)9 * Cin * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)NT};
+    LO_TRY(make_map(&mB, w, 2, dims, str, box));
+  }
+  TcParams p{};
+  p.M = N * Ho * Wo; p.N = Cout; p.K = 9 * Cin; p.conv = 1;
+  p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.pad = pad;
+  p.BW = BW; p.BH = BH; p.tiles_w = cdiv(Wo, BW); p.tiles_h = cdiv(Ho, BH);
+  p.bias = bias; p.mask = mask; p.out = y; p.ldc = Cout;
+  p.out_f32 = 0; p.accumulate = 0; p.relu = relu;
+  const int mtiles = N * p.tiles_w * p.tiles_h;
+  LO_CHECK_ARG(mtiles <= 65535, "too many M tiles for grid.y");
+  return launch_tc_any(mA, mB, p, mtiles, st);
+}
+
+
+template <int NT, int STAGES>
+static int launch_wgrad(const CUtensorMap& mDY, const CUtensorMap& mX, const WgParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int TOTAL = STAGES * (2 + NT / 64) * 16384 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LO_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    attr_set = true;
+  }
+  tc_wgrad_kernel<NT, STAGES><<<grid, TC_THREADS, TOTAL, st>>>(mDY, mX, p);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+// dw must be zeroed by the caller (split-K partial sums are accumulated with atomics)
+int tc_conv3x3_wgrad(const bf16* x, const bf16* dy, float* dw, int N, int H, int W, int Cin, int Cout, int pad, cudaStream_t st) {
+  if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
+  LO_CHECK_ARG(Cin % 64 == 0 && Cout % 128 == 0, "Cin%64==0, Cout%128==0");
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  int BW = 128;
+  while (BW > 8 && BW / 2 >= Wo) BW /= 2;
+  const int BH = 128 / BW;
+  CUtensorMap mDY, mX;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    cuuint64_t str[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+    LO_TRY(make_map(&mDY, dy, 4, dims, str, box));
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+    LO_TRY(make_map(&mX, x, 4, dims, str, box));
+  }
+  WgParams p{};
+  p.Cin = Cin; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo; p.pad = pad;
+  p.BW = BW; p.BH = BH; p.tiles_w = cdiv(Wo, BW); p.tiles_h = cdiv(Ho, BH);
+  p.kstages = N * p.tiles_w * p.tiles_h;
+  p.dw = dw;
+  const int NT = Cin >= 128 ? 128 : 64;
+  p.ci_tiles = Cin / NT;
+  const int tiles = (Cout / 128) * p.ci_tiles * 9;
+  int splits = cdiv(148 * 2, tiles);
+  if (splits > p.kstages) splits = p.kstages;
+  if (splits < 1) splits = 1;
+  p.per_split = cdiv(p.kstages, splits);
+  splits = cdiv(p.kstages, p.per_split);
+  dim3 grid((Cout / 128) * p.ci_tiles, 9, splits);
+  if (NT == 128) return launch_wgrad<128, 3>(mDY, mX, p, grid, st);
+  return launch_wgrad<64, 4>(mDY, mX, p, grid, st);
+}
+
 }  // namespace lo

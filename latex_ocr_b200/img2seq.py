@@ -129,19 +129,27 @@ class Img2SeqModel:
                   "caps": torch.zeros(caps_d.shape, dtype=torch.int64, device=self.device)}
             st["img"].copy_(img_d)
             st["caps"].copy_(caps_d)
+            # warm-up outside capture (allocates workspaces, sets kernel attributes); it must not train:
+            # parameters, Adam moments/step and the bf16 shadows are restored afterwards
+            stores = (self.encoder.store, self.decoder.store)
+            snap = [{k: getattr(S, k).clone() for k in ("master", "m", "v", "adam_state", "shadow") if getattr(S, k) is not None}
+                    for S in stores]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):       # warm-up outside capture (allocates workspaces)
+            with torch.cuda.stream(side):
                 for _ in range(2):
                     mask = self.decoder.make_dropout_mask(N, T)
                     self._step_body(st["img"], st["caps"], decode_lengths, mask)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            for S, sn in zip(stores, snap):
+                for k, v in sn.items():
+                    getattr(S, k).copy_(v)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 mask = self.decoder.make_dropout_mask(N, T)
                 st["loss"] = self._step_body(st["img"], st["caps"], decode_lengths, mask)
-            st["graph"] = graph
+            st["graph"] = graph          # capture records the launches, it does not execute them
             g = self._graphs[key] = st
         g["img"].copy_(img_d, non_blocking=True)
         g["caps"].copy_(caps_d, non_blocking=True)

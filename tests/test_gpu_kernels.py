@@ -98,9 +98,9 @@ def test_conv1_pool(dtype):
     b = torch.randn(64, device="cuda")
     out = torch.zeros(N, H // 2, W // 2, 64, device="cuda", dtype=dtype)
     _lib.check(L.lo_conv1_pool_forward(_lib.ptr(img), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), _lib.dt_of(out), N, H, W, _lib.stream_ptr()))
-    x = img.clone().requires_grad_(False)
-    wr = w.clone().requires_grad_(True)
-    br = b.clone().requires_grad_(True)
+    x = img.double()
+    wr = w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True)
     ref = F.max_pool2d(F.relu(F.conv2d(x, wr, br, padding=1)), 2)
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     assert relerr(out.float().permute(0, 3, 1, 2), ref) < tol
@@ -109,7 +109,7 @@ def test_conv1_pool(dtype):
         ref.backward(g)
         dw = torch.zeros(64, 9, device="cuda")
         db = torch.zeros(64, device="cuda")
-        gp = g.permute(0, 2, 3, 1).contiguous()
+        gp = g.float().permute(0, 2, 3, 1).contiguous()
         _lib.check(L.lo_conv1_pool_wgrad(_lib.ptr(img), _lib.ptr(w), _lib.ptr(b), _lib.ptr(gp), 0, _lib.ptr(dw), _lib.ptr(db), N, H, W, _lib.stream_ptr()))
         assert relerr(dw.view(64, 1, 3, 3), wr.grad) < 1e-4
         assert relerr(db, br.grad) < 1e-4
@@ -120,15 +120,15 @@ def test_conv1_pool(dtype):
 def test_conv3x3_forward_dgrad_wgrad(pad, dtype):
     _lib, L = _L()
     torch.manual_seed(4 + pad)
-    N, H, W, Cin, Cout = 2, 9, 13, 32, 72
+    N, H, W, Cin, Cout = 2, 9, 13, 32, 80
     x = torch.randn(N, Cin, H, W, device="cuda")
     w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
     b = torch.randn(Cout, device="cuda")
     xq, wq = x.to(dtype).float(), w.to(dtype).float()
-    xr = xq.clone().requires_grad_(True)
-    wr = wq.clone().requires_grad_(True)
-    br = b.clone().requires_grad_(True)
-    ref = F.relu(F.conv2d(xr, wr, br, padding=pad))
+    xr = xq.double().requires_grad_(True)
+    wr = wq.double().requires_grad_(True)
+    br = b.double().requires_grad_(True)
+    ref = F.relu(F.conv2d(xr, wr, br, padding=pad))          # float64: cuDNN fp32 would silently use TF32
     xn = xq.permute(0, 2, 3, 1).contiguous().to(dtype)
     wk = wq.permute(0, 2, 3, 1).contiguous().to(dtype)            # [Cout][3][3][Cin]
     Ho, Wo = H + 2 * pad - 2, W + 2 * pad - 2
@@ -138,9 +138,9 @@ def test_conv3x3_forward_dgrad_wgrad(pad, dtype):
     tol = 1e-5 if dtype == torch.float32 else 1.5e-2
     assert relerr(y.float().permute(0, 3, 1, 2), ref) < tol
     # backward pieces against autograd
-    g = torch.randn_like(ref).to(dtype).float()
+    g = torch.randn_like(ref).to(dtype).double()
     ref.backward(g)
-    dy = (g * (ref > 0)).permute(0, 2, 3, 1).contiguous().to(dtype)          # dY (post ReLU mask)
+    dy = (g * (ref > 0)).float().permute(0, 2, 3, 1).contiguous().to(dtype)          # dY (post ReLU mask)
     dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
     db = torch.zeros(Cout, device="cuda")
     _lib.check(L.lo_conv3x3_wgrad(_lib.ptr(xn), _lib.ptr(dy), _lib.ptr(dw), _lib.ptr(db), _lib.dt_of(y), N, H, W, Cin, Cout, pad, 0, st))
