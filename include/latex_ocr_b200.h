@@ -175,9 +175,12 @@ typedef struct lo_decoder_args {
   float* g_w_ih; float* g_b_ih;
   float* g_w_init; float* g_b_init;
   float* g_w_fc; float* g_b_fc;
-  void* work;              /* lo_attention_workspace_bytes(B, max(A,C)) */
+  void* work;              /* lo_attention_workspace_bytes(B, max(A,C)), zero-initialised once */
+  void* bfwork;            /* optional (impl=TC, dt=bf16): bf16 staging for the hoisted tcgen05 GEMMs,
+                              lo_decoder_bfwork_bytes(args) bytes */
 } lo_decoder_args;
 
+int64_t lo_decoder_bfwork_bytes(const lo_decoder_args* a);
 /* sizeof(lo_decoder_args) as compiled into the library (the ctypes mirror checks it) */
 int64_t lo_sizeof_decoder_args(void);
 /* forward through all T steps + logits ; if with_loss, also CE + regulariser into loss[] */

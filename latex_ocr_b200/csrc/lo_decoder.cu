@@ -32,7 +32,7 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(LO_ATT_THREADS) attention_fwd_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
-    float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, int R, int nsplit,
+    float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
     int* __restrict__ counters, float* __restrict__ partials) {
   constexpr int CH = NV * 256;   // A == C == CH
   const int b = blockIdx.y, sp = blockIdx.x;
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_fwd_kernel(
       const float g = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
       gate_pre[(int64_t)b * gate_stride + c] = g;
       gctx[(int64_t)b * CH + c] = g * t;
+      if (gctx_bf) gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(g * t);
     }
   }
   for (int r = threadIdx.x; r < R; r += LO_ATT_THREADS) alb[r] = expf(ldcg_f(alb + r) - Mg) * invL;
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_bwd_kernel(
     int64_t o1_stride, const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride,
     const float* __restrict__ ctx, const float* __restrict__ dgctx, int64_t dg_stride, const float* __restrict__ dreg,
     int64_t dreg_stride, const float* __restrict__ sreg, int64_t sreg_stride, float* __restrict__ de, float* __restrict__ datt2,
-    float* __restrict__ dgp, int64_t dcat_stride, float* __restrict__ dctx_out, int R, int nsplit,
-    int* __restrict__ counters, float* __restrict__ partials) {
+    float* __restrict__ dgp, int64_t dcat_stride, bf16* __restrict__ datt2_bf, bf16* __restrict__ dgp_bf,
+    float* __restrict__ dctx_out, int R, int nsplit, int* __restrict__ counters, float* __restrict__ partials) {
   constexpr int CH = NV * 256;
   const int b = blockIdx.y, sp = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_bwd_kernel(
     }
     if (sp == 0 && wid == 0) {
       st8(dgp + (int64_t)b * dcat_stride + c0, gp);
+      if (dgp_bf) st8(dgp_bf + (int64_t)b * dcat_stride + c0, gp);
       st8(dctx_out + (int64_t)b * CH + c0, dc + j * 8);
     }
   }
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_bwd_kernel(
     float t = 0.f;
     for (int sidx = 0; sidx < nsplit; sidx++) t += ldcg_f(pb + (int64_t)sidx * (CH + 2) + 2 + c);
     datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+    if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
   }
 }
 
@@ -371,8 +374,9 @@ __global__ void mean_rows_kernel(const T* __restrict__ enc, float* __restrict__ 
 __global__ void lstm_pw_fwd_kernel(const float* __restrict__ gtmp, const float* __restrict__ ptab,
                                    const int64_t* __restrict__ tok, int64_t tok_stride, const float* __restrict__ hh,
                                    int64_t hh_stride, const float* __restrict__ c_prev, float* __restrict__ gates,
-                                   float* __restrict__ c_out, float* __restrict__ h_out, float* __restrict__ hd,
-                                   int64_t hd_stride, const float* __restrict__ dmask, int nrows, int D, int V) {
+                                   float* __restrict__ c_out, float* __restrict__ h_out, bf16* __restrict__ h_bf,
+                                   float* __restrict__ hd, int64_t hd_stride, const float* __restrict__ dmask, int nrows, int D,
+                                   int V) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nrows * D) return;
   const int b = idx / D, j = idx % D;
@@ -393,6 +397,7 @@ __global__ void lstm_pw_fwd_kernel(const float* __restrict__ gtmp, const float* 
   gt[j] = i; gt[D + j] = f; gt[2 * D + j] = g; gt[3 * D + j] = o;
   c_out[(int64_t)b * D + j] = c;
   h_out[(int64_t)b * D + j] = h;
+  if (h_bf) h_bf[(int64_t)b * D + j] = __float2bfloat16_rn(h);
   if (hd) hd[(int64_t)b * hd_stride + j] = dmask ? h * dmask[(int64_t)b * hd_stride + j] : h;
 }
 
@@ -401,7 +406,8 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_st
                                    const float* __restrict__ dh_next,
                                    int64_t dhn_stride, float* __restrict__ dc, const float* __restrict__ gates,
                                    const float* __restrict__ c_prev, const float* __restrict__ c_cur,
-                                   float* __restrict__ dG, int64_t dG_stride, int nrows, int D) {
+                                   float* __restrict__ dG, int64_t dG_stride, bf16* __restrict__ dG_bf, float* __restrict__ dxh_zero,
+                                   int C, int nrows, int D) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nrows * D) return;
   const int b = idx / D, j = idx % D;
@@ -418,6 +424,20 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_st
   d[2 * D + j] = dct * i * (1.f - g * g);
   d[3 * D + j] = dh * tc * o * (1.f - o);
   dc[(int64_t)b * D + j] = dct * f;
+  if (dG_bf) {
+    bf16* q = dG_bf + (int64_t)b * dG_stride;
+    q[j] = __float2bfloat16_rn(d[j]);
+    q[D + j] = __float2bfloat16_rn(d[D + j]);
+    q[2 * D + j] = __float2bfloat16_rn(d[2 * D + j]);
+    q[3 * D + j] = __float2bfloat16_rn(d[3 * D + j]);
+  }
+  if (dxh_zero) {
+    // the tcgen05 split-K GEMMs that follow accumulate with atomics: clear [dgctx | dh] (dh_next was consumed above;
+    // entry C+j is this thread's own read location, entries < C are never read here)
+    float* z = dxh_zero + (int64_t)b * (C + D);
+    z[C + j] = 0.f;
+    for (int q = j; q < C; q += D) z[q] = 0.f;
+  }
 }
 
 // fused cross-entropy forward/backward: warp per (b,t) row.  target = caps[b][t+1]; rows with b >= bt[t] get 0.
@@ -536,6 +556,19 @@ __global__ void dptab_kernel(const float* __restrict__ dcat, int64_t row_stride,
   if (j < G) dptab[(int64_t)v * G + j] = acc;
 }
 
+// one-hot rows (t,b) x Vp for the tensor-core form of the embedding-table gradient: dptab = onehot^T @ dG
+__global__ void onehot_kernel(const int64_t* __restrict__ caps, int64_t caps_stride, const int32_t* __restrict__ dlen,
+                              bf16* __restrict__ oh, int B, int Tn, int Vp) {
+  const int64_t total = (int64_t)B * Tn * Vp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % Vp);
+    const int64_t row = i / Vp;
+    const int b = (int)(row % B), t = (int)(row / B);
+    const bool hit = (t < dlen[b]) && (caps[(int64_t)b * caps_stride + t] == (int64_t)v);
+    oh[i] = __float2bfloat16_rn(hit ? 1.f : 0.f);
+  }
+}
+
 // denc[b][r][:] += dmean[b][:] / R
 __global__ void add_rowbcast_kernel(float* __restrict__ denc, const float* __restrict__ dmean, int R, int C, float scale,
                                     int64_t total) {
@@ -603,6 +636,25 @@ static inline Dims dims(const lo_decoder_args* a) {
   return Dims{a->B, a->T, a->R, a->C, a->A, a->D, a->E, a->V, a->A + a->C + 4 * a->D, 4 * a->D};
 }
 
+// bf16 staging used when impl == TC: mirrors written by the step kernels feed the tcgen05 GEMMs directly
+struct BfViews {
+  bool on;
+  bf16 *dcat, *hall, *gctx, *wet, *onehot;
+};
+static BfViews bf_views(const lo_decoder_args* a, const Dims& d) {
+  BfViews v{false, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (a->impl == LO_IMPL_TC && a->dt == LO_BF16 && a->bfwork && tc_available()) {
+    const int64_t TB = (int64_t)d.T * d.B;
+    v.on = true;
+    v.dcat = (bf16*)a->bfwork;
+    v.hall = v.dcat + TB * d.O1;
+    v.gctx = v.hall + (TB + d.B) * d.D;
+    v.wet = v.gctx + TB * d.C;
+    v.onehot = v.wet + (int64_t)d.A * d.C;
+  }
+  return v;
+}
+
 static int check_args(const lo_decoder_args* a) {
   LO_CHECK_ARG(a != nullptr, "args");
   LO_CHECK_ARG(a->B > 0 && a->T > 0 && a->R > 0 && a->V > 1, "B,T,R,V");
@@ -623,14 +675,14 @@ static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a
 
 static int attention_forward_launch(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                                     const float* wf, float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre,
-                                    int64_t gate_stride, float* gctx, int B, int R, int C, void* work, cudaStream_t st) {
+                                    int64_t gate_stride, float* gctx, bf16* gctx_bf, int B, int R, int C, void* work, cudaStream_t st) {
   const int ns = att_splits(B);
   int* cnt = (int*)work;
   float* part = (float*)((char*)work + 4096);
   dim3 grid(ns, B);
 #define LO_ATT_FWD(T, NV)                                                                                           \
   attention_fwd_kernel<T, NV><<<grid, LO_ATT_THREADS, 0, st>>>((const T*)att1, (const T*)enc, att2, att2_stride, wf, \
-                                                               alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, R, ns, cnt, part)
+                                                               alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, R, ns, cnt, part)
   if (dt == LO_F32) {
     if (C == 256) LO_ATT_FWD(float, 1); else if (C == 512) LO_ATT_FWD(float, 2); else LO_ATT_FWD(float, 4);
   } else {
@@ -676,6 +728,8 @@ static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_
   LO_TRY(gemm_nt(a->mean, LO_F32, d.C, a->w_init, dt, d.C, a->hall, LO_F32, d.D, d.B, d.D, d.C, a->b_init, 0, 0, LO_IMPL_SIMT, st));
   LO_TRY(gemm_nt(a->mean, LO_F32, d.C, (const char*)a->w_init + (size_t)d.D * d.C * es, dt, d.C, a->call, LO_F32, d.D, d.B,
                  d.D, d.C, a->b_init + d.D, 0, 0, LO_IMPL_SIMT, st));
+  const BfViews bv = bf_views(a, d);
+  if (bv.on) LO_TRY(lo_cast(a->hall, LO_F32, bv.hall, LO_BF16, (int64_t)d.B * d.D, (void*)st));
   return LO_OK;
 }
 
@@ -687,17 +741,29 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, int nrow
   float* c_prev = a->call + (int64_t)t * d.B * d.D;
   float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
   // [att2 | gate_pre | hh_pre] = h_prev @ [W_d; W_beta; W_hh]^T + b   (seq2seq_torch.py:187, :311, LSTMCell hh part)
-  LO_TRY(gemm_nt(h_prev, LO_F32, d.D, a->wcat1, dt, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D, a->bcat1, 0, 0, LO_IMPL_SIMT, st));
-  LO_TRY(attention_forward_launch(a->att1, a->enc, dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
-                                  a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C, nrows,
-                                  d.R, d.C, a->work, st));
-  // gates_x = (gate*ctx) @ W_ih[:, E:]^T
+  const BfViews bv = bf_views(a, d);
   const size_t es = dt == LO_F32 ? 4 : 2;
-  LO_TRY(gemm_nt(a->gctx + (int64_t)t * d.B * d.C, LO_F32, d.C, (const char*)a->w_ih + (size_t)d.E * es, dt, d.E + d.C, a->gtmp,
-                 LO_F32, d.G, nrows, d.G, d.C, nullptr, 0, 0, LO_IMPL_SIMT, st));
+  if (bv.on) {
+    LO_TRY(tc_gemm_nt_ex(bv.hall + (int64_t)t * d.B * d.D, d.D, (const bf16*)a->wcat1, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D, a->bcat1,
+                         0, 0, 1, 0, 1, st));
+  } else {
+    LO_TRY(gemm_nt(h_prev, LO_F32, d.D, a->wcat1, dt, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D, a->bcat1, 0, 0, LO_IMPL_SIMT, st));
+  }
+  LO_TRY(attention_forward_launch(a->att1, a->enc, dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+                                  a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C,
+                                  bv.on ? bv.gctx + (int64_t)t * d.B * d.C : nullptr, nrows, d.R, d.C, a->work, st));
+  // gates_x = (gate*ctx) @ W_ih[:, E:]^T
+  if (bv.on) {
+    LO_TRY(tc_gemm_nt_ex(bv.gctx + (int64_t)t * d.B * d.C, d.C, (const bf16*)a->w_ih + d.E, d.E + d.C, a->gtmp, LO_F32, d.G, nrows, d.G,
+                         d.C, nullptr, 0, 0, 1, 0, 1, st));
+  } else {
+    LO_TRY(gemm_nt(a->gctx + (int64_t)t * d.B * d.C, LO_F32, d.C, (const char*)a->w_ih + (size_t)d.E * es, dt, d.E + d.C, a->gtmp,
+                   LO_F32, d.G, nrows, d.G, d.C, nullptr, 0, 0, LO_IMPL_SIMT, st));
+  }
   lstm_pw_fwd_kernel<<<cdiv((long)nrows * d.D, 256), 256, 0, st>>>(
       a->gtmp, a->ptab, tok, tok_stride, o1 + d.A + d.C, d.O1, c_prev, a->gates + (int64_t)t * d.B * d.G,
-      a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D, hd_t, hd_stride, dmask_t, nrows, d.D, d.V);
+      a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D,
+      bv.on ? bv.hall + (int64_t)(t + 1) * d.B * d.D : nullptr, hd_t, hd_stride, dmask_t, nrows, d.D, d.V);
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -707,6 +773,13 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, int nrow
 using namespace lo;
 
 extern "C" {
+
+int64_t lo_decoder_bfwork_bytes(const lo_decoder_args* a) {
+  if (!a) return 0;
+  const int64_t TB = (int64_t)a->T * a->B, O1 = a->A + a->C + 4 * a->D;
+  const int64_t Vp = (a->V + 7) / 8 * 8;
+  return (TB * (O1 + a->D + a->C + Vp) + (int64_t)a->B * a->D + (int64_t)a->A * a->C) * 2 + 1024;
+}
 
 int64_t lo_sizeof_decoder_args(void) { return (int64_t)sizeof(lo_decoder_args); }
 
@@ -721,8 +794,8 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
   LO_CHECK_ARG(A == C && (C == 256 || C == 512 || C == 1024), "attention_dim == encoder_dim in {256,512,1024}");
   LO_CHECK_ARG(B > 0 && B <= 512 && R > 0, "B in 1..512, R > 0");
   LO_CHECK_ARG(att2_stride % 4 == 0, "att2 rows must be 16-byte aligned");
-  return attention_forward_launch(att1, enc, dt, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, B,
-                                  R, C, work, (cudaStream_t)stream);
+  return attention_forward_launch(att1, enc, dt, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, nullptr,
+                                  B, R, C, work, (cudaStream_t)stream);
 }
 
 int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
@@ -808,27 +881,37 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     LO_CUDA(cudaMemsetAsync(a->dcat, 0, (size_t)d.T * d.B * d.O1 * 4, st));
     LO_CUDA(cudaMemsetAsync(a->de, 0, (size_t)BT * d.R * 4, st));
     LO_CUDA(cudaMemsetAsync(a->dctx, 0, (size_t)d.T * d.B * d.C * 4, st));
+    const BfViews bz = bf_views(a, d);
+    if (bz.on) LO_CUDA(cudaMemsetAsync(bz.dcat, 0, (size_t)d.T * d.B * d.O1 * 2, st));
   }
   int* cnt = work_counters(a);
   float* part = work_partials(a);
+  const BfViews bv = bf_views(a, d);
   for (int t = d.T - 1; t >= 0; t--) {
     const int nrows = a->bt_host[t];
     float* dcat_t = a->dcat + (int64_t)t * d.B * d.O1;
+    bf16* dcat_bf_t = bv.on ? bv.dcat + (int64_t)t * d.B * d.O1 : nullptr;
     const float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
     const float* dmul = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
     lstm_pw_bwd_kernel<<<cdiv((long)nrows * d.D, 256), 256, 0, st>>>(
         a->dhd + (int64_t)t * d.D, (int64_t)d.T * d.D, dmul, a->dxh + d.C, d.C + d.D, a->dc, a->gates + (int64_t)t * d.B * d.G,
-        a->call + (int64_t)t * d.B * d.D, a->call + (int64_t)(t + 1) * d.B * d.D, dcat_t + d.A + d.C, d.O1, nrows, d.D);
+        a->call + (int64_t)t * d.B * d.D, a->call + (int64_t)(t + 1) * d.B * d.D, dcat_t + d.A + d.C, d.O1,
+        bv.on ? dcat_bf_t + d.A + d.C : nullptr, bv.on ? a->dxh : nullptr, d.C, nrows, d.D);
     LO_LAUNCH_OK();
     // [dgctx | dh_prev] = dG @ [W_ih[:, E:] | W_hh]
-    LO_TRY(gemm_nt(dcat_t + d.A + d.C, LO_F32, d.O1, a->wbwd1, dt, d.G, a->dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 0,
-                   0, LO_IMPL_SIMT, st));
+    if (bv.on) {
+      LO_TRY(tc_gemm_nt_ex(dcat_bf_t + d.A + d.C, d.O1, (const bf16*)a->wbwd1, d.G, a->dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G,
+                           nullptr, 0, 0, 4, 1, 1, st));
+    } else {
+      LO_TRY(gemm_nt(dcat_t + d.A + d.C, LO_F32, d.O1, a->wbwd1, dt, d.G, a->dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 0,
+                     0, LO_IMPL_SIMT, st));
+    }
     dim3 grid(ns, nrows);
 #define LO_ATT_BWD(TY_, NV)                                                                                                       \
   attention_bwd_kernel<TY_, NV><<<grid, LO_ATT_THREADS, 0, st>>>(                                                                 \
       (const TY_*)a->att1, (const TY_*)a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,        \
       a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T, a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, \
-      d.O1, a->dctx + (int64_t)t * d.B * d.C, d.R, ns, cnt, part)
+      d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr, a->dctx + (int64_t)t * d.B * d.C, d.R, ns, cnt, part)
     if (dt == LO_F32) {
       if (d.C == 256) LO_ATT_BWD(float, 1); else if (d.C == 512) LO_ATT_BWD(float, 2); else LO_ATT_BWD(float, 4);
     } else {
@@ -837,8 +920,13 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
 #undef LO_ATT_BWD
     LO_LAUNCH_OK();
     // dh_prev += [datt2 | dgate_pre] @ [W_d ; W_beta]
-    LO_TRY(gemm_nt(dcat_t, LO_F32, d.O1, a->wbwd2, dt, d.A + d.C, a->dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C, nullptr, 1,
-                   0, LO_IMPL_SIMT, st));
+    if (bv.on) {
+      LO_TRY(tc_gemm_nt_ex(dcat_bf_t, d.O1, (const bf16*)a->wbwd2, d.A + d.C, a->dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C,
+                           nullptr, 0, 0, 4, 1, 1, st));
+    } else {
+      LO_TRY(gemm_nt(dcat_t, LO_F32, d.O1, a->wbwd2, dt, d.A + d.C, a->dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C, nullptr, 1,
+                     0, LO_IMPL_SIMT, st));
+    }
   }
   // dinit = [dh0 | dc0]
   LO_CUDA(cudaMemcpy2DAsync(a->dinit, (size_t)2 * d.D * 4, a->dxh + d.C, (size_t)(d.C + d.D) * 4, (size_t)d.D * 4, d.B,
@@ -846,15 +934,36 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   LO_CUDA(cudaMemcpy2DAsync(a->dinit + d.D, (size_t)2 * d.D * 4, a->dc, (size_t)d.D * 4, (size_t)d.D * 4, d.B,
                             cudaMemcpyDeviceToDevice, st));
   // ---- hoisted gradients
+  const bool tc = bv.on;
+  bf16* dcat_bf = bv.dcat;
+  bf16* hall_bf = bv.hall;
+  bf16* gctx_bf = bv.gctx;
+  bf16* wet_bf = bv.wet;
   // [W_d; W_beta; W_hh] and biases: dcat^T @ h_prev
-  LO_TRY(gemm_tn(a->dcat, LO_F32, d.O1, a->hall, LO_F32, d.D, a->g_wcat1, LO_F32, d.D, d.O1, d.D, d.T * d.B, 0, LO_IMPL_SIMT, st));
+  if (tc) {
+    LO_CUDA(cudaMemsetAsync(a->g_wcat1, 0, (size_t)d.O1 * d.D * 4, st));
+    LO_TRY(tc_gemm_tn(dcat_bf, d.O1, hall_bf, d.D, a->g_wcat1, d.D, d.O1, d.D, d.T * d.B, st));
+  } else {
+    LO_TRY(gemm_tn(a->dcat, LO_F32, d.O1, a->hall, LO_F32, d.D, a->g_wcat1, LO_F32, d.D, d.O1, d.D, d.T * d.B, 0, LO_IMPL_SIMT, st));
+  }
   LO_TRY(colsum(a->dcat, LO_F32, a->g_bcat1, d.T * d.B, d.O1, d.O1, 0, st));
   // W_ih[:, E:] : dG^T @ gctx ; b_ih = colsum(dG) (== g_b_hh)
-  LO_TRY(gemm_tn(a->dcat + d.A + d.C, LO_F32, d.O1, a->gctx, LO_F32, d.C, a->g_w_ih + d.E, LO_F32, d.E + d.C, d.G, d.C, d.T * d.B, 0,
-                 LO_IMPL_SIMT, st));
+  if (tc) {
+    LO_CUDA(cudaMemset2DAsync(a->g_w_ih + d.E, (size_t)(d.E + d.C) * 4, 0, (size_t)d.C * 4, d.G, st));
+    LO_TRY(tc_gemm_tn(dcat_bf + d.A + d.C, d.O1, gctx_bf, d.C, a->g_w_ih + d.E, d.E + d.C, d.G, d.C, d.T * d.B, st));
+  } else {
+    LO_TRY(gemm_tn(a->dcat + d.A + d.C, LO_F32, d.O1, a->gctx, LO_F32, d.C, a->g_w_ih + d.E, LO_F32, d.E + d.C, d.G, d.C, d.T * d.B, 0,
+                   LO_IMPL_SIMT, st));
+  }
   LO_TRY(colsum(a->dcat + d.A + d.C, LO_F32, a->g_b_ih, d.T * d.B, d.G, d.O1, 0, st));
   // embedding path through the projection table
-  {
+  if (tc) {
+    const int Vp = (d.V + 7) / 8 * 8;
+    onehot_kernel<<<148 * 8, 256, 0, st>>>(a->caps, a->caps_stride, work_dlen(a), bv.onehot, d.B, d.T, Vp);
+    LO_LAUNCH_OK();
+    LO_CUDA(cudaMemsetAsync(a->dptab, 0, (size_t)d.V * d.G * 4, st));
+    LO_TRY(tc_gemm_tn(bv.onehot, Vp, dcat_bf + d.A + d.C, d.O1, a->dptab, d.G, d.V, d.G, d.T * d.B, st));
+  } else {
     dim3 grid(cdiv(d.G, 256), d.V);
     dptab_kernel<<<grid, 256, 0, st>>>(a->dcat, d.O1, (int64_t)d.B * d.O1, d.A + d.C, a->caps, a->caps_stride, work_dlen(a), a->dptab,
                                        d.B, d.T, d.G);
@@ -872,9 +981,17 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     LO_LAUNCH_OK();
   }
   // encoder_att: g_W = datt1^T enc ; g_b = colsum(datt1) ; denc = datt1 @ W_e
-  LO_TRY(gemm_tn(a->datt1, dt, d.A, a->enc, dt, d.C, a->g_w_enc_att, LO_F32, d.C, d.A, d.C, d.B * d.R, 0, LO_IMPL_SIMT, st));
+  if (tc) {
+    LO_CUDA(cudaMemsetAsync(a->g_w_enc_att, 0, (size_t)d.A * d.C * 4, st));
+    LO_TRY(tc_gemm_tn((const bf16*)a->datt1, d.A, (const bf16*)a->enc, d.C, a->g_w_enc_att, d.C, d.A, d.C, d.B * d.R, st));
+    transpose_kernel<bf16><<<dim3(cdiv(d.C, 32), cdiv(d.A, 32)), dim3(32, 8), 0, st>>>((const bf16*)a->w_enc_att, d.C, wet_bf, d.A, d.A, d.C);
+    LO_LAUNCH_OK();
+    LO_TRY(tc_gemm_nt((const bf16*)a->datt1, d.A, wet_bf, d.A, a->denc, LO_F32, d.C, d.B * d.R, d.C, d.A, nullptr, 0, 0, st));
+  } else {
+    LO_TRY(gemm_tn(a->datt1, dt, d.A, a->enc, dt, d.C, a->g_w_enc_att, LO_F32, d.C, d.A, d.C, d.B * d.R, 0, LO_IMPL_SIMT, st));
+    LO_TRY(gemm_nn(a->datt1, dt, d.A, a->w_enc_att, dt, d.C, a->denc, LO_F32, d.C, d.B * d.R, d.C, d.A, 0, LO_IMPL_SIMT, st));
+  }
   LO_TRY(colsum(a->datt1, dt, a->g_b_enc_att, d.B * d.R, d.A, d.A, 0, st));
-  LO_TRY(gemm_nn(a->datt1, dt, d.A, a->w_enc_att, dt, d.C, a->denc, LO_F32, d.C, d.B * d.R, d.C, d.A, 0, LO_IMPL_SIMT, st));
   // denc[b] += alphas[b]^T @ dctx[:, b, :]   (the context read, summed over time — a batched GEMM instead of a per-step RMW)
   {
     GemmDesc g{d.R, d.C, d.T, 1, d.R, (int64_t)d.B * d.C, 1, d.C, d.B, (int64_t)d.T * d.R, d.C, (int64_t)d.R * d.C, nullptr, 1, 0};

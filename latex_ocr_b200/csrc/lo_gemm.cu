@@ -110,7 +110,7 @@ __global__ void zero2d_kernel(float* C, int M, int N, int64_t ldc, int64_t sC) {
 int gemm(const void* A, int dtA, const void* B, int dtB, void* C, int dtC, const GemmDesc& d, int impl, cudaStream_t st) {
   LO_CHECK_ARG(d.M > 0 && d.N > 0 && d.K > 0 && d.batch > 0, "empty GEMM");
   if (impl == LO_IMPL_TC && dtA == LO_BF16 && dtB == LO_BF16 && d.sak == 1 && d.sbk == 1 && d.batch == 1 &&
-      d.K % 64 == 0 && d.sam % 8 == 0 && d.sbn % 8 == 0 && tc_available()) {
+      d.K % 64 == 0 && d.N % 8 == 0 && d.ldc % 8 == 0 && d.sam % 8 == 0 && d.sbn % 8 == 0 && tc_available()) {
     return tc_gemm_nt((const bf16*)A, d.sam, (const bf16*)B, d.sbn, C, dtC, d.ldc, d.M, d.N, d.K, d.bias,
                       d.accumulate, d.relu, st);
   }
@@ -161,27 +161,36 @@ int gemm_nn(const void* A, int dtA, int64_t lda, const void* B, int dtB, int64_t
   return gemm(A, dtA, B, dtB, C, dtC, d, impl, st);
 }
 
-// out[n] (+)= sum_m X[m][n]: one block per 32 columns, 8 row-lanes, deterministic tree.
+// out[n] (+)= sum_m X[m][n].  grid (N/32, row splits): each block reduces a row range for 32 columns (8 row lanes,
+// fixed tree) and adds its partial with one fp32 atomic per column; `out` is zeroed first unless accumulating.
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ X, float* __restrict__ out, int M, int N, int64_t ld, int accumulate) {
+__global__ void colsum_kernel(const T* __restrict__ X, float* __restrict__ out, int M, int N, int64_t ld, int rows_per_block) {
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
   float s = 0.f;
   if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += ldf(X + (int64_t)m * ld + n);
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) s += ldf(X + (int64_t)m * ld + n);
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) t += red[i][threadIdx.x];
-    out[n] = accumulate ? out[n] + t : t;
+    atomicAdd(out + n, t);
   }
 }
 
 int colsum(const void* X, int dt, float* out, int M, int N, int64_t ld, int accumulate, cudaStream_t st) {
   LO_CHECK_ARG(M > 0 && N > 0, "empty colsum");
-  LO_DISPATCH_DT(dt, T, (colsum_kernel<T><<<cdiv(N, 32), dim3(32, 8), 0, st>>>((const T*)X, out, M, N, ld, accumulate)));
+  if (!accumulate) LO_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
+  const int cb = cdiv(N, 32);
+  int splits = cdiv(148 * 8, cb);
+  if (splits > cdiv(M, 64)) splits = cdiv(M, 64);
+  if (splits < 1) splits = 1;
+  const int rpb = cdiv(M, splits);
+  dim3 grid(cb, cdiv(M, rpb));
+  LO_DISPATCH_DT(dt, T, (colsum_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)X, out, M, N, ld, rpb)));
   LO_LAUNCH_OK();
   return LO_OK;
 }

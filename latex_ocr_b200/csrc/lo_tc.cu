@@ -10,6 +10,8 @@
 // tile per CTA, 2 CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 
+#include <unordered_map>
+
 #include "lo_common.cuh"
 
 namespace lo {
@@ -129,6 +131,7 @@ struct TcParams {
   void* out;
   int64_t ldc;
   int out_f32, accumulate, relu;
+  int kb_per_split, atomic;   // split-K over gridDim.z: fp32 atomics onto `out` (bias added by split 0)
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -156,7 +159,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * NT;
   const int mt = blockIdx.y;
-  const int KB = p.K / TC_BK;
+  const int KB_all = p.K / TC_BK;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int KB = min(KB_all, kb0 + p.kb_per_split) - kb0;      // K blocks of this split
 
   // tile origin
   int img = 0, h0 = 0, w0 = 0, m0 = mt * TC_BM;
@@ -195,14 +200,15 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         uint8_t* sa = smem + s * SM::STAGE_BYTES;
         uint8_t* sb = sa + SM::A_BYTES;
         mbar_expect_tx(full_bar + s, SM::STAGE_BYTES);
+        const int kg = kb0 + kb;
         if (p.conv) {
-          const int tap = kb / cpb, cb = kb % cpb;
+          const int tap = kg / cpb, cb = kg % cpb;
           const int r = tap / 3, q = tap % 3;
           tma_load_4d(sa, &mapA, full_bar + s, cb * TC_BK, w0 + q - p.pad, h0 + r - p.pad, img);
         } else {
-          tma_load_2d(sa, &mapA, full_bar + s, kb * TC_BK, m0);
+          tma_load_2d(sa, &mapA, full_bar + s, kg * TC_BK, m0);
         }
-        tma_load_2d(sb, &mapB, full_bar + s, kb * TC_BK, n0);
+        tma_load_2d(sb, &mapB, full_bar + s, kg * TC_BK, n0);
       }
     }
     __syncwarp();
@@ -257,11 +263,15 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]);
-        if (p.bias) {
+        if (p.bias && blockIdx.z == 0) {
 #pragma unroll
           for (int i = 0; i < 8; i++) f[i] += __ldg(p.bias + n + i);
         }
-        if (p.out_f32) {
+        if (p.atomic) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + n;
+#pragma unroll
+          for (int i = 0; i < 8; i++) atomicAdd(o + i, f[i]);
+        } else if (p.out_f32) {
           float* o = reinterpret_cast<float*>(p.out) + row_off + n;
           if (p.accumulate) {
             float old[8];
@@ -323,6 +333,8 @@ struct WgParams {
   int Cin, Cout, Ho, Wo, pad;
   int BW, BH, tiles_w, tiles_h, kstages, per_split, ci_tiles;
   float* dw;
+  int plain;          // 1: plain C[M][N] += A[K][M]^T B[K][N] (2-D maps; Cout = M, Cin = N, tap ignored)
+  int64_t ldc;
 };
 
 template <int NT, int STAGES>
@@ -368,11 +380,18 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(full_bar + s, STAGE_BYTES);
-          tma_load_4d(sa, &mapDY, full_bar + s, co0, w0, h0, img);
-          tma_load_4d(sa + BOX, &mapDY, full_bar + s, co0 + 64, w0, h0, img);
+          if (p.plain) {
+            tma_load_2d(sa, &mapDY, full_bar + s, co0, ks * 128);
+            tma_load_2d(sa + BOX, &mapDY, full_bar + s, co0 + 64, ks * 128);
 #pragma unroll
-          for (int j = 0; j < NT / 64; j++)
-            tma_load_4d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, w0 + q - p.pad, h0 + r - p.pad, img);
+            for (int j = 0; j < NT / 64; j++) tma_load_2d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, ks * 128);
+          } else {
+            tma_load_4d(sa, &mapDY, full_bar + s, co0, w0, h0, img);
+            tma_load_4d(sa + BOX, &mapDY, full_bar + s, co0 + 64, w0, h0, img);
+#pragma unroll
+            for (int j = 0; j < NT / 64; j++)
+              tma_load_4d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, w0 + q - p.pad, h0 + r - p.pad, img);
+          }
         }
       }
       __syncwarp();
@@ -407,7 +426,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
         if (co < p.Cout) {
-          float* o = p.dw + ((int64_t)co * 9 + tap) * p.Cin + ci0 + c;
+          float* o = p.plain ? p.dw + (int64_t)co * p.ldc + ci0 + c : p.dw + ((int64_t)co * 9 + tap) * p.Cin + ci0 + c;
 #pragma unroll
           for (int j = 0; j < 32; j++)
             if (ci0 + c + j < p.Cin) atomicAdd(o + j, __uint_as_float(v[j]));
@@ -445,37 +464,69 @@ bool tc_available() {
   return true;
 }
 
+// cuTensorMapEncodeTiled costs ~1-2 us of host time; the decoder issues ~600 skinny GEMMs per step with a handful
+// of distinct (pointer, shape) combinations per step index, so encoded maps are cached.
+struct MapKey {
+  const void* base; int rank; cuuint64_t dims[4]; cuuint64_t str[3]; cuuint32_t box[4];
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; i++) { h ^= w[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                     const cuuint32_t* box) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank;
+  for (int i = 0; i < rank; i++) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; i++) key.str[i] = strides_bytes[i];
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) { *m = it->second; return LO_OK; }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LO_ECUDA, "%s: cuTensorMapEncodeTiled failed (%ld)", "tc", (long)r);
+  if (g_map_cache.size() > 20000) g_map_cache.clear();
+  g_map_cache.emplace(key, *m);
   return LO_OK;
 }
 
 template <int NT, int STAGES>
-static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, int splits, cudaStream_t st) {
   using SM = TcSmem<NT, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     LO_CUDA(cudaFuncSetAttribute(tc_gemm_conv_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
-  dim3 grid(cdiv(p.N, NT), mtiles);
+  dim3 grid(cdiv(p.N, NT), mtiles, splits);
   tc_gemm_conv_kernel<NT, STAGES><<<grid, TC_THREADS, SM::TOTAL, st>>>(mA, mB, p);
   LO_LAUNCH_OK();
   return LO_OK;
 }
 
-static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, cudaStream_t st) {
-  if (p.N <= 64) return launch_tc<64, 4>(mA, mB, p, mtiles, st);
-  return launch_tc<128, 3>(mA, mB, p, mtiles, st);
+static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, TcParams& p, int mtiles, int splits, int nt, cudaStream_t st) {
+  const int KB = p.K / TC_BK;
+  if (splits < 1) splits = 1;
+  if (splits > KB) splits = KB;
+  p.kb_per_split = cdiv(KB, splits);
+  splits = cdiv(KB, p.kb_per_split);
+  p.atomic = splits > 1 ? 1 : p.atomic;
+  if (nt == 64) return launch_tc<64, 4>(mA, mB, p, mtiles, splits, st);
+  return launch_tc<128, 3>(mA, mB, p, mtiles, splits, st);
 }
 
-int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
-               const float* bias, int accumulate, int relu, cudaStream_t st) {
+// splits > 1 (or atomic_acc): fp32 C only, partial sums are ADDED onto C with atomics (C must hold the base values)
+int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
+                  const float* bias, int accumulate, int relu, int splits, int atomic_acc, int small_n_tile, cudaStream_t st) {
   if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
   LO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "K%64, N%8, ld%8");
   LO_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0, "16-byte alignment");
@@ -486,18 +537,24 @@ int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, 
     cuuint32_t box[2] = {64, 128};
     LO_TRY(make_map(&mA, A, 2, dims, str, box));
   }
-  const int NT = N <= 64 ? 64 : 128;
+  const int NT = (N <= 64 || small_n_tile) ? 64 : 128;
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t str[1] = {(cuuint64_t)ldw * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)NT};
     LO_TRY(make_map(&mB, W, 2, dims, str, box));
   }
+  LO_CHECK_ARG(!(splits > 1 || atomic_acc) || (dtC == LO_F32 && !relu), "split-K needs fp32 output without ReLU");
   TcParams p{};
   p.M = M; p.N = N; p.K = K; p.conv = 0;
   p.bias = bias; p.mask = nullptr; p.out = C; p.ldc = ldc;
-  p.out_f32 = (dtC == LO_F32); p.accumulate = accumulate; p.relu = relu;
-  return launch_tc_any(mA, mB, p, cdiv(M, TC_BM), st);
+  p.out_f32 = (dtC == LO_F32); p.accumulate = accumulate; p.relu = relu; p.atomic = atomic_acc;
+  return launch_tc_any(mA, mB, p, cdiv(M, TC_BM), splits, NT, st);
+}
+
+int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
+               const float* bias, int accumulate, int relu, cudaStream_t st) {
+  return tc_gemm_nt_ex(A, lda, W, ldw, C, dtC, ldc, M, N, K, bias, accumulate, relu, 1, 0, 0, st);
 }
 
 int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask, bf16* y, int N, int H, int W, int Cin, int Cout,
@@ -530,7 +587,7 @@ int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask
   p.out_f32 = 0; p.accumulate = 0; p.relu = relu;
   const int mtiles = N * p.tiles_w * p.tiles_h;
   LO_CHECK_ARG(mtiles <= 65535, "too many M tiles for grid.y");
-  return launch_tc_any(mA, mB, p, mtiles, st);
+  return launch_tc_any(mA, mB, p, mtiles, 1, NT, st);
 }
 
 
@@ -584,6 +641,43 @@ int tc_conv3x3_wgrad(const bf16* x, const bf16* dy, float* dw, int N, int H, int
   dim3 grid((Cout / 128) * p.ci_tiles, 9, splits);
   if (NT == 128) return launch_wgrad<128, 3>(mDY, mX, p, grid, st);
   return launch_wgrad<64, 4>(mDY, mX, p, grid, st);
+}
+
+// C[M][N] (fp32, ldc) += A[K][M]^T * B[K][N]; A, B bf16 row-major.  C must hold the values to accumulate onto
+// (zero it for a plain product): split-K partial sums land with fp32 atomics.
+int tc_gemm_tn(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
+  LO_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "lda%8, ldb%8");
+  LO_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "16-byte alignment");
+  CUtensorMap mA, mB;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)K};
+    cuuint64_t str[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t box[2] = {64, 128};
+    LO_TRY(make_map(&mA, A, 2, dims, str, box));
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)K};
+    cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t box[2] = {64, 128};
+    LO_TRY(make_map(&mB, B, 2, dims, str, box));
+  }
+  WgParams p{};
+  p.plain = 1; p.Cout = M; p.Cin = N; p.dw = C; p.ldc = ldc;
+  p.tiles_w = p.tiles_h = 1; p.BW = 128; p.BH = 1;
+  p.kstages = cdiv(K, 128);
+  const int NT = N > 64 ? 128 : 64;
+  p.ci_tiles = cdiv(N, NT);
+  const int mt = cdiv(M, 128);
+  const int tiles = mt * p.ci_tiles;
+  int splits = cdiv(148 * 2, tiles);
+  if (splits > p.kstages) splits = p.kstages;
+  if (splits < 1) splits = 1;
+  p.per_split = cdiv(p.kstages, splits);
+  splits = cdiv(p.kstages, p.per_split);
+  dim3 grid(mt * p.ci_tiles, 1, splits);
+  if (NT == 128) return launch_wgrad<128, 3>(mA, mB, p, grid, st);
+  return launch_wgrad<64, 4>(mA, mB, p, grid, st);
 }
 
 }  // namespace lo

@@ -272,6 +272,10 @@ class DecoderWithAttention(nn.Module):
             a.g_w_fc, a.g_b_fc = Gd("fc.weight"), Gd("fc.bias")
         if dalpha_ext is not None:
             a.dalpha_ext = dalpha_ext.data_ptr()
+        if a.impl == _lib.LO_IMPL_TC:
+            if "bfwork" not in t:
+                t["bfwork"] = torch.zeros(int(_lib.lib().lo_decoder_bfwork_bytes(ctypes.byref(a))), dtype=torch.uint8, device=S.device)
+            a.bfwork = t["bfwork"].data_ptr()
         ws["args"] = a
         return a
 
