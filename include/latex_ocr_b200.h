@@ -37,6 +37,9 @@ int lo_version(void);
 const char* lo_last_error(void);
 /* number of kernels launched through this library since load (bench.py's gpu_launches) */
 int64_t lo_launch_count(void);
+/* tuning knobs: "att_pipe" (1: TMA-pipelined attention kernels, 0: register-streaming), "att_policy_enc" /
+ * "att_policy_att1" (L2 policy 0 normal, 1 evict_last, 2 evict_first), "att_nsplit" (0 = automatic) */
+int lo_set_option(const char* name, int value);
 /* 1 if the tcgen05/TMA kernels are built in and the current device is sm_100 */
 int lo_tc_available(void);
 

@@ -1,0 +1,463 @@
+// Attention step kernels, version 2: the att1 / enc row streams go through a TMA bulk-copy (cp.async.bulk) ->
+// shared-memory ring fed by a dedicated producer warp, so the bytes in flight per SM (2 CTAs x 3 stages x 32 KB)
+// no longer depend on register-limited occupancy.  Same math, same combine order, same outputs as the register
+// versions in lo_decoder.cu (attention_fwd_kernel / attention_bwd_kernel), which remain the fallback.
+//   forward : e_r = w . relu(att1_r + att2) ; online softmax ; ctx = sum_r alpha_r enc_r      (seq2seq_torch.py:186-190)
+//   backward: dalpha_r = <dctx, enc_r> + dreg_r ; de_r = alpha_r (dalpha_r - s) ; datt2 = w * sum_r de_r [att1_r + att2 > 0]
+// L2 policy: enc is read again by the next step (and by the backward) -> evict_last; att1 likewise is re-read every
+// step; which of the two to pin is a run-time option (lo_set_option) because together they are as large as the L2.
+#include "lo_common.cuh"
+#include "lo_ptx.cuh"
+
+namespace lo {
+
+int g_opt_att_pipe = 1;
+int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
+int g_opt_att_policy_att1 = 2;
+int g_opt_att_nsplit = 0;        // 0 = automatic
+
+#define AP_THREADS 288
+#define AP_CWARPS 8
+#define AP_STAGES 3
+#define AP_MAXSPLIT 16
+
+__device__ __forceinline__ uint64_t make_policy(int kind) {
+  return kind == 1 ? l2_policy_evict_last() : (kind == 2 ? l2_policy_evict_first() : l2_policy_evict_normal());
+}
+
+template <typename T, int NV>
+struct ApCfg {
+  static constexpr int CH = NV * 256;
+  static constexpr int RPW = (sizeof(T) == 2 && NV <= 2) ? 2 : 1;       // rows per consumer warp per stage
+  static constexpr int ROWS = AP_CWARPS * RPW;
+  static constexpr int HALF_ELEMS = ROWS * CH;                          // att1 part | enc part
+  static constexpr int STAGE_BYTES = 2 * HALF_ELEMS * (int)sizeof(T);
+  static constexpr int SMEM = AP_STAGES * STAGE_BYTES + 128;
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
+    const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
+    const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
+    float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
+    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, int pol_att1) {
+  using C = ApCfg<T, NV>;
+  constexpr int CH = C::CH;
+  extern __shared__ __align__(128) uint8_t ap_smem[];
+  T* ring = reinterpret_cast<T*>(ap_smem);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + AP_STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + AP_STAGES;
+  __shared__ float s_m[AP_CWARPS], s_l[AP_CWARPS];
+  __shared__ float s_scale[AP_MAXSPLIT];
+  __shared__ float s_ML[2];
+  __shared__ int s_last;
+
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rps = (R + nsplit - 1) / nsplit;
+  const int r0 = sp * rps, r1 = min(R, r0 + rps);
+  const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
+  const T* a1b = att1 + (int64_t)b * R * CH;
+  const T* eb = enc + (int64_t)b * R * CH;
+  float* alb = alpha + (int64_t)b * alpha_stride;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AP_STAGES; s++) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, AP_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  float m = -INFINITY, l = 0.f;
+  float acc[NV * 8];
+#pragma unroll
+  for (int i = 0; i < NV * 8; i++) acc[i] = 0.f;
+
+  if (wid == AP_CWARPS) {
+    // ===== producer warp: one lane issues the bulk copies =====
+    if (lane == 0) {
+      const uint64_t pe = make_policy(pol_enc), pa = make_policy(pol_att1);
+      for (int i = 0; i < nst; i++) {
+        const int s = i % AP_STAGES;
+        const uint32_t ph = (i / AP_STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        const int row = r0 + i * C::ROWS;
+        const int rows = min(C::ROWS, r1 - row);
+        const uint32_t bytes = (uint32_t)rows * CH * (uint32_t)sizeof(T);
+        T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
+        mbar_expect_tx(full_bar + s, 2 * bytes);
+        bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
+        bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
+      }
+    }
+  } else {
+    // ===== consumer warps =====
+    float a2[NV * 8], wv[NV * 8];
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
+      ld8(wf + (j * 32 + lane) * 8, wv + j * 8);
+    }
+    for (int i = 0; i < nst; i++) {
+      const int s = i % AP_STAGES;
+      const uint32_t ph = (i / AP_STAGES) & 1;
+      const int row = r0 + i * C::ROWS;
+      const int rows = min(C::ROWS, r1 - row);
+      mbar_wait(full_bar + s, ph);
+      const T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
+      const T* se = sa + C::HALF_ELEMS;
+      const int ra = wid, rb = wid + AP_CWARPS;
+      const bool one = ra < rows;
+      const bool two = (C::RPW == 2) && (rb < rows);
+      if (one) {
+        float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          float v[8];
+          ld8(sa + (size_t)ra * CH + (j * 32 + lane) * 8, v);
+#pragma unroll
+          for (int q = 0; q < 8; q++) e0 = fmaf(wv[j * 8 + q], fmaxf(v[q] + a2[j * 8 + q], 0.f), e0);
+          if (two) {
+            ld8(sa + (size_t)rb * CH + (j * 32 + lane) * 8, v);
+#pragma unroll
+            for (int q = 0; q < 8; q++) e1 = fmaf(wv[j * 8 + q], fmaxf(v[q] + a2[j * 8 + q], 0.f), e1);
+          }
+        }
+        e0 = warp_sum(e0);
+        e1 = warp_sum(e1);
+        if (lane == 0) {
+          alb[row + ra] = e0;
+          if (two) alb[row + rb] = e1;
+        }
+        const float mn = two ? fmaxf(m, fmaxf(e0, e1)) : fmaxf(m, e0);
+        const float sc = expf(m - mn);
+        const float p0 = expf(e0 - mn);
+        const float p1 = two ? expf(e1 - mn) : 0.f;
+        l = l * sc + p0 + p1;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          float u[8];
+          ld8(se + (size_t)ra * CH + (j * 32 + lane) * 8, u);
+#pragma unroll
+          for (int q = 0; q < 8; q++) acc[j * 8 + q] = fmaf(p0, u[q], acc[j * 8 + q] * sc);
+          if (two) {
+            ld8(se + (size_t)rb * CH + (j * 32 + lane) * 8, u);
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc[j * 8 + q] = fmaf(p1, u[q], acc[j * 8 + q]);
+          }
+        }
+        m = mn;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + s);
+    }
+  }
+  __syncthreads();     // every TMA write has landed and been consumed: the ring can be reused for the combine
+  float* s_acc = reinterpret_cast<float*>(ap_smem);          // [AP_CWARPS][CH]
+  if (wid < AP_CWARPS) {
+    if (lane == 0) { s_m[wid] = m; s_l[wid] = l; }
+#pragma unroll
+    for (int j = 0; j < NV; j++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) s_acc[wid * CH + (j * 32 + lane) * 8 + i] = acc[j * 8 + i];
+  }
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < AP_CWARPS; w++) M = fmaxf(M, s_m[w]);
+  float L = 0.f;
+  float wsc[AP_CWARPS];
+#pragma unroll
+  for (int w = 0; w < AP_CWARPS; w++) {
+    wsc[w] = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - M);
+    L += s_l[w] * wsc[w];
+  }
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < AP_CWARPS; w++) t = fmaf(s_acc[w * CH + c], wsc[w], t);
+    part[2 + c] = t;
+  }
+  if (threadIdx.x == 0) { part[0] = M; part[1] = L; }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + b, 1);
+    s_last = (ticket == nsplit - 1);
+    if (s_last) counters[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = partials + (int64_t)b * nsplit * (CH + 2);
+  if (threadIdx.x == 0) {
+    float Mg = -INFINITY;
+    for (int s = 0; s < nsplit; s++) Mg = fmaxf(Mg, __ldcg(pb + (int64_t)s * (CH + 2)));
+    float Lg = 0.f;
+    for (int s = 0; s < nsplit; s++) {
+      const float ms = __ldcg(pb + (int64_t)s * (CH + 2));
+      const float scl = (ms == -INFINITY) ? 0.f : expf(ms - Mg);
+      s_scale[s] = scl;
+      Lg += __ldcg(pb + (int64_t)s * (CH + 2) + 1) * scl;
+    }
+    s_ML[0] = Mg;
+    s_ML[1] = 1.0f / Lg;
+  }
+  __syncthreads();
+  const float Mg = s_ML[0], invL = s_ML[1];
+  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    float t = 0.f;
+    for (int s = 0; s < nsplit; s++) t = fmaf(__ldcg(pb + (int64_t)s * (CH + 2) + 2 + c), s_scale[s], t);
+    t *= invL;
+    ctx[(int64_t)b * CH + c] = t;
+    if (gate_pre) {
+      const float g = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
+      gate_pre[(int64_t)b * gate_stride + c] = g;
+      gctx[(int64_t)b * CH + c] = g * t;
+      if (gctx_bf) gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(g * t);
+    }
+  }
+  for (int r = threadIdx.x; r < R; r += AP_THREADS) alb[r] = expf(__ldcg(alb + r) - Mg) * invL;
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
+    const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, const float* __restrict__ gate,
+    int64_t o1_stride, const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride,
+    const float* __restrict__ ctx, const float* __restrict__ dgctx, int64_t dg_stride, const float* __restrict__ dreg,
+    int64_t dreg_stride, const float* __restrict__ sreg, int64_t sreg_stride, float* __restrict__ de, float* __restrict__ datt2,
+    float* __restrict__ dgp, int64_t dcat_stride, bf16* __restrict__ datt2_bf, bf16* __restrict__ dgp_bf,
+    float* __restrict__ dctx_out, int R, int nsplit, int* __restrict__ counters, float* __restrict__ partials, int pol_enc,
+    int pol_att1) {
+  using C = ApCfg<T, NV>;
+  constexpr int CH = C::CH;
+  extern __shared__ __align__(128) uint8_t ap_smem[];
+  T* ring = reinterpret_cast<T*>(ap_smem);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + AP_STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + AP_STAGES;
+  __shared__ int s_last;
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rps = (R + nsplit - 1) / nsplit;
+  const int r0 = sp * rps, r1 = min(R, r0 + rps);
+  const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
+  const T* a1b = att1 + (int64_t)b * R * CH;
+  const T* eb = enc + (int64_t)b * R * CH;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AP_STAGES; s++) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, AP_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  float macc[NV * 8];
+#pragma unroll
+  for (int i = 0; i < NV * 8; i++) macc[i] = 0.f;
+
+  if (wid == AP_CWARPS) {
+    if (lane == 0) {
+      const uint64_t pe = make_policy(pol_enc), pa = make_policy(pol_att1);
+      for (int i = 0; i < nst; i++) {
+        const int s = i % AP_STAGES;
+        const uint32_t ph = (i / AP_STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        const int row = r0 + i * C::ROWS;
+        const int rows = min(C::ROWS, r1 - row);
+        const uint32_t bytes = (uint32_t)rows * CH * (uint32_t)sizeof(T);
+        T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
+        mbar_expect_tx(full_bar + s, 2 * bytes);
+        bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
+        bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
+      }
+    }
+  } else {
+    float a2[NV * 8], dc[NV * 8];
+    float sdot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const int c0 = (j * 32 + lane) * 8;
+      float g[8], cx[8], dg[8], gp[8];
+      ld8(att2 + (int64_t)b * o1_stride + c0, a2 + j * 8);
+      ld8(gate + (int64_t)b * o1_stride + c0, g);
+      ld8(ctx + (int64_t)b * CH + c0, cx);
+      ld8(dgctx + (int64_t)b * dg_stride + c0, dg);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        dc[j * 8 + i] = dg[i] * g[i];
+        sdot = fmaf(dc[j * 8 + i], cx[i], sdot);
+        gp[i] = dg[i] * cx[i] * g[i] * (1.f - g[i]);
+      }
+      if (sp == 0 && wid == 0) {
+        st8(dgp + (int64_t)b * dcat_stride + c0, gp);
+        if (dgp_bf) st8(dgp_bf + (int64_t)b * dcat_stride + c0, gp);
+        st8(dctx_out + (int64_t)b * CH + c0, dc + j * 8);
+      }
+    }
+    const float sall = warp_sum(sdot) + sreg[(int64_t)b * sreg_stride];
+    const float* alb = alpha + (int64_t)b * alpha_stride;
+    float* deb = de + (int64_t)b * alpha_stride;
+    const float* drb = dreg + (int64_t)b * dreg_stride;
+    for (int i = 0; i < nst; i++) {
+      const int s = i % AP_STAGES;
+      const uint32_t ph = (i / AP_STAGES) & 1;
+      const int row = r0 + i * C::ROWS;
+      const int rows = min(C::ROWS, r1 - row);
+      mbar_wait(full_bar + s, ph);
+      const T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
+      const T* se = sa + C::HALF_ELEMS;
+      const int ra = wid, rb = wid + AP_CWARPS;
+      const bool one = ra < rows;
+      const bool two = (C::RPW == 2) && (rb < rows);
+      if (one) {
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          float u[8];
+          ld8(se + (size_t)ra * CH + (j * 32 + lane) * 8, u);
+#pragma unroll
+          for (int q = 0; q < 8; q++) d0 = fmaf(dc[j * 8 + q], u[q], d0);
+          if (two) {
+            ld8(se + (size_t)rb * CH + (j * 32 + lane) * 8, u);
+#pragma unroll
+            for (int q = 0; q < 8; q++) d1 = fmaf(dc[j * 8 + q], u[q], d1);
+          }
+        }
+        d0 = warp_sum(d0);
+        d1 = warp_sum(d1);
+        const float de0 = alb[row + ra] * (d0 + drb[row + ra] - sall);
+        const float de1 = two ? alb[row + rb] * (d1 + drb[row + rb] - sall) : 0.f;
+        if (lane == 0) {
+          deb[row + ra] = de0;
+          if (two) deb[row + rb] = de1;
+        }
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          float v[8];
+          ld8(sa + (size_t)ra * CH + (j * 32 + lane) * 8, v);
+#pragma unroll
+          for (int q = 0; q < 8; q++) macc[j * 8 + q] += (v[q] + a2[j * 8 + q] > 0.f) ? de0 : 0.f;
+          if (two) {
+            ld8(sa + (size_t)rb * CH + (j * 32 + lane) * 8, v);
+#pragma unroll
+            for (int q = 0; q < 8; q++) macc[j * 8 + q] += (v[q] + a2[j * 8 + q] > 0.f) ? de1 : 0.f;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + s);
+    }
+  }
+  __syncthreads();
+  float* s_acc = reinterpret_cast<float*>(ap_smem);
+  if (wid < AP_CWARPS) {
+#pragma unroll
+    for (int j = 0; j < NV; j++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) s_acc[wid * CH + (j * 32 + lane) * 8 + i] = macc[j * 8 + i];
+  }
+  __syncthreads();
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < AP_CWARPS; w++) t += s_acc[w * CH + c];
+    part[2 + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + b, 1);
+    s_last = (ticket == nsplit - 1);
+    if (s_last) counters[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = partials + (int64_t)b * nsplit * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    float t = 0.f;
+    for (int sidx = 0; sidx < nsplit; sidx++) t += __ldcg(pb + (int64_t)sidx * (CH + 2) + 2 + c);
+    datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+    if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
+  }
+}
+
+int att_pipe_splits(int B) {
+  if (g_opt_att_nsplit > 0) return g_opt_att_nsplit > AP_MAXSPLIT ? AP_MAXSPLIT : g_opt_att_nsplit;
+  // two CTAs per SM resident: aim at ~2 full waves of 296 CTAs
+  int s = (592 + B - 1) / B;
+  if (s < 1) s = 1;
+  if (s > AP_MAXSPLIT) s = AP_MAXSPLIT;
+  return s;
+}
+
+template <typename T, int NV>
+static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
+  using C = ApCfg<T, NV>;
+  static bool attr = false;
+  if (!attr) {
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr = true;
+  }
+  const int ns = att_pipe_splits(x.B);
+  attention_fwd_pipe_kernel<T, NV><<<dim3(ns, x.B), AP_THREADS, C::SMEM, st>>>(
+      (const T*)x.att1, (const T*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride,
+      x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st) {
+  if (dt == LO_F32) {
+    if (C == 256) return fwd_launch<float, 1>(x, st);
+    if (C == 512) return fwd_launch<float, 2>(x, st);
+    return fwd_launch<float, 4>(x, st);
+  }
+  if (C == 256) return fwd_launch<bf16, 1>(x, st);
+  if (C == 512) return fwd_launch<bf16, 2>(x, st);
+  return fwd_launch<bf16, 4>(x, st);
+}
+
+template <typename T, int NV>
+static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
+  using C = ApCfg<T, NV>;
+  static bool attr = false;
+  if (!attr) {
+    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr = true;
+  }
+  const int ns = att_pipe_splits(x.B);
+  attention_bwd_pipe_kernel<T, NV><<<dim3(ns, x.B), AP_THREADS, C::SMEM, st>>>(
+      (const T*)x.att1, (const T*)x.enc, x.att2, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride,
+      x.dreg, x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,
+      (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
+int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st) {
+  if (dt == LO_F32) {
+    if (C == 256) return bwd_launch<float, 1>(x, st);
+    if (C == 512) return bwd_launch<float, 2>(x, st);
+    return bwd_launch<float, 4>(x, st);
+  }
+  if (C == 256) return bwd_launch<bf16, 1>(x, st);
+  if (C == 512) return bwd_launch<bf16, 2>(x, st);
+  return bwd_launch<bf16, 4>(x, st);
+}
+
+}  // namespace lo
+
+extern "C" int lo_set_option(const char* name, int value) {
+  if (!name) return LO_EINVAL;
+  if (!strcmp(name, "att_pipe")) lo::g_opt_att_pipe = value;
+  else if (!strcmp(name, "att_policy_enc")) lo::g_opt_att_policy_enc = value;
+  else if (!strcmp(name, "att_policy_att1")) lo::g_opt_att_policy_att1 = value;
+  else if (!strcmp(name, "att_nsplit")) lo::g_opt_att_nsplit = value;
+  else return lo::fail(LO_EINVAL, "lo_set_option: unknown option %s", name);
+  return LO_OK;
+}

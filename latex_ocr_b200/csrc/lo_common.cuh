@@ -129,6 +129,30 @@ int gemm_nn(const void* A, int dtA, int64_t lda, const void* B, int dtB, int64_t
             int M, int N, int K, int accumulate, int impl, cudaStream_t st);
 int colsum(const void* X, int dt, float* out, int M, int N, int64_t ld, int accumulate, cudaStream_t st);
 
+// attention step kernels, TMA-pipelined version (lo_attention.cu)
+struct AttFwdArgs {
+  const void *att1, *enc;
+  const float* att2; int64_t att2_stride;
+  const float* wf;
+  float* alpha; int64_t alpha_stride;
+  float* ctx; float* gate_pre; int64_t gate_stride; float* gctx; bf16* gctx_bf;
+  int B, R;
+  void* work;
+};
+struct AttBwdArgs {
+  const void *att1, *enc;
+  const float *att2, *gate; int64_t o1_stride;
+  const float* wf; const float* alpha; int64_t alpha_stride;
+  const float* ctx; const float* dgctx; int64_t dg_stride;
+  const float* dreg; int64_t dreg_stride; const float* sreg; int64_t sreg_stride;
+  float* de; float* datt2; float* dgp; int64_t dcat_stride; bf16* datt2_bf; bf16* dgp_bf; float* dctx_out;
+  int B, R;
+  void* work;
+};
+extern int g_opt_att_pipe;
+int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st);
+int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st);
+
 // tcgen05 paths (lo_tc.cu)
 bool tc_available();
 int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc,

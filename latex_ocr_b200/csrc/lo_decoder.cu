@@ -676,6 +676,10 @@ static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a
 static int attention_forward_launch(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                                     const float* wf, float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre,
                                     int64_t gate_stride, float* gctx, bf16* gctx_bf, int B, int R, int C, void* work, cudaStream_t st) {
+  if (g_opt_att_pipe) {
+    AttFwdArgs x{att1, enc, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, B, R, work};
+    return attention_fwd_pipe(x, dt, C, st);
+  }
   const int ns = att_splits(B);
   int* cnt = (int*)work;
   float* part = (float*)((char*)work + 4096);
@@ -906,6 +910,13 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
       LO_TRY(gemm_nt(dcat_t + d.A + d.C, LO_F32, d.O1, a->wbwd1, dt, d.G, a->dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 0,
                      0, LO_IMPL_SIMT, st));
     }
+    if (g_opt_att_pipe) {
+      AttBwdArgs x{a->att1, a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+                   a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T,
+                   a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr,
+                   a->dctx + (int64_t)t * d.B * d.C, nrows, d.R, a->work};
+      LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
+    } else {
     dim3 grid(ns, nrows);
 #define LO_ATT_BWD(TY_, NV)                                                                                                       \
   attention_bwd_kernel<TY_, NV><<<grid, LO_ATT_THREADS, 0, st>>>(                                                                 \
@@ -919,6 +930,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     }
 #undef LO_ATT_BWD
     LO_LAUNCH_OK();
+    }
     // dh_prev += [datt2 | dgate_pre] @ [W_d ; W_beta]
     if (bv.on) {
       LO_TRY(tc_gemm_nt_ex(dcat_bf_t, d.O1, (const bf16*)a->wbwd2, d.A + d.C, a->dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C,

@@ -175,10 +175,13 @@ def test_maxpool(k):
     assert relerr(dx.permute(0, 3, 1, 2), want) < 1e-6
 
 
+@pytest.mark.parametrize("pipe", [0, 1])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,R", [(3, 37), (8, 180), (64, 868)])
-def test_attention_forward(dtype, B, R):
+@pytest.mark.parametrize("B,R", [(3, 37), (8, 180), (64, 868), (2, 5)])
+def test_attention_forward(dtype, B, R, pipe):
+    """pipe=1: TMA bulk-copy -> smem ring version (lo_attention.cu); pipe=0: register-streaming version."""
     _lib, L = _L()
+    _lib.set_option("att_pipe", pipe)
     torch.manual_seed(6)
     C = A = 512
     enc = torch.randn(B, R, C, device="cuda").to(dtype)
@@ -204,6 +207,7 @@ def test_attention_forward(dtype, B, R):
     assert relerr(ctx, cx.float()) < 2e-5
     assert relerr(gate_pre, torch.sigmoid(gp0)) < 1e-6
     assert relerr(gctx, (torch.sigmoid(gp0.double()) * cx).float()) < 2e-5
+    _lib.set_option("att_pipe", 1)
 
 
 def test_adam_matches_torch():

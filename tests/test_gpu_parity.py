@@ -123,7 +123,7 @@ def test_train_step_fp32_vs_oracle_all_gradients():
                 continue          # gradient is exactly 0 here, rounding noise (1e-9) in the reference -> Adam moves the
                                   # reference's copy by ~lr; the softmax is invariant to this bias, no output depends on it
             d = (v.cpu() - ref[k]).abs()
-            assert d.max().item() <= 1.01e-3, k
+            assert d.max().item() <= 2.02e-3, k      # a sign flip of a rounding-level gradient moves a weight by 2*lr
             assert (d > 5e-5).float().mean().item() < 1e-3, k
 
 
@@ -194,3 +194,26 @@ def test_getloss_surface_and_state_dict_roundtrip(tmp_path):
         assert torch.equal(t, m2.decoder.state_dict()[k])
     assert set(m.encoder.state_dict().keys()) == set(pe.keys())
     assert set(m.decoder.state_dict().keys()) == set(pd.keys())
+
+
+def test_attention_kernel_versions_agree_on_a_full_step():
+    """Register-streaming (att_pipe=0) and TMA-pipelined (att_pipe=1) attention kernels give the same loss/gradients."""
+    from latex_ocr_b200 import _lib
+    rm = _oracle()
+    V = 60
+    pe, pd = rm.init_params(V, seed=15)
+    img, formula = rm.synthetic_batch(3, 40, 72, V, 4, 9, seed=16)
+    B, T = formula.shape[0], formula.shape[1] - 1
+    res = {}
+    try:
+        for pipe in (0, 1):
+            _lib.set_option("att_pipe", pipe)
+            m = build_model(V, pe, pd, "fp32")
+            loss = m._step_body(img.cuda(), formula.cuda(), [T] * B, None)
+            torch.cuda.synchronize()
+            res[pipe] = (loss[0].item(), m.decoder.store.grad.clone(), m.encoder.store.grad.clone())
+    finally:
+        _lib.set_option("att_pipe", 1)
+    assert abs(res[0][0] - res[1][0]) / abs(res[0][0]) < 1e-6
+    for i in (1, 2):
+        assert (res[0][i] - res[1][i]).abs().max().item() <= 1e-4 * res[0][i].abs().max().item() + 1e-8
