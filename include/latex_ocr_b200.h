@@ -116,9 +116,9 @@ typedef struct lo_decoder_args {
   int32_t dt;              /* storage of enc/att1/weight shadows */
   int32_t impl;            /* LO_IMPL_SIMT | LO_IMPL_TC for the hoisted GEMMs */
   int32_t has_dropout;     /* 0: eval ; 1: multiply h by dropout_mask before fc */
-  int32_t reserved0;
+  int32_t ldl;             /* row stride of logits/dlogits (>= V; a multiple of 64 enables the tcgen05 fc GEMMs); 0 -> V */
   float alpha_c;           /* doubly-stochastic regulariser weight (img2seq_torch.py:157) */
-  float reserved1;
+  int32_t rows_per_img;    /* decode only: consecutive rows that share one image (beam size); 0/1 for training */
   const int32_t* bt_host;  /* HOST int[T]: rows active at step t (seq2seq_torch.py:308); non-increasing */
   const int64_t* caps;     /* [B][caps_stride] token ids (sorted rows) */
   int64_t caps_stride;
@@ -150,12 +150,12 @@ typedef struct lo_decoder_args {
   float* gtmp;             /* [B][4D] scratch */
   const float* dropout_mask; /* [B][T][D] multipliers or NULL */
   float* hd;               /* [B][T][D] h after dropout */
-  float* logits;           /* [B][T][V]  (== predictions) */
+  float* logits;           /* [B][T][ldl]  (== predictions in the first V columns) */
   /* loss */
   float* row_loss;         /* [B*T] */
   float* loss;             /* [4]: total, ce, reg, n_valid */
   /* backward state */
-  float* dlogits;          /* [B][T][V] */
+  float* dlogits;          /* [B][T][ldl] */
   float* dhd;              /* [B][T][D] */
   float* dreg;             /* [B][R] gradient of the regulariser w.r.t. alpha (same for every t) */
   const float* dalpha_ext; /* optional external d loss/d alphas [B][T][R] (generic autograd mode); overrides dreg */
@@ -196,6 +196,17 @@ int lo_decoder_pack_bwd_weights(const lo_decoder_args* a, void* stream);
  * greedy_decoder_cell.py:46-66): tokens out [B][max_steps] int64, first input token = start_id */
 int lo_decoder_greedy(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps,
                       int64_t* tokens, int32_t* finished, void* stream);
+/* greedy: tokens [B][max_steps]; fin_hist (optional) [B][max_steps] int32 = finished flag after each step */
+int lo_decoder_greedy_hist(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps,
+                           int64_t* tokens, int32_t* finished, int32_t* fin_hist, void* stream);
+
+/* beam search on the same step kernels: beam_search_decoder_cell.py:98-187 (log-softmax, finished mask with
+ * dtype.min, only beam 0 at time 0, top-k over beam*V with the lower index winning ties, state gather by parents;
+ * no length normalisation, diversity penalty off as in configs/model.json:15-16).  a->B = n_img*beam rows,
+ * a->rows_per_img = beam, a->enc holds n_img images.  ids/parents out [n_img][max_steps][beam] int64,
+ * fin_hist [n_img][max_steps][beam] int32 (finished flags after each step), logp [n_img][beam] final scores. */
+int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* ids,
+                    int64_t* parents, int32_t* fin_hist, float* logp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimiser: torch.optim.Adam defaults (img2seq_torch.py:86-87, :168-170) on one flat buffer.

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
     float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
-    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, int pol_att1) {
+    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, int pol_att1, int rpi) {
   using C = ApCfg<T, NV>;
   constexpr int CH = C::CH;
   extern __shared__ __align__(128) uint8_t ap_smem[];
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   const int rps = (R + nsplit - 1) / nsplit;
   const int r0 = sp * rps, r1 = min(R, r0 + rps);
   const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
-  const T* a1b = att1 + (int64_t)b * R * CH;
-  const T* eb = enc + (int64_t)b * R * CH;
+  const T* a1b = att1 + (int64_t)(b / rpi) * R * CH;      // beam search: rpi consecutive rows attend over one image
+  const T* eb = enc + (int64_t)(b / rpi) * R * CH;
   float* alb = alpha + (int64_t)b * alpha_stride;
 
   if (threadIdx.x == 0) {
@@ -388,8 +388,10 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
 
 int att_pipe_splits(int B) {
   if (g_opt_att_nsplit > 0) return g_opt_att_nsplit > AP_MAXSPLIT ? AP_MAXSPLIT : g_opt_att_nsplit;
-  // two CTAs per SM resident: aim at ~2 full waves of 296 CTAs
-  int s = (592 + B - 1) / B;
+  // two CTAs per SM are resident (smem): one full wave of <= 296 CTAs.  Measured at B=64, R=868 (bf16): 4 splits
+  // (256 CTAs, 14 stages each) 25.9 us vs 9 splits (576 CTAs = 2 waves) 32.8 us — per-CTA start-up/combine
+  // costs dominate short CTAs (profiles/r1_attention_nsplit_sweep.txt)
+  int s = 296 / B;
   if (s < 1) s = 1;
   if (s > AP_MAXSPLIT) s = AP_MAXSPLIT;
   return s;
@@ -406,7 +408,8 @@ static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
   const int ns = att_pipe_splits(x.B);
   attention_fwd_pipe_kernel<T, NV><<<dim3(ns, x.B), AP_THREADS, C::SMEM, st>>>(
       (const T*)x.att1, (const T*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride,
-      x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1);
+      x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1,
+      x.rows_per_img > 1 ? x.rows_per_img : 1);
   LO_LAUNCH_OK();
   return LO_OK;
 }

@@ -138,6 +138,7 @@ struct AttFwdArgs {
   float* ctx; float* gate_pre; int64_t gate_stride; float* gctx; bf16* gctx_bf;
   int B, R;
   void* work;
+  int rows_per_img;
 };
 struct AttBwdArgs {
   const void *att1, *enc;

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_fwd_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
     float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
-    int* __restrict__ counters, float* __restrict__ partials) {
+    int* __restrict__ counters, float* __restrict__ partials, int rpi) {
   constexpr int CH = NV * 256;   // A == C == CH
   const int b = blockIdx.y, sp = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_fwd_kernel(
     for (int i = 0; i < 8; i++) acc[j * 8 + i] = 0.f;
   }
   float m = -INFINITY, l = 0.f;
-  const T* a1b = att1 + (int64_t)b * R * CH;
-  const T* eb = enc + (int64_t)b * R * CH;
+  const T* a1b = att1 + (int64_t)(b / rpi) * R * CH;
+  const T* eb = enc + (int64_t)(b / rpi) * R * CH;
   float* alb = alpha + (int64_t)b * alpha_stride;
   for (int r = r0 + wid; r < r1; r += 2 * LO_ATT_WARPS) {
     const int rb = r + LO_ATT_WARPS;
@@ -362,11 +362,11 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
 // small pointwise / reduction kernels
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void mean_rows_kernel(const T* __restrict__ enc, float* __restrict__ mean, int R, int C) {
+__global__ void mean_rows_kernel(const T* __restrict__ enc, float* __restrict__ mean, int R, int C, int rpi) {
   const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
-  for (int r = 0; r < R; r++) s += ldf(enc + ((int64_t)b * R + r) * C + c);
+  for (int r = 0; r < R; r++) s += ldf(enc + ((int64_t)(b / rpi) * R + r) * C + c);
   mean[(int64_t)b * C + c] = s / (float)R;
 }
 
@@ -443,16 +443,18 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_st
 // fused cross-entropy forward/backward: warp per (b,t) row.  target = caps[b][t+1]; rows with b >= bt[t] get 0.
 __global__ void ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ caps, int64_t caps_stride,
                           const int32_t* __restrict__ dlen, float* __restrict__ row_loss, float* __restrict__ dlogits,
-                          int B, int Tn, int V, float inv_n) {
+                          bf16* __restrict__ dlogits_bf, int B, int Tn, int V, int ld, float inv_n) {
   const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * Tn) return;
   const int b = row / Tn, t = row % Tn;
-  const float* lg = logits + (int64_t)row * V;
-  float* dl = dlogits ? dlogits + (int64_t)row * V : nullptr;
+  const float* lg = logits + (int64_t)row * ld;
+  float* dl = dlogits ? dlogits + (int64_t)row * ld : nullptr;
+  bf16* dlb = dlogits_bf ? dlogits_bf + (int64_t)row * ld : nullptr;
   if (t >= dlen[b]) {
     if (lane == 0) row_loss[row] = 0.f;
-    if (dl) for (int v = lane; v < V; v += 32) dl[v] = 0.f;
+    if (dl) for (int v = lane; v < ld; v += 32) dl[v] = 0.f;
+    if (dlb) for (int v = lane; v < ld; v += 32) dlb[v] = __float2bfloat16_rn(0.f);
     return;
   }
   float mx = -INFINITY;
@@ -467,7 +469,11 @@ __global__ void ce_kernel(const float* __restrict__ logits, const int64_t* __res
   if (tg >= V) tg = V - 1;
   if (lane == 0) row_loss[row] = lse - lg[tg];
   if (dl)
-    for (int v = lane; v < V; v += 32) dl[v] = (expf(lg[v] - lse) - (v == (int)tg ? 1.f : 0.f)) * inv_n;
+    for (int v = lane; v < ld; v += 32) {
+      const float g = v < V ? (expf(lg[v] - lse) - (v == (int)tg ? 1.f : 0.f)) * inv_n : 0.f;
+      dl[v] = g;
+      if (dlb) dlb[v] = __float2bfloat16_rn(g);
+    }
 }
 
 // doubly-stochastic regulariser: S = sum_t alpha ; sq -> row_loss tail ; dreg = -2 alpha_c (1-S)/(B R)
@@ -615,6 +621,107 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int V, int64_t* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// beam search step (beam_search_decoder_cell.py:123-187): one block per image.
+//   lp = log_softmax(logits) ; finished beams -> [END: 0, else: dtype.min] ; total = prev + lp ;
+//   time 0: beam 0 only ; top-k(beam) over beam*V (lower flat index wins ties) ; id = idx % V ; parent = idx / V
+// ------------------------------------------------------------------------------------------------
+#define LO_BEAM_MAX 16
+__global__ void __launch_bounds__(256) beam_step_kernel(const float* __restrict__ logits, int V, int beam, int t, int64_t end_id,
+                                                        float* __restrict__ logp, int32_t* __restrict__ finished,
+                                                        int64_t* __restrict__ ids, int64_t* __restrict__ parents,
+                                                        int32_t* __restrict__ fin_hist, int64_t* __restrict__ next_tok,
+                                                        int32_t* __restrict__ parent_rows, int max_steps) {
+  extern __shared__ float s_tot[];            // [beam*V]
+  __shared__ float s_red[8];
+  __shared__ int s_redi[8];
+  __shared__ float s_lse[LO_BEAM_MAX];
+  __shared__ float s_newp[LO_BEAM_MAX];
+  __shared__ int s_newi[LO_BEAM_MAX];
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int row0 = img * beam;
+  // log-sum-exp per beam row (warp w handles rows w, w+8, ...)
+  for (int k = wid; k < beam; k += 8) {
+    const float* lg = logits + (int64_t)(row0 + k) * V;
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, lg[v]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int v = lane; v < V; v += 32) se += expf(lg[v] - mx);
+    se = warp_sum(se);
+    if (lane == 0) s_lse[k] = mx + logf(se);
+  }
+  __syncthreads();
+  const int nb = (t == 0) ? 1 : beam;          // beam_search_decoder_cell.py:159-160
+  const int total = nb * V;
+  for (int i = tid; i < total; i += 256) {
+    const int k = i / V, v = i % V;
+    float lp = logits[(int64_t)(row0 + k) * V + v] - s_lse[k];
+    if (finished[row0 + k]) lp = (v == (int)end_id) ? 0.f : -3.4028234663852886e38f;   // mask_probs :353-367
+    s_tot[i] = logp[row0 + k] + lp;
+  }
+  __syncthreads();
+  for (int j = 0; j < beam; j++) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < total; i += 256) {
+      const float x = s_tot[i];
+      if (x > best || (x == best && i < bi)) { best = x; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_red[wid] = best; s_redi[wid] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float b2 = s_red[0];
+      int i2 = s_redi[0];
+      for (int w = 1; w < 8; w++)
+        if (s_red[w] > b2 || (s_red[w] == b2 && s_redi[w] < i2)) { b2 = s_red[w]; i2 = s_redi[w]; }
+      if (i2 == 0x7fffffff) i2 = 0;          // fewer candidates than beams (beam*V < beam): cannot happen for V >= beam
+      s_newp[j] = b2;
+      s_newi[j] = i2;
+      s_tot[i2] = -INFINITY;                  // remove from the candidate set
+    }
+    __syncthreads();
+  }
+  if (tid < beam) {
+    const int idx = s_newi[tid];
+    const int id = idx % V, par = idx / V;
+    const int fin = finished[row0 + par] | (id == (int)end_id ? 1 : 0);
+    const int64_t o = ((int64_t)img * max_steps + t) * beam + tid;
+    ids[o] = id;
+    parents[o] = par;
+    fin_hist[o] = fin;
+    next_tok[row0 + tid] = id;
+    parent_rows[row0 + tid] = row0 + par;
+    logp[row0 + tid] = s_newp[tid];           // (every read of the old logp happened before the top-k loop)
+  }
+  __syncthreads();                            // finished[] of the parents is read above, overwritten below
+  if (tid < beam) {
+    const int64_t o = ((int64_t)img * max_steps + t) * beam + tid;
+    finished[row0 + tid] = fin_hist[o];
+  }
+}
+
+// dst[r][:] = src[rows[r]][:]  (state gather by parents, gather_helper beam_search_decoder_cell.py:370-391)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, float* __restrict__ dst, int n,
+                                   int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * D) return;
+  const int r = idx / D, j = idx % D;
+  dst[idx] = src[(int64_t)rows[r] * D + j];
+}
+
+__global__ void fin_hist_kernel(const int32_t* __restrict__ finished, int32_t* __restrict__ hist, int64_t stride, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) hist[(int64_t)i * stride] = finished[i];
+}
+
 __global__ void fill_i64_kernel(int64_t* p, int64_t v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -630,19 +737,19 @@ __global__ void dlen_kernel(int32_t* dlen, int B, int Tn, int full) {
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 struct Dims {
-  int B, T, R, C, A, D, E, V, O1, G;
+  int B, T, R, C, A, D, E, V, O1, G, Vl;
 };
 static inline Dims dims(const lo_decoder_args* a) {
-  return Dims{a->B, a->T, a->R, a->C, a->A, a->D, a->E, a->V, a->A + a->C + 4 * a->D, 4 * a->D};
+  return Dims{a->B, a->T, a->R, a->C, a->A, a->D, a->E, a->V, a->A + a->C + 4 * a->D, 4 * a->D, a->ldl > 0 ? a->ldl : a->V};
 }
 
 // bf16 staging used when impl == TC: mirrors written by the step kernels feed the tcgen05 GEMMs directly
 struct BfViews {
   bool on;
-  bf16 *dcat, *hall, *gctx, *wet, *onehot;
+  bf16 *dcat, *hall, *gctx, *wet, *onehot, *hd, *dlogits, *wfct;
 };
 static BfViews bf_views(const lo_decoder_args* a, const Dims& d) {
-  BfViews v{false, nullptr, nullptr, nullptr, nullptr, nullptr};
+  BfViews v{false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (a->impl == LO_IMPL_TC && a->dt == LO_BF16 && a->bfwork && tc_available()) {
     const int64_t TB = (int64_t)d.T * d.B;
     v.on = true;
@@ -651,6 +758,9 @@ static BfViews bf_views(const lo_decoder_args* a, const Dims& d) {
     v.gctx = v.hall + (TB + d.B) * d.D;
     v.wet = v.gctx + TB * d.C;
     v.onehot = v.wet + (int64_t)d.A * d.C;
+    v.hd = v.onehot + TB * ((d.V + 7) / 8 * 8);
+    v.dlogits = v.hd + TB * d.D;
+    v.wfct = v.dlogits + TB * d.Vl;
   }
   return v;
 }
@@ -661,6 +771,8 @@ static int check_args(const lo_decoder_args* a) {
   LO_CHECK_ARG(a->A == a->C && (a->C == 256 || a->C == 512 || a->C == 1024), "attention_dim == encoder_dim in {256,512,1024}");
   LO_CHECK_ARG(a->D % 8 == 0 && a->E % 8 == 0, "D, E multiples of 8");
   LO_CHECK_ARG(a->dt == LO_F32 || a->dt == LO_BF16, "dt");
+  LO_CHECK_ARG(a->ldl == 0 || a->ldl >= a->V, "ldl >= V");
+  LO_CHECK_ARG(a->rows_per_img <= 1 || a->B % a->rows_per_img == 0, "B must be a multiple of rows_per_img");
   LO_CHECK_ARG(a->bt_host && a->caps && a->enc && a->work, "null pointer");
   for (int t = 0; t < a->T; t++) {
     LO_CHECK_ARG(a->bt_host[t] >= 1 && a->bt_host[t] <= a->B, "bt_host out of range");
@@ -675,9 +787,11 @@ static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a
 
 static int attention_forward_launch(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                                     const float* wf, float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre,
-                                    int64_t gate_stride, float* gctx, bf16* gctx_bf, int B, int R, int C, void* work, cudaStream_t st) {
+                                    int64_t gate_stride, float* gctx, bf16* gctx_bf, int B, int R, int C, void* work, cudaStream_t st,
+                                    int rpi = 1) {
+  if (rpi < 1) rpi = 1;
   if (g_opt_att_pipe) {
-    AttFwdArgs x{att1, enc, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, B, R, work};
+    AttFwdArgs x{att1, enc, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, B, R, work, rpi};
     return attention_fwd_pipe(x, dt, C, st);
   }
   const int ns = att_splits(B);
@@ -686,7 +800,7 @@ static int attention_forward_launch(const void* att1, const void* enc, int dt, c
   dim3 grid(ns, B);
 #define LO_ATT_FWD(T, NV)                                                                                           \
   attention_fwd_kernel<T, NV><<<grid, LO_ATT_THREADS, 0, st>>>((const T*)att1, (const T*)enc, att2, att2_stride, wf, \
-                                                               alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, R, ns, cnt, part)
+                                                               alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, R, ns, cnt, part, rpi)
   if (dt == LO_F32) {
     if (C == 256) LO_ATT_FWD(float, 1); else if (C == 512) LO_ATT_FWD(float, 2); else LO_ATT_FWD(float, 4);
   } else {
@@ -718,14 +832,15 @@ static int upload_dlen(const lo_decoder_args* a, cudaStream_t st) {
 
 static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_t st) {
   const int dt = a->dt;
+  const int rpi = a->rows_per_img > 1 ? a->rows_per_img : 1;
   // att1 = enc @ W_e^T + b_e   (hoisted: the reference recomputes it every step, seq2seq_torch.py:186)
-  LO_TRY(gemm_nt(a->enc, dt, d.C, a->w_enc_att, dt, d.C, a->att1, dt, d.A, d.B * d.R, d.A, d.C, a->b_enc_att, 0, 0, a->impl, st));
+  LO_TRY(gemm_nt(a->enc, dt, d.C, a->w_enc_att, dt, d.C, a->att1, dt, d.A, (d.B / rpi) * d.R, d.A, d.C, a->b_enc_att, 0, 0, a->impl, st));
   // embedding -> gate projection table (replaces embedding lookup + x[:, :E] @ W_ih[:, :E]^T, seq2seq_torch.py:291,:313)
   LO_TRY(gemm_nt(a->emb, dt, d.E, a->w_ih, dt, d.E + d.C, a->ptab, LO_F32, d.G, d.V, d.G, d.E, a->b_ih, 0, 0, LO_IMPL_SIMT, st));
   // init_hidden_state (seq2seq_torch.py:255-265)
   {
     dim3 grid(cdiv(d.C, 256), d.B);
-    LO_DISPATCH_DT(dt, T, (mean_rows_kernel<T><<<grid, 256, 0, st>>>((const T*)a->enc, a->mean, d.R, d.C)));
+    LO_DISPATCH_DT(dt, T, (mean_rows_kernel<T><<<grid, 256, 0, st>>>((const T*)a->enc, a->mean, d.R, d.C, rpi)));
     LO_LAUNCH_OK();
   }
   const size_t es = dt == LO_F32 ? 4 : 2;
@@ -755,7 +870,7 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, int nrow
   }
   LO_TRY(attention_forward_launch(a->att1, a->enc, dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
                                   a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C,
-                                  bv.on ? bv.gctx + (int64_t)t * d.B * d.C : nullptr, nrows, d.R, d.C, a->work, st));
+                                  bv.on ? bv.gctx + (int64_t)t * d.B * d.C : nullptr, nrows, d.R, d.C, a->work, st, a->rows_per_img));
   // gates_x = (gate*ctx) @ W_ih[:, E:]^T
   if (bv.on) {
     LO_TRY(tc_gemm_nt_ex(bv.gctx + (int64_t)t * d.B * d.C, d.C, (const bf16*)a->w_ih + d.E, d.E + d.C, a->gtmp, LO_F32, d.G, nrows, d.G,
@@ -782,7 +897,8 @@ int64_t lo_decoder_bfwork_bytes(const lo_decoder_args* a) {
   if (!a) return 0;
   const int64_t TB = (int64_t)a->T * a->B, O1 = a->A + a->C + 4 * a->D;
   const int64_t Vp = (a->V + 7) / 8 * 8;
-  return (TB * (O1 + a->D + a->C + Vp) + (int64_t)a->B * a->D + (int64_t)a->A * a->C) * 2 + 1024;
+  const int64_t Vl = a->ldl > 0 ? a->ldl : a->V;
+  return (TB * (O1 + a->D + a->C + Vp + a->D + Vl) + (int64_t)a->B * a->D + (int64_t)a->A * a->C + (int64_t)a->D * Vl) * 2 + 1024;
 }
 
 int64_t lo_sizeof_decoder_args(void) { return (int64_t)sizeof(lo_decoder_args); }
@@ -818,7 +934,14 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
     LO_TRY(forward_step(a, d, t, a->bt_host[t], a->caps + t, a->caps_stride, a->hd + (int64_t)t * d.D, (int64_t)d.T * d.D, dm, st));
   }
   // predictions = fc(dropout(h))  (seq2seq_torch.py:316), hoisted out of the loop
-  LO_TRY(gemm_nt(a->hd, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B * d.T, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));
+  const BfViews bvf = bf_views(a, d);
+  const bool fc_tc = bvf.on && d.Vl % 64 == 0 && d.D % 64 == 0;
+  if (fc_tc) {
+    LO_TRY(lo_cast(a->hd, LO_F32, bvf.hd, LO_BF16, (int64_t)d.B * d.T * d.D, stream));
+    LO_TRY(tc_gemm_nt_ex(bvf.hd, d.D, (const bf16*)a->w_fc, d.D, a->logits, LO_F32, d.Vl, d.B * d.T, d.V, d.D, a->b_fc, 0, 0, 1, 0, 0, st));
+  } else {
+    LO_TRY(gemm_nt(a->hd, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.Vl, d.B * d.T, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));
+  }
   if (ragged) {
     // rows that stopped decoding keep zeros in `predictions` (seq2seq_torch.py:301): re-zero what the GEMM wrote (bias)
     // handled by the CE kernel (ignores them) and by the Python side for the returned tensor.
@@ -828,7 +951,7 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
     for (int t = 0; t < d.T; t++) nvalid += a->bt_host[t];
     const float inv_n = 1.0f / (float)nvalid;
     ce_kernel<<<cdiv((long)d.B * d.T, 8), 256, 0, st>>>(a->logits, a->caps, a->caps_stride, work_dlen(a), a->row_loss, a->dlogits,
-                                                         d.B, d.T, d.V, inv_n);
+                                                         (fc_tc && a->dlogits) ? bvf.dlogits : nullptr, d.B, d.T, d.V, d.Vl, inv_n);
     LO_LAUNCH_OK();
     reg_kernel<<<cdiv((long)d.B * d.R, 256), 256, 0, st>>>(a->alphas, a->row_loss + (int64_t)d.B * d.T, a->dreg, d.B, d.T, d.R, a->alpha_c);
     LO_LAUNCH_OK();
@@ -876,9 +999,20 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   sreg_kernel<<<cdiv(BT, 8), 256, 0, st>>>(a->alphas, dal, dal_b, dal_t, a->sreg, d.B, d.T, d.R);
   LO_LAUNCH_OK();
   // fc backward (hoisted): g_w_fc = dlogits^T hd ; g_b_fc ; dhd = dlogits @ W_fc (* dropout mask)
-  LO_TRY(gemm_tn(a->dlogits, LO_F32, d.V, a->hd, LO_F32, d.D, a->g_w_fc, LO_F32, d.D, d.V, d.D, (int)BT, 0, LO_IMPL_SIMT, st));
-  LO_TRY(colsum(a->dlogits, LO_F32, a->g_b_fc, (int)BT, d.V, d.V, 0, st));
-  LO_TRY(gemm_nn(a->dlogits, LO_F32, d.V, a->w_fc, dt, d.D, a->dhd, LO_F32, d.D, (int)BT, d.D, d.V, 0, LO_IMPL_SIMT, st));
+  const BfViews bvf = bf_views(a, d);
+  const bool fc_tc = bvf.on && d.Vl % 64 == 0 && d.D % 64 == 0 && !a->dalpha_ext;
+  if (fc_tc) {
+    // (dlogits bf16 mirror was written by ce_kernel; generic-autograd callers that fill dlogits themselves use the SIMT path)
+    LO_CUDA(cudaMemsetAsync(a->g_w_fc, 0, (size_t)d.V * d.D * 4, st));
+    LO_TRY(tc_gemm_tn(bvf.dlogits, d.Vl, bvf.hd, d.D, a->g_w_fc, d.D, d.V, d.D, (int)BT, st));
+    transpose_kernel<bf16><<<dim3(cdiv(d.D, 32), cdiv(d.V, 32)), dim3(32, 8), 0, st>>>((const bf16*)a->w_fc, d.D, bvf.wfct, d.Vl, d.V, d.D);
+    LO_LAUNCH_OK();
+    LO_TRY(tc_gemm_nt_ex(bvf.dlogits, d.Vl, bvf.wfct, d.Vl, a->dhd, LO_F32, d.D, (int)BT, d.D, d.Vl, nullptr, 0, 0, 1, 0, 0, st));
+  } else {
+    LO_TRY(gemm_tn(a->dlogits, LO_F32, d.Vl, a->hd, LO_F32, d.D, a->g_w_fc, LO_F32, d.D, d.V, d.D, (int)BT, 0, LO_IMPL_SIMT, st));
+    LO_TRY(gemm_nn(a->dlogits, LO_F32, d.Vl, a->w_fc, dt, d.D, a->dhd, LO_F32, d.D, (int)BT, d.D, d.V, 0, LO_IMPL_SIMT, st));
+  }
+  LO_TRY(colsum(a->dlogits, LO_F32, a->g_b_fc, (int)BT, d.V, d.Vl, 0, st));
   LO_CUDA(cudaMemsetAsync(a->dxh, 0, (size_t)d.B * (d.C + d.D) * 4, st));
   LO_CUDA(cudaMemsetAsync(a->dc, 0, (size_t)d.B * d.D * 4, st));
   if (ragged) {
@@ -1021,15 +1155,13 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   return LO_OK;
 }
 
-int lo_decoder_greedy(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* tokens,
-                      int32_t* finished, void* stream) {
+int lo_decoder_greedy_hist(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* tokens,
+                           int32_t* finished, int32_t* fin_hist, void* stream) {
   LO_TRY(check_args(a));
   LO_CHECK_ARG(tokens && finished && max_steps > 0 && max_steps <= a->T, "tokens/finished/max_steps (<= T capacity)");
   cudaStream_t st = (cudaStream_t)stream;
   const Dims d = dims(a);
-  // next-token buffer lives in the dlen scratch area's neighbour: reuse dptab-free region -> use `sreg` as int64 scratch
-  int64_t* next_tok = (int64_t*)a->sreg;
-  LO_CHECK_ARG((int64_t)d.B * d.T * 4 >= (int64_t)d.B * 8, "sreg scratch too small");
+  int64_t* next_tok = (int64_t*)a->sreg;          // scratch: [B] int64 fits in sreg [B][>=2] floats
   fill_i64_kernel<<<cdiv(d.B, 128), 128, 0, st>>>(next_tok, start_id, d.B);
   LO_LAUNCH_OK();
   LO_CUDA(cudaMemsetAsync(finished, 0, (size_t)d.B * 4, st));
@@ -1041,6 +1173,62 @@ int lo_decoder_greedy(const lo_decoder_args* a, int64_t start_id, int64_t end_id
                    a->b_fc, 0, 0, LO_IMPL_SIMT, st));
     argmax_kernel<<<cdiv(d.B, 8), 256, 0, st>>>(a->logits, d.V, tokens + t, max_steps, next_tok, finished, end_id, d.B);
     LO_LAUNCH_OK();
+    if (fin_hist) {
+      fin_hist_kernel<<<cdiv(d.B, 128), 128, 0, st>>>(finished, fin_hist + t, max_steps, d.B);
+      LO_LAUNCH_OK();
+    }
+  }
+  return LO_OK;
+}
+
+int lo_decoder_greedy(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* tokens,
+                      int32_t* finished, void* stream) {
+  return lo_decoder_greedy_hist(a, start_id, end_id, max_steps, tokens, finished, nullptr, stream);
+}
+
+int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents,
+                    int32_t* fin_hist, float* logp, void* stream) {
+  LO_TRY(check_args(a));
+  const int beam = a->rows_per_img;
+  LO_CHECK_ARG(beam >= 1 && beam <= LO_BEAM_MAX && a->B % beam == 0, "1 <= beam (rows_per_img) <= 16, B % beam == 0");
+  LO_CHECK_ARG(ids && parents && fin_hist && logp && max_steps > 0 && max_steps <= a->T, "outputs / max_steps (<= T capacity)");
+  LO_CHECK_ARG((size_t)beam * a->V * 4 <= 200 * 1024, "beam*V too large for the shared-memory top-k");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Dims d = dims(a);
+  const int n_img = d.B / beam;
+  // scratch: next tokens (int64 [B]) in sreg, finished + parent rows (int32 [B] each) in row_loss
+  int64_t* next_tok = (int64_t*)a->sreg;
+  int32_t* finished = (int32_t*)a->row_loss;
+  int32_t* parent_rows = finished + d.B;
+  LO_CHECK_ARG((int64_t)d.B * d.T >= 2 * d.B, "row_loss scratch too small");
+  fill_i64_kernel<<<cdiv(d.B, 128), 128, 0, st>>>(next_tok, start_id, d.B);
+  LO_LAUNCH_OK();
+  LO_CUDA(cudaMemsetAsync(finished, 0, (size_t)d.B * 4, st));
+  LO_CUDA(cudaMemsetAsync(logp, 0, (size_t)d.B * 4, st));          // initial log-probs are zeros (:106-107)
+  LO_TRY(forward_prologue(a, d, st));
+  const BfViews bv = bf_views(a, d);
+  const size_t smem = (size_t)beam * d.V * 4;
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    LO_CUDA(cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  for (int t = 0; t < max_steps; t++) {
+    LO_TRY(forward_step(a, d, t, d.B, next_tok, 1, nullptr, 0, nullptr, st));
+    float* h_new = a->hall + (int64_t)(t + 1) * d.B * d.D;
+    float* c_new = a->call + (int64_t)(t + 1) * d.B * d.D;
+    LO_TRY(gemm_nt(h_new, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));
+    beam_step_kernel<<<n_img, 256, smem, st>>>(a->logits, d.V, beam, t, end_id, logp, finished, ids, parents, fin_hist, next_tok,
+                                               parent_rows, max_steps);
+    LO_LAUNCH_OK();
+    // reorder the recurrent state by parents (through gtmp as a temporary)
+    gather_rows_kernel<<<cdiv((long)d.B * d.D, 256), 256, 0, st>>>(h_new, parent_rows, a->gtmp, d.B, d.D);
+    LO_LAUNCH_OK();
+    gather_rows_kernel<<<cdiv((long)d.B * d.D, 256), 256, 0, st>>>(c_new, parent_rows, a->gtmp + (int64_t)d.B * d.D, d.B, d.D);
+    LO_LAUNCH_OK();
+    LO_CUDA(cudaMemcpyAsync(h_new, a->gtmp, (size_t)d.B * d.D * 4, cudaMemcpyDeviceToDevice, st));
+    LO_CUDA(cudaMemcpyAsync(c_new, a->gtmp + (int64_t)d.B * d.D, (size_t)d.B * d.D * 4, cudaMemcpyDeviceToDevice, st));
+    if (bv.on) LO_TRY(lo_cast(h_new, LO_F32, bv.hall + (int64_t)(t + 1) * d.B * d.D, LO_BF16, (int64_t)d.B * d.D, stream));
   }
   return LO_OK;
 }

@@ -502,7 +502,7 @@ static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, TcParams&
 int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
                   const float* bias, int accumulate, int relu, int splits, int atomic_acc, int small_n_tile, cudaStream_t st) {
   if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
-  LO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "K%64, N%8, ld%8");
+  LO_CHECK_ARG(K % 64 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && ldc >= (N + 7) / 8 * 8, "K%64, ld%8, ldc >= roundup8(N)");
   LO_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0, "16-byte alignment");
   CUtensorMap mA, mB;
   {

@@ -198,7 +198,8 @@ class DecoderWithAttention(nn.Module):
             t["gates"] = z(T, B, G)
             t["gtmp"] = z(B, G)
             t["hd"] = z(B, T, D)
-            t["logits"] = z(B, T, V)
+            ws["ldl"] = (V + 63) // 64 * 64
+            t["logits"] = z(B, T, ws["ldl"])
             t["row_loss"] = z(B * T + B * R)
             t["loss"] = z(4)
             t["sreg"] = z(B, max(T, 2))
@@ -210,7 +211,7 @@ class DecoderWithAttention(nn.Module):
             t = ws["t"]
             t["wbwd1"] = z(C + D, G, dtype=self.tdtype)
             t["wbwd2"] = z(D, A + C, dtype=self.tdtype)
-            t["dlogits"] = z(B, T, V)
+            t["dlogits"] = z(B, T, ws["ldl"])
             t["dhd"] = z(B, T, D)
             t["dreg"] = z(B, R)
             t["dcat"] = z(T, B, O1)
@@ -234,6 +235,7 @@ class DecoderWithAttention(nn.Module):
         a.dt = _dt(self.precision)
         a.impl = _lib.LO_IMPL_TC if (self.impl == "tc" and self.precision == "bf16") else _lib.LO_IMPL_SIMT
         a.has_dropout = 1 if has_dropout else 0
+        a.ldl = ws["ldl"]
         a.alpha_c = float(self.alpha_c)
         a.bt_host = ctypes.cast(ws["bt"], ctypes.c_void_p)
         a.caps = t["caps"].data_ptr()
@@ -343,7 +345,7 @@ class DecoderWithAttention(nn.Module):
             T = max(decode_lengths)
             mask = self.make_dropout_mask(B, T)
             ws = self.run_forward(enc, caps, decode_lengths, with_loss=False, need_grad=False, dropout_mask=mask)
-            preds = ws["t"]["logits"].clone()
+            preds = ws["t"]["logits"][:, :, :self.vocab_size].clone()
             alphas = ws["t"]["alphas"].clone()
             if min(decode_lengths) < T:      # rows that stopped decoding keep zeros (:301-302, :317-318)
                 act = torch.arange(T, device=enc.device)[None, :] < torch.tensor(decode_lengths, device=enc.device)[:, None]

@@ -197,6 +197,23 @@ class Img2SeqModel:
                 break
         return best_score
 
+    # --- inference: img2seq.py:256-285 (TF surface) ------------------------------------------------------
+    def predict_batch(self, images, start_id=None, decoding=None, beam_size=None):
+        """images: float tensor [N,1,H,W].  Returns list[beam][N] of token-id lists truncated at END
+        (greedy: one hypothesis), like Img2SeqModel.predict_batch of the TF path."""
+        from . import decode
+        decoding = decoding or getattr(self._config, "decoding", "greedy")
+        end_id = self._vocab.id_end if self._vocab is not None else self._n_tok - 1
+        start_id = end_id - 1 if start_id is None else start_id          # default: the PAD id (no START in the torch flavour)
+        L = int(getattr(self._config, "max_length_formula", 150))
+        self.train_mode(False)
+        if decoding == "greedy":
+            ids = decode.greedy_decode(self, images, start_id, end_id, L)
+            return [decode.truncate_end(ids.tolist(), end_id)]
+        beam = int(beam_size or getattr(self._config, "beam_size", 5))
+        ids, _ = decode.beam_decode(self, images, start_id, end_id, beam, L)
+        return [decode.truncate_end(ids[:, k].tolist(), end_id) for k in range(beam)]
+
     # --- checkpoints: state_dict round-trips with the reference modules ----------------------------
     def state_dict(self):
         return {"encoder": self.encoder.state_dict(), "decoder": self.decoder.state_dict()}

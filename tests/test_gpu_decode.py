@@ -1,0 +1,56 @@
+"""-m gpu: greedy and beam decoding through the C ABI vs the CPU restatement of the reference's decode loop
+(oracle/ref_decode.py; parity unpinned — the TF graph cannot run here).  fp32 mode: token ids must match exactly."""
+import pytest
+import torch
+
+from util import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(V=30, seed=4, N=3, H=32, W=80):
+    from oracle import ref_model as rm
+    pe, pd = rm.init_params(V, seed=seed)
+    # make decoding non-degenerate: larger output layer so the argmax moves and END appears
+    g = torch.Generator().manual_seed(seed)
+    pd["fc.weight"] = (torch.rand(V, 512, generator=g) * 2 - 1) * 0.5
+    pd["embedding.weight"] = (torch.rand(V, 512, generator=g) * 2 - 1) * 1.0
+    img, _ = rm.synthetic_batch(N, H, W, V, 3, 5, seed=seed + 1)
+    m = build_model(V, pe, pd, "fp32")
+    enc = rm.encoder_forward(pe, img).reshape(N, -1, 512)
+    return rm, pd, m, img, enc
+
+
+def test_greedy_tokens_match_oracle():
+    from latex_ocr_b200 import decode
+    from oracle import ref_decode as rd
+    V = 30
+    rm, pd, m, img, enc = _setup(V)
+    for end_id, L in ((V - 1, 6), (7, 12)):
+        want = rd.greedy_decode(pd, enc, start_id=V - 2, end_id=end_id, max_iter=L + 1)
+        got = decode.greedy_decode(m, img, start_id=V - 2, end_id=end_id, max_length_formula=L)
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("beam", [1, 3, 5])
+def test_beam_tokens_match_oracle(beam):
+    from latex_ocr_b200 import decode
+    from oracle import ref_decode as rd
+    V = 30
+    rm, pd, m, img, enc = _setup(V, seed=6)
+    for fin in ("reference", "backtrack"):
+        want, wlp = rd.beam_decode(pd, enc, start_id=V - 2, end_id=5, beam=beam, max_iter=9, finalize=fin)
+        got, glp = decode.beam_decode(m, img, start_id=V - 2, end_id=5, beam_size=beam, max_length_formula=8, finalize=fin)
+        assert got.shape == want.permute(0, 2, 1).shape
+        assert torch.equal(got, want.permute(0, 2, 1))
+        assert (glp - wlp).abs().max().item() < 1e-3 * max(1.0, wlp.abs().max().item())
+
+
+def test_predict_batch_surface():
+    rm, pd, m, img, enc = _setup(30, seed=8)
+    out = m.predict_batch(img, decoding="greedy")
+    assert len(out) == 1 and len(out[0]) == img.shape[0]
+    out = m.predict_batch(img, decoding="beam_search", beam_size=2)
+    assert len(out) == 2 and all(len(h) == img.shape[0] for h in out)
+    assert all(29 not in seq for seq in out[0])        # truncated at END
