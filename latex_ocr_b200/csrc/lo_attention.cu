@@ -12,6 +12,7 @@
 namespace lo {
 
 int g_opt_att_pipe = 1;
+int g_opt_pdl = 0;               // programmatic dependent launch for the per-step kernels
 int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
 int g_opt_att_policy_att1 = 2;
 int g_opt_att_nsplit = 0;        // 0 = automatic
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     }
     fence_barrier_init();
   }
+  pdl_wait();
+  pdl_trigger();
   __syncthreads();
 
   float m = -INFINITY, l = 0.f;
@@ -253,6 +256,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     }
     fence_barrier_init();
   }
+  pdl_wait();
+  pdl_trigger();
   __syncthreads();
   float macc[NV * 8];
 #pragma unroll
@@ -406,10 +411,10 @@ static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
     attr = true;
   }
   const int ns = att_pipe_splits(x.B);
-  attention_fwd_pipe_kernel<T, NV><<<dim3(ns, x.B), AP_THREADS, C::SMEM, st>>>(
-      (const T*)x.att1, (const T*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride,
-      x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1,
-      x.rows_per_img > 1 ? x.rows_per_img : 1);
+  LO_CUDA(launch_pdl(attention_fwd_pipe_kernel<T, NV>, dim3(ns, x.B), dim3(AP_THREADS), (size_t)C::SMEM, st,
+                     (const T*)x.att1, (const T*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre,
+                     x.gate_stride, x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc,
+                     g_opt_att_policy_att1, x.rows_per_img > 1 ? x.rows_per_img : 1));
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -434,10 +439,11 @@ static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
     attr = true;
   }
   const int ns = att_pipe_splits(x.B);
-  attention_bwd_pipe_kernel<T, NV><<<dim3(ns, x.B), AP_THREADS, C::SMEM, st>>>(
-      (const T*)x.att1, (const T*)x.enc, x.att2, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride,
-      x.dreg, x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,
-      (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1);
+  LO_CUDA(launch_pdl(attention_bwd_pipe_kernel<T, NV>, dim3(ns, x.B), dim3(AP_THREADS), (size_t)C::SMEM, st,
+                     (const T*)x.att1, (const T*)x.enc, x.att2, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx,
+                     x.dg_stride, x.dreg, x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf,
+                     x.dgp_bf, x.dctx_out, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc,
+                     g_opt_att_policy_att1));
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -461,6 +467,7 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "att_policy_enc")) lo::g_opt_att_policy_enc = value;
   else if (!strcmp(name, "att_policy_att1")) lo::g_opt_att_policy_att1 = value;
   else if (!strcmp(name, "att_nsplit")) lo::g_opt_att_nsplit = value;
+  else if (!strcmp(name, "pdl")) lo::g_opt_pdl = value;
   else return lo::fail(LO_EINVAL, "lo_set_option: unknown option %s", name);
   return LO_OK;
 }

@@ -6,6 +6,7 @@
 // gradient, d att1 and d enc).  Inside the loop each step reads enc and att1 exactly ONCE in forward
 // and ONCE in backward (the HBM roofline of SURVEY.md §8-d) and runs two skinny GEMMs.
 #include "lo_common.cuh"
+#include "lo_ptx.cuh"
 
 namespace lo {
 
@@ -377,6 +378,8 @@ __global__ void lstm_pw_fwd_kernel(const float* __restrict__ gtmp, const float* 
                                    float* __restrict__ c_out, float* __restrict__ h_out, bf16* __restrict__ h_bf,
                                    float* __restrict__ hd, int64_t hd_stride, const float* __restrict__ dmask, int nrows, int D,
                                    int V) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nrows * D) return;
   const int b = idx / D, j = idx % D;
@@ -408,6 +411,8 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_st
                                    const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                                    float* __restrict__ dG, int64_t dG_stride, bf16* __restrict__ dG_bf, float* __restrict__ dxh_zero,
                                    int C, int nrows, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nrows * D) return;
   const int b = idx / D, j = idx % D;
@@ -879,10 +884,10 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, int nrow
     LO_TRY(gemm_nt(a->gctx + (int64_t)t * d.B * d.C, LO_F32, d.C, (const char*)a->w_ih + (size_t)d.E * es, dt, d.E + d.C, a->gtmp,
                    LO_F32, d.G, nrows, d.G, d.C, nullptr, 0, 0, LO_IMPL_SIMT, st));
   }
-  lstm_pw_fwd_kernel<<<cdiv((long)nrows * d.D, 256), 256, 0, st>>>(
-      a->gtmp, a->ptab, tok, tok_stride, o1 + d.A + d.C, d.O1, c_prev, a->gates + (int64_t)t * d.B * d.G,
-      a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D,
-      bv.on ? bv.hall + (int64_t)(t + 1) * d.B * d.D : nullptr, hd_t, hd_stride, dmask_t, nrows, d.D, d.V);
+  LO_CUDA(launch_pdl(lstm_pw_fwd_kernel, dim3(cdiv((long)nrows * d.D, 256)), dim3(256), (size_t)0, st, (const float*)a->gtmp,
+                     (const float*)a->ptab, tok, tok_stride, (const float*)(o1 + d.A + d.C), (int64_t)d.O1, (const float*)c_prev,
+                     a->gates + (int64_t)t * d.B * d.G, a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D,
+                     bv.on ? bv.hall + (int64_t)(t + 1) * d.B * d.D : (bf16*)nullptr, hd_t, hd_stride, dmask_t, nrows, d.D, d.V));
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -1031,10 +1036,12 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     bf16* dcat_bf_t = bv.on ? bv.dcat + (int64_t)t * d.B * d.O1 : nullptr;
     const float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
     const float* dmul = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
-    lstm_pw_bwd_kernel<<<cdiv((long)nrows * d.D, 256), 256, 0, st>>>(
-        a->dhd + (int64_t)t * d.D, (int64_t)d.T * d.D, dmul, a->dxh + d.C, d.C + d.D, a->dc, a->gates + (int64_t)t * d.B * d.G,
-        a->call + (int64_t)t * d.B * d.D, a->call + (int64_t)(t + 1) * d.B * d.D, dcat_t + d.A + d.C, d.O1,
-        bv.on ? dcat_bf_t + d.A + d.C : nullptr, bv.on ? a->dxh : nullptr, d.C, nrows, d.D);
+    LO_CUDA(launch_pdl(lstm_pw_bwd_kernel, dim3(cdiv((long)nrows * d.D, 256)), dim3(256), (size_t)0, st,
+                       (const float*)(a->dhd + (int64_t)t * d.D), (int64_t)d.T * d.D, dmul, (const float*)(a->dxh + d.C),
+                       (int64_t)(d.C + d.D), a->dc, (const float*)(a->gates + (int64_t)t * d.B * d.G),
+                       (const float*)(a->call + (int64_t)t * d.B * d.D), (const float*)(a->call + (int64_t)(t + 1) * d.B * d.D),
+                       dcat_t + d.A + d.C, (int64_t)d.O1, bv.on ? dcat_bf_t + d.A + d.C : (bf16*)nullptr,
+                       bv.on ? a->dxh : (float*)nullptr, d.C, nrows, d.D));
     LO_LAUNCH_OK();
     // [dgctx | dh_prev] = dG @ [W_ih[:, E:] | W_hh]
     if (bv.on) {

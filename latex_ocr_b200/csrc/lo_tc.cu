@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, NT);
+  pdl_wait();          // everything above touched only shared memory / TMEM / kernel parameters
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -482,7 +484,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcParam
     attr_set = true;
   }
   dim3 grid(cdiv(p.N, NT), mtiles, splits);
-  tc_gemm_conv_kernel<NT, STAGES><<<grid, TC_THREADS, SM::TOTAL, st>>>(mA, mB, p);
+  LO_CUDA(launch_pdl(tc_gemm_conv_kernel<NT, STAGES>, grid, dim3(TC_THREADS), (size_t)SM::TOTAL, st, mA, mB, p));
   LO_LAUNCH_OK();
   return LO_OK;
 }
