@@ -12,7 +12,7 @@
 namespace lo {
 
 int g_opt_att_pipe = 1;
-int g_opt_pdl = 0;               // programmatic dependent launch for the per-step kernels
+int g_opt_pdl = 1;               // programmatic dependent launch for the per-step kernels
 int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
 int g_opt_att_policy_att1 = 2;
 int g_opt_att_nsplit = 0;        // 0 = automatic

@@ -29,6 +29,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
                "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
@@ -106,6 +113,7 @@ struct TcParams {
   int64_t ldc;
   int out_f32, accumulate, relu;
   int kb_per_split, atomic;   // split-K over gridDim.z: fp32 atomics onto `out` (bias added by split 0)
+  int w_evict_last;           // keep the B (weight) tiles in L2: the per-step decoder GEMMs re-read them every step
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -169,6 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     if (lane == 0) {
       // ===== TMA producer =====
       const int cpb = p.conv ? p.Cin / TC_BK : 1;
+      const uint64_t polB = p.w_evict_last ? l2_policy_evict_last() : l2_policy_evict_normal();
       for (int kb = 0; kb < KB; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         } else {
           tma_load_2d(sa, &mapA, full_bar + s, kg * TC_BK, m0);
         }
-        tma_load_2d(sb, &mapB, full_bar + s, kg * TC_BK, n0);
+        tma_load_2d_hint(sb, &mapB, full_bar + s, kg * TC_BK, n0, polB);
       }
     }
     __syncwarp();
@@ -496,6 +505,7 @@ static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, TcParams&
   p.kb_per_split = cdiv(KB, splits);
   splits = cdiv(KB, p.kb_per_split);
   p.atomic = splits > 1 ? 1 : p.atomic;
+  if (nt == 64 && mtiles == 1 && p.kb_per_split > 4) return launch_tc<64, 8>(mA, mB, p, mtiles, splits, st);   // skinny: all K in flight
   if (nt == 64) return launch_tc<64, 4>(mA, mB, p, mtiles, splits, st);
   return launch_tc<128, 3>(mA, mB, p, mtiles, splits, st);
 }
@@ -525,6 +535,7 @@ int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* 
   p.M = M; p.N = N; p.K = K; p.conv = 0;
   p.bias = bias; p.mask = nullptr; p.out = C; p.ldc = ldc;
   p.out_f32 = (dtC == LO_F32); p.accumulate = accumulate; p.relu = relu; p.atomic = atomic_acc;
+  p.w_evict_last = (M <= 128) ? 1 : 0;
   return launch_tc_any(mA, mB, p, cdiv(M, TC_BM), splits, NT, st);
 }
 
