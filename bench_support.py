@@ -82,8 +82,16 @@ def kernel_probes(model, c, pk):
 
     ms_att = _time_ms(att_steps, 3) / T
     att_bytes = B * R * (A + C) * bpe + B * R * 4
-    att = {"kernel": "attention_fwd_kernel (score+softmax+context, one decode step)", "bound": "hbm",
-           "achieved": att_bytes / (ms_att * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "traffic": None,
+    traffic = None
+    try:
+        import json
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+        if B == 64 and R == 868 and bpe == 2:
+            traffic = tj["attention_fwd_pipe_kernel"]["bytes"]
+    except Exception:
+        pass
+    att = {"kernel": "attention_fwd_pipe_kernel (score + softmax + context + gate, one decode step, TMA ring)", "bound": "hbm",
+           "achieved": att_bytes / (ms_att * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "traffic": traffic,
            "us_per_launch": ms_att * 1e3, "algorithmic_bytes": att_bytes, "peak_source": pk["src"]}
     att["frac"] = att["achieved"] / att["peak"]
 

@@ -40,6 +40,9 @@ int64_t lo_launch_count(void);
 /* tuning knobs: "att_pipe" (1: TMA-pipelined attention kernels, 0: register-streaming), "att_policy_enc" /
  * "att_policy_att1" (L2 policy 0 normal, 1 evict_last, 2 evict_first), "att_nsplit" (0 = automatic) */
 int lo_set_option(const char* name, int value);
+/* development aid: device buffer (>= 16 int64) that CTA (0,0,0) of the tcgen05 NT GEMM stamps with clock64 at its
+ * pipeline milestones; NULL disables */
+int lo_debug_buffer(void* p);
 /* 1 if the tcgen05/TMA kernels are built in and the current device is sm_100 */
 int lo_tc_available(void);
 

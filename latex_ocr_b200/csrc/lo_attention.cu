@@ -6,8 +6,12 @@
 //   backward: dalpha_r = <dctx, enc_r> + dreg_r ; de_r = alpha_r (dalpha_r - s) ; datt2 = w * sum_r de_r [att1_r + att2 > 0]
 // L2 policy: enc is read again by the next step (and by the backward) -> evict_last; att1 likewise is re-read every
 // step; which of the two to pin is a run-time option (lo_set_option) because together they are as large as the L2.
+#include <cooperative_groups.h>
+
 #include "lo_common.cuh"
 #include "lo_ptx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lo {
 
@@ -16,6 +20,7 @@ int g_opt_pdl = 1;               // programmatic dependent launch for the per-st
 int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
 int g_opt_att_policy_att1 = 2;
 int g_opt_att_nsplit = 0;        // 0 = automatic
+int g_opt_att_cluster = 1;       // 1: the splits of one batch row form a thread-block cluster and combine through DSMEM
 
 #define AP_THREADS 288
 #define AP_CWARPS 8
@@ -36,7 +41,7 @@ struct ApCfg {
   static constexpr int SMEM = AP_STAGES * STAGE_BYTES + 128;
 };
 
-template <typename T, int NV>
+template <typename T, int NV, bool CL>
 __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
@@ -48,6 +53,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   T* ring = reinterpret_cast<T*>(ap_smem);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + AP_STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + AP_STAGES;
+  float* s_e = reinterpret_cast<float*>(ap_smem + AP_STAGES * C::STAGE_BYTES + 128);   // cluster mode: raw scores of this CTA's rows
   __shared__ float s_m[AP_CWARPS], s_l[AP_CWARPS];
   __shared__ float s_scale[AP_MAXSPLIT];
   __shared__ float s_ML[2];
@@ -131,8 +137,13 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
         e0 = warp_sum(e0);
         e1 = warp_sum(e1);
         if (lane == 0) {
-          alb[row + ra] = e0;
-          if (two) alb[row + rb] = e1;
+          if constexpr (CL) {
+            s_e[row + ra - r0] = e0;
+            if (two) s_e[row + rb - r0] = e1;
+          } else {
+            alb[row + ra] = e0;
+            if (two) alb[row + rb] = e1;
+          }
         }
         const float mn = two ? fmaxf(m, fmaxf(e0, e1)) : fmaxf(m, e0);
         const float sc = expf(m - mn);
@@ -176,6 +187,55 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   for (int w = 0; w < AP_CWARPS; w++) {
     wsc[w] = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - M);
     L += s_l[w] * wsc[w];
+  }
+  if constexpr (CL) {
+    // ===== cluster combine: the nsplit CTAs of this batch row exchange (M, L, acc) through distributed shared memory =====
+    cg::cluster_group cluster = cg::this_cluster();
+    float* s_part = s_acc + AP_CWARPS * CH;                 // [CH] combined accumulator of this CTA (still inside the ring)
+    __shared__ float s_MLp[2];
+    for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < AP_CWARPS; w++) t = fmaf(s_acc[w * CH + c], wsc[w], t);
+      s_part[c] = t;
+    }
+    if (threadIdx.x == 0) { s_MLp[0] = M; s_MLp[1] = L; }
+    cluster.sync();
+    float Mg = -INFINITY;
+    for (int q = 0; q < nsplit; q++) Mg = fmaxf(Mg, cluster.map_shared_rank(s_MLp, q)[0]);
+    float Lg = 0.f;
+    float scl[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      scl[q] = 0.f;
+      if (q < nsplit) {
+        const float* ml = cluster.map_shared_rank(s_MLp, q);
+        const float ms = ml[0];
+        scl[q] = (ms == -INFINITY) ? 0.f : expf(ms - Mg);
+        Lg += ml[1] * scl[q];
+      }
+    }
+    const float invL = 1.0f / Lg;
+    // this CTA finalises its slice of the channels ...
+    const int cps = (CH + nsplit - 1) / nsplit;
+    for (int c = sp * cps + threadIdx.x; c < min(CH, (sp + 1) * cps); c += AP_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (q < nsplit) t = fmaf(cluster.map_shared_rank(s_part, q)[c], scl[q], t);
+      t *= invL;
+      ctx[(int64_t)b * CH + c] = t;
+      if (gate_pre) {
+        const float g = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
+        gate_pre[(int64_t)b * gate_stride + c] = g;
+        gctx[(int64_t)b * CH + c] = g * t;
+        if (gctx_bf) gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(g * t);
+      }
+    }
+    // ... and normalises the attention weights of its own rows (scores never leave shared memory)
+    for (int r = r0 + threadIdx.x; r < r1; r += AP_THREADS) alb[r] = expf(s_e[r - r0] - Mg) * invL;
+    cluster.sync();                                          // peers may still be reading this CTA's shared memory
+    return;
   }
   float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
   for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
@@ -226,7 +286,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   for (int r = threadIdx.x; r < R; r += AP_THREADS) alb[r] = expf(__ldcg(alb + r) - Mg) * invL;
 }
 
-template <typename T, int NV>
+template <typename T, int NV, bool CL>
 __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, const float* __restrict__ gate,
     int64_t o1_stride, const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride,
@@ -234,7 +294,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     int64_t dreg_stride, const float* __restrict__ sreg, int64_t sreg_stride, float* __restrict__ de, float* __restrict__ datt2,
     float* __restrict__ dgp, int64_t dcat_stride, bf16* __restrict__ datt2_bf, bf16* __restrict__ dgp_bf,
     float* __restrict__ dctx_out, int R, int nsplit, int* __restrict__ counters, float* __restrict__ partials, int pol_enc,
-    int pol_att1) {
+    int pol_att1, float* __restrict__ dwf_part) {
   using C = ApCfg<T, NV>;
   constexpr int CH = C::CH;
   extern __shared__ __align__(128) uint8_t ap_smem[];
@@ -259,9 +319,9 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
   pdl_wait();
   pdl_trigger();
   __syncthreads();
-  float macc[NV * 8];
+  float macc[NV * 8], wacc[NV * 8];     // wacc: d w_full partial = sum_r de_r * relu(att1_r + att2)   (full_att.weight gradient)
 #pragma unroll
-  for (int i = 0; i < NV * 8; i++) macc[i] = 0.f;
+  for (int i = 0; i < NV * 8; i++) { macc[i] = 0.f; wacc[i] = 0.f; }
 
   if (wid == AP_CWARPS) {
     if (lane == 0) {
@@ -344,11 +404,19 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
           float v[8];
           ld8(sa + (size_t)ra * CH + (j * 32 + lane) * 8, v);
 #pragma unroll
-          for (int q = 0; q < 8; q++) macc[j * 8 + q] += (v[q] + a2[j * 8 + q] > 0.f) ? de0 : 0.f;
+          for (int q = 0; q < 8; q++) {
+            const float pre = v[q] + a2[j * 8 + q];
+            macc[j * 8 + q] += (pre > 0.f) ? de0 : 0.f;
+            wacc[j * 8 + q] = fmaf(de0, fmaxf(pre, 0.f), wacc[j * 8 + q]);
+          }
           if (two) {
             ld8(sa + (size_t)rb * CH + (j * 32 + lane) * 8, v);
 #pragma unroll
-            for (int q = 0; q < 8; q++) macc[j * 8 + q] += (v[q] + a2[j * 8 + q] > 0.f) ? de1 : 0.f;
+            for (int q = 0; q < 8; q++) {
+              const float pre = v[q] + a2[j * 8 + q];
+              macc[j * 8 + q] += (pre > 0.f) ? de1 : 0.f;
+              wacc[j * 8 + q] = fmaf(de1, fmaxf(pre, 0.f), wacc[j * 8 + q]);
+            }
           }
         }
       }
@@ -357,14 +425,52 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     }
   }
   __syncthreads();
-  float* s_acc = reinterpret_cast<float*>(ap_smem);
+  float* s_acc = reinterpret_cast<float*>(ap_smem);            // [8][CH] mask sums | [2][CH] CTA totals | [8][CH] w_full sums
+  float* s_part = s_acc + AP_CWARPS * CH;
+  float* s_wacc = s_part + 2 * CH;
   if (wid < AP_CWARPS) {
 #pragma unroll
     for (int j = 0; j < NV; j++)
 #pragma unroll
-      for (int i = 0; i < 8; i++) s_acc[wid * CH + (j * 32 + lane) * 8 + i] = macc[j * 8 + i];
+      for (int i = 0; i < 8; i++) {
+        s_acc[wid * CH + (j * 32 + lane) * 8 + i] = macc[j * 8 + i];
+        s_wacc[wid * CH + (j * 32 + lane) * 8 + i] = wacc[j * 8 + i];
+      }
   }
   __syncthreads();
+  if constexpr (CL) {
+    cg::cluster_group cluster = cg::this_cluster();
+    for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+      float t = 0.f, u = 0.f;
+#pragma unroll
+      for (int w = 0; w < AP_CWARPS; w++) { t += s_acc[w * CH + c]; u += s_wacc[w * CH + c]; }
+      s_part[c] = t;
+      s_part[CH + c] = u;
+    }
+    cluster.sync();
+    const int cps = (CH + nsplit - 1) / nsplit;
+    for (int c = sp * cps + threadIdx.x; c < min(CH, (sp + 1) * cps); c += AP_THREADS) {
+      float t = 0.f, u = 0.f;
+      for (int q = 0; q < nsplit; q++) {                       // fixed order -> deterministic
+        const float* rp = cluster.map_shared_rank(s_part, q);
+        t += rp[c];
+        u += rp[CH + c];
+      }
+      datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+      if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
+      if (dwf_part) dwf_part[(int64_t)b * CH + c] += u;       // one writer per (b, c): plain accumulate over the time loop
+    }
+    cluster.sync();
+    return;
+  }
+  if (dwf_part) {
+    for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+      float u = 0.f;
+#pragma unroll
+      for (int w = 0; w < AP_CWARPS; w++) u += s_wacc[w * CH + c];
+      atomicAdd(dwf_part + (int64_t)b * CH + c, u);
+    }
+  }
   float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
   for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
     float t = 0.f;
@@ -399,22 +505,64 @@ int att_pipe_splits(int B) {
   int s = 296 / B;
   if (s < 1) s = 1;
   if (s > AP_MAXSPLIT) s = AP_MAXSPLIT;
+  if (g_opt_att_cluster && s > 8) s = 8;       // portable cluster size limit
   return s;
+}
+
+// launch with (optional) cluster dimension {ns,1,1} and the PDL attribute
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_att(void (*kernel)(KArgs...), dim3 grid, size_t smem, int cluster_x, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(AP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (g_opt_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    n++;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+static inline bool use_cluster(int ns, int R) {
+  // cluster mode keeps the raw scores of a CTA's rows in shared memory: ceil(R/ns) floats next to the ring
+  return g_opt_att_cluster && ns >= 2 && ns <= 8 && ((R + ns - 1) / ns) * 4 <= 16 * 1024;
 }
 
 template <typename T, int NV>
 static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
   using C = ApCfg<T, NV>;
+  constexpr int SM_MAX = C::SMEM + 16 * 1024;
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
     attr = true;
   }
   const int ns = att_pipe_splits(x.B);
-  LO_CUDA(launch_pdl(attention_fwd_pipe_kernel<T, NV>, dim3(ns, x.B), dim3(AP_THREADS), (size_t)C::SMEM, st,
-                     (const T*)x.att1, (const T*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre,
-                     x.gate_stride, x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc,
-                     g_opt_att_policy_att1, x.rows_per_img > 1 ? x.rows_per_img : 1));
+  const int rpi = x.rows_per_img > 1 ? x.rows_per_img : 1;
+  if (use_cluster(ns, x.R)) {
+    const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, true>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc, x.att2,
+                       x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R, ns,
+                       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
+  } else {
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, false>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1, (const T*)x.enc,
+                       x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R,
+                       ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
+  }
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -435,15 +583,21 @@ static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
   using C = ApCfg<T, NV>;
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
   const int ns = att_pipe_splits(x.B);
-  LO_CUDA(launch_pdl(attention_bwd_pipe_kernel<T, NV>, dim3(ns, x.B), dim3(AP_THREADS), (size_t)C::SMEM, st,
-                     (const T*)x.att1, (const T*)x.enc, x.att2, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx,
-                     x.dg_stride, x.dreg, x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf,
-                     x.dgp_bf, x.dctx_out, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc,
-                     g_opt_att_policy_att1));
+#define LO_BWD_ARGS                                                                                                              \
+  (const T*)x.att1, (const T*)x.enc, x.att2, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride, x.dreg, \
+      x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,       \
+      (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, x.dwf_part
+  if (use_cluster(ns, x.R)) {
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, true>, dim3(ns, x.B), (size_t)C::SMEM, ns, st, LO_BWD_ARGS));
+  } else {
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, false>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, LO_BWD_ARGS));
+  }
+#undef LO_BWD_ARGS
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -461,6 +615,9 @@ int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st) {
 
 }  // namespace lo
 
+namespace lo { extern long long* g_tc_dbg; }
+extern "C" int lo_debug_buffer(void* p) { lo::g_tc_dbg = (long long*)p; return LO_OK; }
+
 extern "C" int lo_set_option(const char* name, int value) {
   if (!name) return LO_EINVAL;
   if (!strcmp(name, "att_pipe")) lo::g_opt_att_pipe = value;
@@ -468,6 +625,13 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "att_policy_att1")) lo::g_opt_att_policy_att1 = value;
   else if (!strcmp(name, "att_nsplit")) lo::g_opt_att_nsplit = value;
   else if (!strcmp(name, "pdl")) lo::g_opt_pdl = value;
+  else if (!strcmp(name, "att_cluster")) lo::g_opt_att_cluster = value;
+  else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
+  else if (!strcmp(name, "l2_persist_mb")) {
+    // size of the L2 set-aside that evict_last / persisting accesses may occupy (0 = driver default)
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)value << 20);
+    if (e != cudaSuccess) return lo::fail(LO_ECUDA, "lo_set_option(l2_persist_mb): %s (%ld)", cudaGetErrorString(e), (long)e);
+  }
   else return lo::fail(LO_EINVAL, "lo_set_option: unknown option %s", name);
   return LO_OK;
 }

@@ -167,8 +167,10 @@ struct AttBwdArgs {
   float* de; float* datt2; float* dgp; int64_t dcat_stride; bf16* datt2_bf; bf16* dgp_bf; float* dctx_out;
   int B, R;
   void* work;
+  float* dwf_part;     // [B][A] running sum over the time loop of the full_att.weight gradient contributions (optional)
 };
 extern int g_opt_att_pipe;
+extern int g_opt_conv_mc;
 int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st);
 int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st);
 

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_bwd_kernel(
 //   dwf[a]      += sum_{b,r,t} de[b,t,r] * relu(att1[b,r,a] + att2[t,b,a])
 // grid (A/64, ceil(R/32), B), 128 threads, thread tile 4(r) x 4(a), time chunks of 32 staged in smem.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool WACC>
 __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, const float* __restrict__ out1,
                                                      int64_t o1_row, int64_t o1_step, const float* __restrict__ de,
                                                      const float* __restrict__ wf, T* __restrict__ datt1,
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
           const float pre = x[i][j] + a2v[j];
           const bool on = pre > 0.f;
           acc[i][j] += on ? dv[i] : 0.f;
-          wacc[j] = fmaf(dv[i], on ? pre : 0.f, wacc[j]);   // (never 0 * -inf: padded rows carry pre = -inf)
+          if (WACC) wacc[j] = fmaf(dv[i], on ? pre : 0.f, wacc[j]);   // (never 0 * -inf: padded rows carry pre = -inf)
         }
     }
     __syncthreads();
@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
 #pragma unroll
     for (int j = 0; j < 4; j++) stf(datt1 + ((int64_t)b * R + r) * A + a0 + tx * 4 + j, acc[i][j] * wv[j]);
   }
+  if (!WACC) return;
 #pragma unroll
   for (int j = 0; j < 4; j++) s_w[ty][tx * 4 + j] = wacc[j];
   __syncthreads();
@@ -1030,6 +1031,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   int* cnt = work_counters(a);
   float* part = work_partials(a);
   const BfViews bv = bf_views(a, d);
+  if (g_opt_att_pipe) LO_CUDA(cudaMemsetAsync(a->dmean, 0, (size_t)d.B * d.A * 4, st));    // [B][A] scratch for d w_full
   for (int t = d.T - 1; t >= 0; t--) {
     const int nrows = a->bt_host[t];
     float* dcat_t = a->dcat + (int64_t)t * d.B * d.O1;
@@ -1055,7 +1057,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
       AttBwdArgs x{a->att1, a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
                    a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T,
                    a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr,
-                   a->dctx + (int64_t)t * d.B * d.C, nrows, d.R, a->work};
+                   a->dctx + (int64_t)t * d.B * d.C, nrows, d.R, a->work, a->dmean};
       LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
     } else {
     dim3 grid(ns, nrows);
@@ -1129,8 +1131,15 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   LO_CUDA(cudaMemsetAsync(a->g_b_full, 0, 4, st));   // sum_r de = 0 exactly (softmax); reference value is rounding noise
   {
     dim3 grid(d.A / 64, cdiv(d.R, 32), d.B);
-    LO_DISPATCH_DT(dt, T, (datt1_kernel<T><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de, a->w_full,
-                                                                  (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
+    if (g_opt_att_pipe) {
+      // d w_full was accumulated per batch row by the attention backward kernels (dmean doubles as the [B][A] scratch)
+      LO_TRY(colsum(a->dmean, LO_F32, a->g_w_full, d.B, d.A, d.A, 0, st));
+      LO_DISPATCH_DT(dt, T, (datt1_kernel<T, false><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,
+                                                                           a->w_full, (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
+    } else {
+      LO_DISPATCH_DT(dt, T, (datt1_kernel<T, true><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,
+                                                                          a->w_full, (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
+    }
     LO_LAUNCH_OK();
   }
   // encoder_att: g_W = datt1^T enc ; g_b = colsum(datt1) ; denc = datt1 @ W_e

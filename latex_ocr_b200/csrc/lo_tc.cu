@@ -43,6 +43,35 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// multicast variants: the box lands at the same CTA-relative offset in every CTA of `mask` and completes on each one's mbarrier
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -114,6 +143,8 @@ struct TcParams {
   int out_f32, accumulate, relu;
   int kb_per_split, atomic;   // split-K over gridDim.z: fp32 atomics onto `out` (bias added by split 0)
   int w_evict_last;           // keep the B (weight) tiles in L2: the per-step decoder GEMMs re-read them every step
+  int half_w, half_h;         // MC=1 conv: box offset of the second half of the A tile (one of them is 0)
+  long long* dbg;             // optional: clock64 stamps of CTA (0,0,0) at the pipeline milestones (lo_debug_buffer)
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -127,7 +158,10 @@ struct TcSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int NT, int STAGES>
+// MC = 1: the two CTAs of a (2,1,1) cluster compute neighbouring N tiles of the SAME 128-row A tile; each loads one
+// 64-row half of A and multicasts it to both (halves the L2 -> SM traffic of A; the kernel is L2-bandwidth bound at
+// 128x128 tiles).  mapA then describes HALF boxes.
+template <int NT, int STAGES, int MC>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, TcParams p) {
   using SM = TcSmem<NT, STAGES>;
@@ -155,12 +189,14 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     w0 = (rem % p.tiles_w) * p.BW;
   }
 
+  const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < STAGES; s++) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
+      mbar_init(empty_bar + s, MC ? 2 : 1);       // MC: the slot is also written by the peer -> both MMA threads release it
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -169,9 +205,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
   pdl_wait();          // everything above touched only shared memory / TMEM / kernel parameters
   pdl_trigger();
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all(); else __syncthreads();   // peer barriers must be initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = MC ? cluster_ctarank() : 0;
+  if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -186,7 +224,17 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         uint8_t* sb = sa + SM::A_BYTES;
         mbar_expect_tx(full_bar + s, SM::STAGE_BYTES);
         const int kg = kb0 + kb;
-        if (p.conv) {
+        if (MC) {
+          uint8_t* sh = sa + crank * (SM::A_BYTES / 2);        // my half of the tile, delivered to both CTAs
+          if (p.conv) {
+            const int tap = kg / cpb, cb = kg % cpb;
+            const int r = tap / 3, q = tap % 3;
+            tma_load_4d_mc(sh, &mapA, full_bar + s, cb * TC_BK, w0 + (int)crank * p.half_w + q - p.pad,
+                           h0 + (int)crank * p.half_h + r - p.pad, img, (uint16_t)3);
+          } else {
+            tma_load_2d_mc(sh, &mapA, full_bar + s, kg * TC_BK, m0 + (int)crank * (TC_BM / 2), (uint16_t)3);
+          }
+        } else if (p.conv) {
           const int tap = kg / cpb, cb = kg % cpb;
           const int r = tap / 3, q = tap % 3;
           tma_load_4d(sa, &mapA, full_bar + s, cb * TC_BK, w0 + q - p.pad, h0 + r - p.pad, img);
@@ -194,7 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
           tma_load_2d(sa, &mapA, full_bar + s, kg * TC_BK, m0);
         }
         tma_load_2d_hint(sb, &mapB, full_bar + s, kg * TC_BK, n0, polB);
+        if (dbg && kb == 0) p.dbg[2] = clock64();
       }
+      if (dbg) p.dbg[3] = clock64();
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -205,6 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(full_bar + s, ph);
+        if (dbg && kb == 0) p.dbg[4] = clock64();
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
         const uint32_t sb = sa + SM::A_BYTES;
@@ -215,9 +266,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
           // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the 16 B-unit address field
           umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
+        if (MC) umma_commit_mc(empty_bar + s, (uint16_t)3);   // frees the slot in BOTH CTAs
+        else umma_commit(empty_bar + s);                       // frees the smem stage when these MMAs retire
       }
       umma_commit(tmem_full_bar);             // accumulator complete
+      if (dbg) p.dbg[5] = clock64();
     }
     __syncwarp();
   } else {
@@ -225,6 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     const int quad = warp & 3;
     const int row = quad * 32 + lane;          // row inside the 128-row tile == TMEM lane
     mbar_wait(tmem_full_bar, 0);
+    if (dbg && warp == 2 && lane == 0) p.dbg[6] = clock64();
     tc_fence_after();
     bool row_ok;
     int64_t row_off;
@@ -293,8 +347,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all(); else __syncthreads();   // a CTA may not exit while its peer can still multicast into it
+  if (dbg && threadIdx.x == 0) p.dbg[7] = clock64();
   if (warp == 1) tmem_dealloc(tmem_base, NT);
+  if (dbg && threadIdx.x == 32) p.dbg[8] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,30 +540,56 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return LO_OK;
 }
 
-template <int NT, int STAGES>
+int g_opt_conv_mc = 1;    // cluster-of-2 multicast of the A tile
+long long* g_tc_dbg = nullptr;
+
+template <int NT, int STAGES, int MC>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, int splits, cudaStream_t st) {
   using SM = TcSmem<NT, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    LO_CUDA(cudaFuncSetAttribute(tc_gemm_conv_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    LO_CUDA(cudaFuncSetAttribute(tc_gemm_conv_kernel<NT, STAGES, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(cdiv(p.N, NT), mtiles, splits);
-  LO_CUDA(launch_pdl(tc_gemm_conv_kernel<NT, STAGES>, grid, dim3(TC_THREADS), (size_t)SM::TOTAL, st, mA, mB, p));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SM::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (g_opt_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  if (MC) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 2;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    n++;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  LO_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_conv_kernel<NT, STAGES, MC>, mA, mB, p));
   LO_LAUNCH_OK();
   return LO_OK;
 }
 
-static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, TcParams& p, int mtiles, int splits, int nt, cudaStream_t st) {
+static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, TcParams& p, int mtiles, int splits, int nt, cudaStream_t st,
+                         int mc = 0) {
   const int KB = p.K / TC_BK;
   if (splits < 1) splits = 1;
   if (splits > KB) splits = KB;
   p.kb_per_split = cdiv(KB, splits);
   splits = cdiv(KB, p.kb_per_split);
   p.atomic = splits > 1 ? 1 : p.atomic;
-  if (nt == 64 && mtiles == 1 && p.kb_per_split > 4) return launch_tc<64, 8>(mA, mB, p, mtiles, splits, st);   // skinny: all K in flight
-  if (nt == 64) return launch_tc<64, 4>(mA, mB, p, mtiles, splits, st);
-  return launch_tc<128, 3>(mA, mB, p, mtiles, splits, st);
+  if (nt == 64 && mtiles == 1 && p.kb_per_split > 4) return launch_tc<64, 8, 0>(mA, mB, p, mtiles, splits, st);   // skinny: all K in flight
+  if (nt == 64) return launch_tc<64, 4, 0>(mA, mB, p, mtiles, splits, st);
+  if (mc) return launch_tc<128, 3, 1>(mA, mB, p, mtiles, splits, st);
+  return launch_tc<128, 3, 0>(mA, mB, p, mtiles, splits, st);
 }
 
 // splits > 1 (or atomic_acc): fp32 C only, partial sums are ADDED onto C with atomics (C must hold the base values)
@@ -517,13 +599,14 @@ int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* 
   LO_CHECK_ARG(K % 64 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && ldc >= (N + 7) / 8 * 8, "K%64, ld%8, ldc >= roundup8(N)");
   LO_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0, "16-byte alignment");
   CUtensorMap mA, mB;
+  const int NT = (N <= 64 || small_n_tile) ? 64 : 128;
+  const int mc = (g_opt_conv_mc && NT == 128 && cdiv(N, 128) % 2 == 0 && splits <= 1 && !atomic_acc) ? 1 : 0;
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
     cuuint64_t str[1] = {(cuuint64_t)lda * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)(mc ? 64 : 128)};
     LO_TRY(make_map(&mA, A, 2, dims, str, box));
   }
-  const int NT = (N <= 64 || small_n_tile) ? 64 : 128;
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t str[1] = {(cuuint64_t)ldw * 2};
@@ -536,7 +619,8 @@ int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* 
   p.bias = bias; p.mask = nullptr; p.out = C; p.ldc = ldc;
   p.out_f32 = (dtC == LO_F32); p.accumulate = accumulate; p.relu = relu; p.atomic = atomic_acc;
   p.w_evict_last = (M <= 128) ? 1 : 0;
-  return launch_tc_any(mA, mB, p, cdiv(M, TC_BM), splits, NT, st);
+  p.dbg = g_tc_dbg;
+  return launch_tc_any(mA, mB, p, cdiv(M, TC_BM), splits, NT, st, mc);
 }
 
 int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
@@ -553,13 +637,16 @@ int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask
   while (BW > 8 && BW / 2 >= Wo) BW /= 2;     // smallest power of two >= Wo (capped at 128)
   const int BH = 128 / BW;
   CUtensorMap mA, mB;
+  const int NT = Cout <= 64 ? 64 : 128;
+  const int mc = (g_opt_conv_mc && NT == 128 && cdiv(Cout, 128) % 2 == 0) ? 1 : 0;
+  // MC: each CTA of the pair loads one 64-position half of the tile (the first BH/2 rows, or the first BW/2 columns when BH == 1)
+  const int hbw = mc ? (BH >= 2 ? BW : BW / 2) : BW, hbh = mc ? (BH >= 2 ? BH / 2 : 1) : BH;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)hbw, (cuuint32_t)hbh, 1};
     LO_TRY(make_map(&mA, x, 4, dims, str, box));
   }
-  const int NT = Cout <= 64 ? 64 : 128;
   {
     cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
     cuuint64_t str[1] = {(cuuint64_t)9 * Cin * 2};
@@ -572,9 +659,11 @@ int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask
   p.BW = BW; p.BH = BH; p.tiles_w = cdiv(Wo, BW); p.tiles_h = cdiv(Ho, BH);
   p.bias = bias; p.mask = mask; p.out = y; p.ldc = Cout;
   p.out_f32 = 0; p.accumulate = 0; p.relu = relu;
+  p.half_w = (mc && BH < 2) ? BW / 2 : 0;
+  p.half_h = (mc && BH >= 2) ? BH / 2 : 0;
   const int mtiles = N * p.tiles_w * p.tiles_h;
   LO_CHECK_ARG(mtiles <= 65535, "too many M tiles for grid.y");
-  return launch_tc_any(mA, mB, p, mtiles, 1, NT, st);
+  return launch_tc_any(mA, mB, p, mtiles, 1, NT, st, mc);
 }
 
 
