@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  __shared__ __align__(16) float s_bias[NT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * NT;
@@ -277,9 +278,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     // ===== epilogue: warps 2..5 ; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
     const int quad = warp & 3;
     const int row = quad * 32 + lane;          // row inside the 128-row tile == TMEM lane
-    mbar_wait(tmem_full_bar, 0);
-    if (dbg && warp == 2 && lane == 0) p.dbg[6] = clock64();
-    tc_fence_after();
+    // while the main loop runs: stage the bias slice of this N tile in shared memory (a dependent global load per
+    // 8 columns inside the drain loop cost ~6 us per tile before)
+    {
+      const int te = threadIdx.x - 64;
+      if (te < NT) s_bias[te] = (p.bias && blockIdx.z == 0 && n0 + te < p.N) ? __ldg(p.bias + n0 + te) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     bool row_ok;
     int64_t row_off;
     if (p.conv) {
@@ -290,8 +295,18 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
       row_ok = (m0 + row) < p.M;
       row_off = (int64_t)(m0 + row) * p.ldc;
     }
+    const bool use_mask = p.mask && !p.out_f32 && !p.atomic;
+    mbar_wait(tmem_full_bar, 0);
+    if (dbg && warp == 2 && lane == 0) p.dbg[6] = clock64();
+    tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < NT; c += 32) {
+      uint4 mk4[4];
+      if (use_mask && row_ok) {                 // issue the mask loads of the whole chunk before the TMEM read
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+          if (n0 + c + g * 8 < p.N) mk4[g] = *reinterpret_cast<const uint4*>(p.mask + row_off + n0 + c + g * 8);
+      }
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective: no divergence around it
       if (!row_ok) continue;
@@ -300,12 +315,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         const int n = n0 + c + g * 8;
         if (n >= p.N) continue;
         float f[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[c + g * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[c + g * 8 + 4]);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]);
-        if (p.bias && blockIdx.z == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) f[i] += __ldg(p.bias + n + i);
-        }
+        for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]) + bb[i];
         if (p.atomic) {
           float* o = reinterpret_cast<float*>(p.out) + row_off + n;
 #pragma unroll
@@ -335,11 +349,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
           }
-          if (p.mask) {
-            float mk[8];
-            ld8(p.mask + row_off + n, mk);
+          if (use_mask) {
+            const uint32_t w[4] = {mk4[g].x, mk4[g].y, mk4[g].z, mk4[g].w};
 #pragma unroll
-            for (int i = 0; i < 8; i++) f[i] = mk[i] > 0.f ? f[i] : 0.f;
+            for (int i = 0; i < 4; i++) {
+              if (!(__uint_as_float(w[i] << 16) > 0.f)) f[2 * i] = 0.f;
+              if (!(__uint_as_float(w[i] & 0xffff0000u) > 0.f)) f[2 * i + 1] = 0.f;
+            }
           }
           st8(o, f);
         }
