@@ -102,6 +102,7 @@ int lo_relu_mask_cast(const float* g, const void* y, void* out, int dt, int64_t 
  * gctx [B][C] = gate*ctx (seq2seq_torch.py:311-312).  work: lo_attention_workspace_bytes(B, C) bytes.
  */
 int64_t lo_attention_workspace_bytes(int B, int C);
+int64_t lo_decoder_workspace_bytes(int B, int C);   /* `work` of lo_decoder_args: two attention regions (two row chains) */
 int lo_attention_forward(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                          const float* wf, float* alpha, int64_t alpha_stride, float* ctx,
                          float* gate_pre, int64_t gate_stride, float* gctx,
@@ -181,7 +182,7 @@ typedef struct lo_decoder_args {
   float* g_w_ih; float* g_b_ih;
   float* g_w_init; float* g_b_init;
   float* g_w_fc; float* g_b_fc;
-  void* work;              /* lo_attention_workspace_bytes(B, max(A,C)), zero-initialised once */
+  void* work;              /* lo_decoder_workspace_bytes(B, max(A,C)), zero-initialised once */
   void* bfwork;            /* optional (impl=TC, dt=bf16): bf16 staging for the hoisted tcgen05 GEMMs,
                               lo_decoder_bfwork_bytes(args) bytes */
 } lo_decoder_args;

@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
   }
 }
 
-int att_pipe_splits(int B) {
+int att_pipe_splits(int B, int hint = 0) {
+  if (hint > 0) return hint > 8 ? 8 : hint;
   if (g_opt_att_nsplit > 0) return g_opt_att_nsplit > AP_MAXSPLIT ? AP_MAXSPLIT : g_opt_att_nsplit;
   // two CTAs per SM are resident (smem): one full wave of <= 296 CTAs.  Measured at B=64, R=868 (bf16): 4 splits
   // (256 CTAs, 14 stages each) 25.9 us vs 9 splits (576 CTAs = 2 waves) 32.8 us — per-CTA start-up/combine
@@ -551,7 +552,7 @@ static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
     LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
     attr = true;
   }
-  const int ns = att_pipe_splits(x.B);
+  const int ns = att_pipe_splits(x.B, x.nsplit_hint);
   const int rpi = x.rows_per_img > 1 ? x.rows_per_img : 1;
   if (use_cluster(ns, x.R)) {
     const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
@@ -587,7 +588,7 @@ static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
     LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
-  const int ns = att_pipe_splits(x.B);
+  const int ns = att_pipe_splits(x.B, x.nsplit_hint);
 #define LO_BWD_ARGS                                                                                                              \
   (const T*)x.att1, (const T*)x.enc, x.att2, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride, x.dreg, \
       x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,       \
@@ -627,6 +628,8 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "pdl")) lo::g_opt_pdl = value;
   else if (!strcmp(name, "att_cluster")) lo::g_opt_att_cluster = value;
   else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
+  else if (!strcmp(name, "dec_streams")) { lo::g_opt_dec_streams = value; lo::g_opt_skinny8 = value >= 2 ? 0 : 1; }
+  else if (!strcmp(name, "skinny8")) lo::g_opt_skinny8 = value;
   else if (!strcmp(name, "l2_persist_mb")) {
     // size of the L2 set-aside that evict_last / persisting accesses may occupy (0 = driver default)
     cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)value << 20);

@@ -157,6 +157,7 @@ struct AttFwdArgs {
   int B, R;
   void* work;
   int rows_per_img;
+  int nsplit_hint;
 };
 struct AttBwdArgs {
   const void *att1, *enc;
@@ -168,9 +169,12 @@ struct AttBwdArgs {
   int B, R;
   void* work;
   float* dwf_part;     // [B][A] running sum over the time loop of the full_att.weight gradient contributions (optional)
+  int nsplit_hint;
 };
 extern int g_opt_att_pipe;
 extern int g_opt_conv_mc;
+extern int g_opt_dec_streams;
+extern int g_opt_skinny8;
 int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st);
 int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st);
 

@@ -794,10 +794,11 @@ static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a
 static int attention_forward_launch(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                                     const float* wf, float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre,
                                     int64_t gate_stride, float* gctx, bf16* gctx_bf, int B, int R, int C, void* work, cudaStream_t st,
-                                    int rpi = 1) {
+                                    int rpi = 1, int nsplit_hint = 0) {
   if (rpi < 1) rpi = 1;
   if (g_opt_att_pipe) {
-    AttFwdArgs x{att1, enc, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, B, R, work, rpi};
+    AttFwdArgs x{att1, enc, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, B, R, work, rpi,
+                 nsplit_hint};
     return attention_fwd_pipe(x, dt, C, st);
   }
   const int ns = att_splits(B);
@@ -858,39 +859,86 @@ static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_
   return LO_OK;
 }
 
-// one decoder step t with nrows active rows; tok: token ids consumed at this step
-static int forward_step(const lo_decoder_args* a, const Dims& d, int t, int nrows, const int64_t* tok, int64_t tok_stride,
+// a contiguous slice of batch rows processed on one stream.  The rows of a batch never interact inside the time loop
+// (only the hoisted weight-gradient GEMMs mix them), so the loop can run as independent half-batch chains on two
+// streams: while one chain streams att1/enc (HBM bound, all SMs) the other runs its latency-bound GEMM / LSTM kernels.
+struct Rows {
+  int row0, nrows;
+  void* work;       // attention workspace of this chain
+  int nsplit;       // attention split hint (0 = automatic)
+};
+int g_opt_dec_streams = 1;
+
+// one decoder step t for the rows of `rs`; tok: token ids consumed at this step (row 0 of the batch)
+static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Rows& rs, const int64_t* tok, int64_t tok_stride,
                         float* hd_t, int64_t hd_stride, const float* dmask_t, cudaStream_t st) {
   const int dt = a->dt;
-  float* h_prev = a->hall + (int64_t)t * d.B * d.D;
-  float* c_prev = a->call + (int64_t)t * d.B * d.D;
-  float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+  const int nrows = rs.nrows;
+  const int64_t r0 = rs.row0;
+  if (nrows <= 0) return LO_OK;
+  const size_t es = dt == LO_F32 ? 4 : 2;
+  float* h_prev = a->hall + ((int64_t)t * d.B + r0) * d.D;
+  float* c_prev = a->call + ((int64_t)t * d.B + r0) * d.D;
+  float* o1 = a->out1 + ((int64_t)t * d.B + r0) * d.O1;
+  float* gtmp = a->gtmp + r0 * d.G;
+  const int rpi = a->rows_per_img > 1 ? a->rows_per_img : 1;
+  const char* att1 = (const char*)a->att1 + (size_t)(r0 / rpi) * d.R * d.A * es;
+  const char* enc = (const char*)a->enc + (size_t)(r0 / rpi) * d.R * d.C * es;
   // [att2 | gate_pre | hh_pre] = h_prev @ [W_d; W_beta; W_hh]^T + b   (seq2seq_torch.py:187, :311, LSTMCell hh part)
   const BfViews bv = bf_views(a, d);
-  const size_t es = dt == LO_F32 ? 4 : 2;
   if (bv.on) {
-    LO_TRY(tc_gemm_nt_ex(bv.hall + (int64_t)t * d.B * d.D, d.D, (const bf16*)a->wcat1, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D, a->bcat1,
-                         0, 0, 1, 0, 1, st));
+    LO_TRY(tc_gemm_nt_ex(bv.hall + ((int64_t)t * d.B + r0) * d.D, d.D, (const bf16*)a->wcat1, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D,
+                         a->bcat1, 0, 0, 1, 0, 1, st));
   } else {
     LO_TRY(gemm_nt(h_prev, LO_F32, d.D, a->wcat1, dt, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D, a->bcat1, 0, 0, LO_IMPL_SIMT, st));
   }
-  LO_TRY(attention_forward_launch(a->att1, a->enc, dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
-                                  a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C,
-                                  bv.on ? bv.gctx + (int64_t)t * d.B * d.C : nullptr, nrows, d.R, d.C, a->work, st, a->rows_per_img));
+  LO_TRY(attention_forward_launch(att1, enc, dt, o1, d.O1, a->w_full, a->alphas + (r0 * d.T + t) * d.R, (int64_t)d.T * d.R,
+                                  a->ctx + ((int64_t)t * d.B + r0) * d.C, o1 + d.A, d.O1, a->gctx + ((int64_t)t * d.B + r0) * d.C,
+                                  bv.on ? bv.gctx + ((int64_t)t * d.B + r0) * d.C : nullptr, nrows, d.R, d.C, rs.work, st,
+                                  a->rows_per_img, rs.nsplit));
   // gates_x = (gate*ctx) @ W_ih[:, E:]^T
   if (bv.on) {
-    LO_TRY(tc_gemm_nt_ex(bv.gctx + (int64_t)t * d.B * d.C, d.C, (const bf16*)a->w_ih + d.E, d.E + d.C, a->gtmp, LO_F32, d.G, nrows, d.G,
-                         d.C, nullptr, 0, 0, 1, 0, 1, st));
+    LO_TRY(tc_gemm_nt_ex(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, (const bf16*)a->w_ih + d.E, d.E + d.C, gtmp, LO_F32, d.G, nrows,
+                         d.G, d.C, nullptr, 0, 0, 1, 0, 1, st));
   } else {
-    LO_TRY(gemm_nt(a->gctx + (int64_t)t * d.B * d.C, LO_F32, d.C, (const char*)a->w_ih + (size_t)d.E * es, dt, d.E + d.C, a->gtmp,
+    LO_TRY(gemm_nt(a->gctx + ((int64_t)t * d.B + r0) * d.C, LO_F32, d.C, (const char*)a->w_ih + (size_t)d.E * es, dt, d.E + d.C, gtmp,
                    LO_F32, d.G, nrows, d.G, d.C, nullptr, 0, 0, LO_IMPL_SIMT, st));
   }
-  LO_CUDA(launch_pdl(lstm_pw_fwd_kernel, dim3(cdiv((long)nrows * d.D, 256)), dim3(256), (size_t)0, st, (const float*)a->gtmp,
-                     (const float*)a->ptab, tok, tok_stride, (const float*)(o1 + d.A + d.C), (int64_t)d.O1, (const float*)c_prev,
-                     a->gates + (int64_t)t * d.B * d.G, a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D,
-                     bv.on ? bv.hall + (int64_t)(t + 1) * d.B * d.D : (bf16*)nullptr, hd_t, hd_stride, dmask_t, nrows, d.D, d.V));
+  LO_CUDA(launch_pdl(lstm_pw_fwd_kernel, dim3(cdiv((long)nrows * d.D, 256)), dim3(256), (size_t)0, st, (const float*)gtmp,
+                     (const float*)a->ptab, tok + r0 * tok_stride, tok_stride, (const float*)(o1 + d.A + d.C), (int64_t)d.O1,
+                     (const float*)c_prev, a->gates + ((int64_t)t * d.B + r0) * d.G, a->call + ((int64_t)(t + 1) * d.B + r0) * d.D,
+                     a->hall + ((int64_t)(t + 1) * d.B + r0) * d.D,
+                     bv.on ? bv.hall + ((int64_t)(t + 1) * d.B + r0) * d.D : (bf16*)nullptr,
+                     hd_t ? hd_t + r0 * hd_stride : (float*)nullptr, hd_stride,
+                     dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, nrows, d.D, d.V));
   LO_LAUNCH_OK();
   return LO_OK;
+}
+
+// fork/join helpers for the two-chain time loop (legal inside stream capture: the side stream joins back)
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+static int side_stream_init() {
+  if (g_side) return LO_OK;
+  LO_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+  LO_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+  LO_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+  return LO_OK;
+}
+static inline bool two_chains(const lo_decoder_args* a, const Dims& d) {
+  return g_opt_dec_streams >= 2 && d.B >= 32 && a->rows_per_img <= 1;
+}
+static inline Rows chain_rows(const lo_decoder_args* a, const Dims& d, int chain, int nchains, int active) {
+  // rows [0, half) -> chain 0, [half, B) -> chain 1; `active` = rows still decoding at this step (sorted by length)
+  const int half = nchains == 2 ? (d.B + 1) / 2 : d.B;
+  Rows r;
+  r.row0 = chain * half;
+  const int hi = chain == 0 ? (active < half ? active : half) : active;
+  r.nrows = hi - r.row0 > 0 ? hi - r.row0 : 0;
+  if (chain == 0 && nchains == 1) r.nrows = active;
+  r.work = (char*)a->work + (size_t)chain * lo_attention_workspace_bytes(d.B, d.C);
+  r.nsplit = nchains == 2 ? (148 / (half > 0 ? half : 1) > 0 ? 148 / half : 1) : 0;   // each chain fills one CTA slot per SM
+  return r;
 }
 
 }  // namespace lo
@@ -912,6 +960,8 @@ int64_t lo_sizeof_decoder_args(void) { return (int64_t)sizeof(lo_decoder_args); 
 int64_t lo_attention_workspace_bytes(int B, int C) {
   return 4096 + (int64_t)B * LO_ATT_MAXSPLIT * (C + 2) * 4;
 }
+/* the decoder entry points use two such regions (one per row chain) */
+int64_t lo_decoder_workspace_bytes(int B, int C) { return 2 * lo_attention_workspace_bytes(B, C); }
 
 int lo_attention_forward(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride, const float* wf,
                          float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre, int64_t gate_stride, float* gctx,
@@ -935,9 +985,23 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
   }
   LO_TRY(upload_dlen(a, st));
   LO_TRY(forward_prologue(a, d, st));
-  for (int t = 0; t < d.T; t++) {
-    const float* dm = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
-    LO_TRY(forward_step(a, d, t, a->bt_host[t], a->caps + t, a->caps_stride, a->hd + (int64_t)t * d.D, (int64_t)d.T * d.D, dm, st));
+  const int nchains = two_chains(a, d) ? 2 : 1;
+  if (nchains == 2) {
+    LO_TRY(side_stream_init());
+    LO_CUDA(cudaEventRecord(g_ev_fork, st));
+    LO_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
+  }
+  for (int chain = 0; chain < nchains; chain++) {
+    cudaStream_t cs = chain == 0 ? st : g_side;
+    for (int t = 0; t < d.T; t++) {
+      const float* dm = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+      const Rows rs = chain_rows(a, d, chain, nchains, a->bt_host[t]);
+      LO_TRY(forward_step(a, d, t, rs, a->caps + t, a->caps_stride, a->hd + (int64_t)t * d.D, (int64_t)d.T * d.D, dm, cs));
+    }
+  }
+  if (nchains == 2) {
+    LO_CUDA(cudaEventRecord(g_ev_join, g_side));
+    LO_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
   }
   // predictions = fc(dropout(h))  (seq2seq_torch.py:316), hoisted out of the loop
   const BfViews bvf = bf_views(a, d);
@@ -1028,44 +1092,65 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     const BfViews bz = bf_views(a, d);
     if (bz.on) LO_CUDA(cudaMemsetAsync(bz.dcat, 0, (size_t)d.T * d.B * d.O1 * 2, st));
   }
-  int* cnt = work_counters(a);
-  float* part = work_partials(a);
   const BfViews bv = bf_views(a, d);
   if (g_opt_att_pipe) LO_CUDA(cudaMemsetAsync(a->dmean, 0, (size_t)d.B * d.A * 4, st));    // [B][A] scratch for d w_full
-  for (int t = d.T - 1; t >= 0; t--) {
-    const int nrows = a->bt_host[t];
-    float* dcat_t = a->dcat + (int64_t)t * d.B * d.O1;
-    bf16* dcat_bf_t = bv.on ? bv.dcat + (int64_t)t * d.B * d.O1 : nullptr;
-    const float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
-    const float* dmul = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+  const int nchains = two_chains(a, d) ? 2 : 1;
+  if (nchains == 2) {
+    LO_TRY(side_stream_init());
+    LO_CUDA(cudaEventRecord(g_ev_fork, st));
+    LO_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
+  }
+  const cudaStream_t st_main = st;
+  for (int chain = 0; chain < nchains; chain++) {
+   st = chain == 0 ? st_main : g_side;
+   for (int t = d.T - 1; t >= 0; t--) {
+    const Rows rs = chain_rows(a, d, chain, nchains, a->bt_host[t]);
+    const int nrows = rs.nrows;
+    const int64_t r0 = rs.row0;
+    if (nrows <= 0) continue;
+    const size_t es = dt == LO_F32 ? 4 : 2;
+    float* dcat_t = a->dcat + ((int64_t)t * d.B + r0) * d.O1;
+    bf16* dcat_bf_t = bv.on ? bv.dcat + ((int64_t)t * d.B + r0) * d.O1 : nullptr;
+    const float* o1 = a->out1 + ((int64_t)t * d.B + r0) * d.O1;
+    float* dxh = a->dxh + r0 * (d.C + d.D);
+    const float* dmul = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D + r0 * d.T * d.D : nullptr;
     LO_CUDA(launch_pdl(lstm_pw_bwd_kernel, dim3(cdiv((long)nrows * d.D, 256)), dim3(256), (size_t)0, st,
-                       (const float*)(a->dhd + (int64_t)t * d.D), (int64_t)d.T * d.D, dmul, (const float*)(a->dxh + d.C),
-                       (int64_t)(d.C + d.D), a->dc, (const float*)(a->gates + (int64_t)t * d.B * d.G),
-                       (const float*)(a->call + (int64_t)t * d.B * d.D), (const float*)(a->call + (int64_t)(t + 1) * d.B * d.D),
-                       dcat_t + d.A + d.C, (int64_t)d.O1, bv.on ? dcat_bf_t + d.A + d.C : (bf16*)nullptr,
-                       bv.on ? a->dxh : (float*)nullptr, d.C, nrows, d.D));
+                       (const float*)(a->dhd + (int64_t)t * d.D + r0 * d.T * d.D), (int64_t)d.T * d.D, dmul, (const float*)(dxh + d.C),
+                       (int64_t)(d.C + d.D), a->dc + r0 * d.D, (const float*)(a->gates + ((int64_t)t * d.B + r0) * d.G),
+                       (const float*)(a->call + ((int64_t)t * d.B + r0) * d.D),
+                       (const float*)(a->call + ((int64_t)(t + 1) * d.B + r0) * d.D), dcat_t + d.A + d.C, (int64_t)d.O1,
+                       bv.on ? dcat_bf_t + d.A + d.C : (bf16*)nullptr, bv.on ? dxh : (float*)nullptr, d.C, nrows, d.D));
     LO_LAUNCH_OK();
     // [dgctx | dh_prev] = dG @ [W_ih[:, E:] | W_hh]
     if (bv.on) {
-      LO_TRY(tc_gemm_nt_ex(dcat_bf_t + d.A + d.C, d.O1, (const bf16*)a->wbwd1, d.G, a->dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G,
+      LO_TRY(tc_gemm_nt_ex(dcat_bf_t + d.A + d.C, d.O1, (const bf16*)a->wbwd1, d.G, dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G,
                            nullptr, 0, 0, 4, 1, 1, st));
     } else {
-      LO_TRY(gemm_nt(dcat_t + d.A + d.C, LO_F32, d.O1, a->wbwd1, dt, d.G, a->dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 0,
+      LO_TRY(gemm_nt(dcat_t + d.A + d.C, LO_F32, d.O1, a->wbwd1, dt, d.G, dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 0,
                      0, LO_IMPL_SIMT, st));
     }
+    const char* att1 = (const char*)a->att1 + (size_t)r0 * d.R * d.A * es;
+    const char* enc = (const char*)a->enc + (size_t)r0 * d.R * d.C * es;
+    const float* alpha_t = a->alphas + (r0 * d.T + t) * d.R;
+    const float* ctx_t = a->ctx + ((int64_t)t * d.B + r0) * d.C;
+    const float* dal_t_ptr = dal + (int64_t)t * dal_t + r0 * dal_b;
+    const float* sreg_t = a->sreg + r0 * d.T + t;
+    float* de_t = a->de + (r0 * d.T + t) * d.R;
+    float* dctx_t = a->dctx + ((int64_t)t * d.B + r0) * d.C;
     if (g_opt_att_pipe) {
-      AttBwdArgs x{a->att1, a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
-                   a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T,
-                   a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr,
-                   a->dctx + (int64_t)t * d.B * d.C, nrows, d.R, a->work, a->dmean};
+      AttBwdArgs x{att1, enc, o1, o1 + d.A, d.O1, a->w_full, alpha_t, (int64_t)d.T * d.R, ctx_t, dxh, d.C + d.D, dal_t_ptr, dal_b, sreg_t,
+                   d.T, de_t, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr, dctx_t, nrows, d.R, rs.work,
+                   a->dmean + r0 * d.A, rs.nsplit};
       LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
     } else {
+    int* cnt_c = (int*)rs.work;
+    float* part_c = (float*)((char*)rs.work + 4096);
     dim3 grid(ns, nrows);
 #define LO_ATT_BWD(TY_, NV)                                                                                                       \
   attention_bwd_kernel<TY_, NV><<<grid, LO_ATT_THREADS, 0, st>>>(                                                                 \
-      (const TY_*)a->att1, (const TY_*)a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,        \
-      a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T, a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, \
-      d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr, a->dctx + (int64_t)t * d.B * d.C, d.R, ns, cnt, part)
+      (const TY_*)att1, (const TY_*)enc, o1, o1 + d.A, d.O1, a->w_full, alpha_t, (int64_t)d.T * d.R, ctx_t, dxh, d.C + d.D, dal_t_ptr, \
+      dal_b, sreg_t, d.T, de_t, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr, dctx_t, d.R, ns, cnt_c,  \
+      part_c)
     if (dt == LO_F32) {
       if (d.C == 256) LO_ATT_BWD(float, 1); else if (d.C == 512) LO_ATT_BWD(float, 2); else LO_ATT_BWD(float, 4);
     } else {
@@ -1076,12 +1161,18 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     }
     // dh_prev += [datt2 | dgate_pre] @ [W_d ; W_beta]
     if (bv.on) {
-      LO_TRY(tc_gemm_nt_ex(dcat_bf_t, d.O1, (const bf16*)a->wbwd2, d.A + d.C, a->dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C,
+      LO_TRY(tc_gemm_nt_ex(dcat_bf_t, d.O1, (const bf16*)a->wbwd2, d.A + d.C, dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C,
                            nullptr, 0, 0, 4, 1, 1, st));
     } else {
-      LO_TRY(gemm_nt(dcat_t, LO_F32, d.O1, a->wbwd2, dt, d.A + d.C, a->dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C, nullptr, 1,
+      LO_TRY(gemm_nt(dcat_t, LO_F32, d.O1, a->wbwd2, dt, d.A + d.C, dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C, nullptr, 1,
                      0, LO_IMPL_SIMT, st));
     }
+   }
+  }
+  st = st_main;
+  if (nchains == 2) {
+    LO_CUDA(cudaEventRecord(g_ev_join, g_side));
+    LO_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
   }
   // dinit = [dh0 | dc0]
   LO_CUDA(cudaMemcpy2DAsync(a->dinit, (size_t)2 * d.D * 4, a->dxh + d.C, (size_t)(d.C + d.D) * 4, (size_t)d.D * 4, d.B,
@@ -1183,7 +1274,7 @@ int lo_decoder_greedy_hist(const lo_decoder_args* a, int64_t start_id, int64_t e
   LO_CUDA(cudaMemsetAsync(finished, 0, (size_t)d.B * 4, st));
   LO_TRY(forward_prologue(a, d, st));
   for (int t = 0; t < max_steps; t++) {
-    LO_TRY(forward_step(a, d, t, d.B, next_tok, 1, nullptr, 0, nullptr, st));
+    LO_TRY(forward_step(a, d, t, Rows{0, d.B, a->work, 0}, next_tok, 1, nullptr, 0, nullptr, st));
     // logits_t = fc(h_t)   (no dropout at decode time)
     LO_TRY(gemm_nt(a->hall + (int64_t)(t + 1) * d.B * d.D, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D,
                    a->b_fc, 0, 0, LO_IMPL_SIMT, st));
@@ -1230,7 +1321,7 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
     attr = true;
   }
   for (int t = 0; t < max_steps; t++) {
-    LO_TRY(forward_step(a, d, t, d.B, next_tok, 1, nullptr, 0, nullptr, st));
+    LO_TRY(forward_step(a, d, t, Rows{0, d.B, a->work, 0}, next_tok, 1, nullptr, 0, nullptr, st));
     float* h_new = a->hall + (int64_t)(t + 1) * d.B * d.D;
     float* c_new = a->call + (int64_t)(t + 1) * d.B * d.D;
     LO_TRY(gemm_nt(h_new, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));

@@ -148,7 +148,7 @@ struct TcParams {
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;   // warp 0: A-tile TMA producer, 1: TMEM + MMA issuer, 2..5: epilogue, 6: B-tile TMA producer
 
 template <int NT, int STAGES>
 struct TcSmem {
@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(full_bar + s, 1);
+      mbar_init(full_bar + s, 2);                 // two producer threads (A tiles / B tiles): one TMA issue costs ~200 cycles,
+                                                  // a single producer (~410 cycles per K block) could not feed the 256-cycle MMAs
       mbar_init(empty_bar + s, MC ? 2 : 1);       // MC: the slot is also written by the peer -> both MMA threads release it
     }
     mbar_init(tmem_full_bar, 1);
@@ -214,16 +215,14 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer, A tiles =====
       const int cpb = p.conv ? p.Cin / TC_BK : 1;
-      const uint64_t polB = p.w_evict_last ? l2_policy_evict_last() : l2_policy_evict_normal();
       for (int kb = 0; kb < KB; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
         uint8_t* sa = smem + s * SM::STAGE_BYTES;
-        uint8_t* sb = sa + SM::A_BYTES;
-        mbar_expect_tx(full_bar + s, SM::STAGE_BYTES);
+        mbar_expect_tx(full_bar + s, SM::A_BYTES);
         const int kg = kb0 + kb;
         if (MC) {
           uint8_t* sh = sa + crank * (SM::A_BYTES / 2);        // my half of the tile, delivered to both CTAs
@@ -242,10 +241,24 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         } else {
           tma_load_2d(sa, &mapA, full_bar + s, kg * TC_BK, m0);
         }
-        tma_load_2d_hint(sb, &mapB, full_bar + s, kg * TC_BK, n0, polB);
         if (dbg && kb == 0) p.dbg[2] = clock64();
+        if (dbg && kb < 40) p.dbg[64 + kb] = clock64();          // A-producer: TMA of K block kb issued
       }
       if (dbg) p.dbg[3] = clock64();
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ===== TMA producer, B tiles (weights) =====
+      const uint64_t polB = p.w_evict_last ? l2_policy_evict_last() : l2_policy_evict_normal();
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* sb = smem + s * SM::STAGE_BYTES + SM::A_BYTES;
+        mbar_expect_tx(full_bar + s, SM::B_BYTES);
+        tma_load_2d_hint(sb, &mapB, full_bar + s, (kb0 + kb) * TC_BK, n0, polB);
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -257,6 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(full_bar + s, ph);
         if (dbg && kb == 0) p.dbg[4] = clock64();
+        if (dbg && kb < 40) p.dbg[16 + kb] = clock64();          // MMA thread: K block kb landed
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
         const uint32_t sb = sa + SM::A_BYTES;
@@ -285,82 +299,105 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
       if (te < NT) s_bias[te] = (p.bias && blockIdx.z == 0 && n0 + te < p.N) ? __ldg(p.bias + n0 + te) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    bool row_ok;
-    int64_t row_off;
-    if (p.conv) {
-      const int h = h0 + row / p.BW, w = w0 + row % p.BW;
-      row_ok = (h < p.Ho) && (w < p.Wo);
-      row_off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
-    } else {
-      row_ok = (m0 + row) < p.M;
-      row_off = (int64_t)(m0 + row) * p.ldc;
-    }
     const bool use_mask = p.mask && !p.out_f32 && !p.atomic;
+    // Stores are transposed through shared memory (the pipeline ring is idle once the accumulator is complete): in TMEM
+    // order each thread owns one ROW, so a warp store touched 32 different rows (32 transactions per instruction);
+    // after the transpose a warp instruction covers whole 128 B / 64 B row segments.
+    float* stg = reinterpret_cast<float*>(smem) + quad * (32 * 36);      // 32 rows x 36 floats (pitch keeps 16 B alignment)
     mbar_wait(tmem_full_bar, 0);
     if (dbg && warp == 2 && lane == 0) p.dbg[6] = clock64();
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < NT; c += 32) {
-      uint4 mk4[4];
-      if (use_mask && row_ok) {                 // issue the mask loads of the whole chunk before the TMEM read
-#pragma unroll
-        for (int g = 0; g < 4; g++)
-          if (n0 + c + g * 8 < p.N) mk4[g] = *reinterpret_cast<const uint4*>(p.mask + row_off + n0 + c + g * 8);
-      }
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective: no divergence around it
-      if (!row_ok) continue;
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective
+      if (dbg && warp == 4 && lane == 0 && c == 0) p.dbg[9] = clock64();
 #pragma unroll
-      for (int g = 0; g < 4; g++) {
-        const int n = n0 + c + g * 8;
-        if (n >= p.N) continue;
-        float f[8];
-        const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[c + g * 8]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[c + g * 8 + 4]);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int g = 0; g < 8; g++)
+        *reinterpret_cast<uint4*>(&stg[lane * 36 + g * 4]) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      __syncwarp();
+      if (p.out_f32 || p.atomic) {
+        // lane -> (row = i*4 + lane/8, 4 columns at (lane%8)*4): one instruction = 4 rows x 128 B
+        const int c4 = (lane & 7) * 4;
+        const int n = n0 + c + c4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]) + bb[i];
-        if (p.atomic) {
-          float* o = reinterpret_cast<float*>(p.out) + row_off + n;
+        for (int i = 0; i < 8; i++) {
+          const int r = quad * 32 + i * 4 + (lane >> 3);
+          bool ok;
+          int64_t off;
+          if (p.conv) {
+            const int h = h0 + r / p.BW, w = w0 + r % p.BW;
+            ok = (h < p.Ho) && (w < p.Wo);
+            off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
+          } else {
+            ok = (m0 + r) < p.M;
+            off = (int64_t)(m0 + r) * p.ldc;
+          }
+          if (!ok || n >= p.N) continue;
+          float4 x = *reinterpret_cast<const float4*>(&stg[(i * 4 + (lane >> 3)) * 36 + c4]);
+          const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c + c4]);
+          x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+          float* o = reinterpret_cast<float*>(p.out) + off + n;
+          if (p.atomic) {
+            atomicAdd(o, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
+          } else {
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(o);
+              x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
+            }
+            if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            *reinterpret_cast<float4*>(o) = x;
+          }
+        }
+      } else {
+        // bf16 output: lane -> (row = i*8 + lane/4, 8 columns at (lane%4)*8): one instruction = 8 rows x 64 B
+        const int c8 = (lane & 3) * 8;
+        const int n = n0 + c + c8;
 #pragma unroll
-          for (int i = 0; i < 8; i++) atomicAdd(o + i, f[i]);
-        } else if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + row_off + n;
+        for (int i = 0; i < 4; i++) {
+          const int rl = i * 8 + (lane >> 2);
+          const int r = quad * 32 + rl;
+          bool ok;
+          int64_t off;
+          if (p.conv) {
+            const int h = h0 + r / p.BW, w = w0 + r % p.BW;
+            ok = (h < p.Ho) && (w < p.Wo);
+            off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
+          } else {
+            ok = (m0 + r) < p.M;
+            off = (int64_t)(m0 + r) * p.ldc;
+          }
+          if (!ok || n >= p.N) continue;
+          float f[8];
+          const float4 x0 = *reinterpret_cast<const float4*>(&stg[rl * 36 + c8]);
+          const float4 x1 = *reinterpret_cast<const float4*>(&stg[rl * 36 + c8 + 4]);
+          const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[c + c8]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[c + c8 + 4]);
+          f[0] = x0.x + b0.x; f[1] = x0.y + b0.y; f[2] = x0.z + b0.z; f[3] = x0.w + b0.w;
+          f[4] = x1.x + b1.x; f[5] = x1.y + b1.y; f[6] = x1.z + b1.z; f[7] = x1.w + b1.w;
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off + n;
           if (p.accumulate) {
             float old[8];
             ld8(o, old);
 #pragma unroll
-            for (int i = 0; i < 8; i++) f[i] += old[i];
+            for (int q = 0; q < 8; q++) f[q] += old[q];
           }
           if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
-          }
-          st8(o, f);
-        } else {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + row_off + n;
-          if (p.accumulate) {
-            float old[8];
-            ld8(o, old);
-#pragma unroll
-            for (int i = 0; i < 8; i++) f[i] += old[i];
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
+            for (int q = 0; q < 8; q++) f[q] = fmaxf(f[q], 0.f);
           }
           if (use_mask) {
-            const uint32_t w[4] = {mk4[g].x, mk4[g].y, mk4[g].z, mk4[g].w};
+            float mk[8];
+            ld8(p.mask + off + n, mk);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              if (!(__uint_as_float(w[i] << 16) > 0.f)) f[2 * i] = 0.f;
-              if (!(__uint_as_float(w[i] & 0xffff0000u) > 0.f)) f[2 * i + 1] = 0.f;
-            }
+            for (int q = 0; q < 8; q++) f[q] = mk[q] > 0.f ? f[q] : 0.f;
           }
           st8(o, f);
         }
       }
+      __syncwarp();       // the staging tile is rewritten by the next chunk
     }
+    if (dbg && warp == 4 && lane == 0) p.dbg[10] = clock64();
   }
   tc_fence_before();
   if (MC) cluster_sync_all(); else __syncthreads();   // a CTA may not exit while its peer can still multicast into it
@@ -414,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapDY);
     tma_prefetch_desc(&mapX);
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 2); mbar_init(empty_bar + s, 1); }   // two producers
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
@@ -435,16 +472,33 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
           const int img = ks / per_img, rem = ks % per_img;
           const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
           uint8_t* sa = smem + s * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          mbar_expect_tx(full_bar + s, A_BYTES);
           if (p.plain) {
             tma_load_2d(sa, &mapDY, full_bar + s, co0, ks * 128);
             tma_load_2d(sa + BOX, &mapDY, full_bar + s, co0 + 64, ks * 128);
-#pragma unroll
-            for (int j = 0; j < NT / 64; j++) tma_load_2d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, ks * 128);
           } else {
             tma_load_4d(sa, &mapDY, full_bar + s, co0, w0, h0, img);
             tma_load_4d(sa + BOX, &mapDY, full_bar + s, co0 + 64, w0, h0, img);
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 6) {
+      if (lane == 0) {            // second producer: the X (B operand) boxes
+        const int per_img = p.tiles_w * p.tiles_h;
+        for (int i = 0; i < KS; i++) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          const int ks = ks0 + i;
+          const int img = ks / per_img, rem = ks % per_img;
+          const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+          uint8_t* sb = smem + s * STAGE_BYTES + A_BYTES;
+          mbar_expect_tx(full_bar + s, B_BYTES);
+          if (p.plain) {
+#pragma unroll
+            for (int j = 0; j < NT / 64; j++) tma_load_2d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, ks * 128);
+          } else {
 #pragma unroll
             for (int j = 0; j < NT / 64; j++)
               tma_load_4d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, w0 + q - p.pad, h0 + r - p.pad, img);
@@ -475,19 +529,28 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
       __syncwarp();
     } else {
       const int quad = warp & 3;
-      const int co = co0 + quad * 32 + lane;
+      float* stg = reinterpret_cast<float*>(smem) + quad * (32 * 36);    // transpose staging in the (now idle) ring
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < NT; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
-        if (co < p.Cout) {
-          float* o = p.plain ? p.dw + (int64_t)co * p.ldc + ci0 + c : p.dw + ((int64_t)co * 9 + tap) * p.Cin + ci0 + c;
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (ci0 + c + j < p.Cin) atomicAdd(o + j, __uint_as_float(v[j]));
+        for (int g = 0; g < 8; g++)
+          *reinterpret_cast<uint4*>(&stg[lane * 36 + g * 4]) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        __syncwarp();
+        // one warp instruction = one 128 B row segment of dW -> coalesced red.global.add
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr++) {
+          const int co = co0 + quad * 32 + rr;
+          const int ci = ci0 + c + lane;
+          if (co < p.Cout && ci < p.Cin) {
+            float* o = p.plain ? p.dw + (int64_t)co * p.ldc + ci : p.dw + ((int64_t)co * 9 + tap) * p.Cin + ci;
+            atomicAdd(o, stg[rr * 36 + lane]);
+          }
         }
+        __syncwarp();
       }
     }
   }
@@ -558,6 +621,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
 
 int g_opt_conv_mc = 1;    // cluster-of-2 multicast of the A tile
 long long* g_tc_dbg = nullptr;
+int g_opt_skinny8 = 1;    // 8-stage (198 KB smem) config for M <= 128 GEMMs; off when two decoder chains share the SMs
 
 template <int NT, int STAGES, int MC>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, int splits, cudaStream_t st) {
@@ -602,7 +666,7 @@ static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, TcParams&
   p.kb_per_split = cdiv(KB, splits);
   splits = cdiv(KB, p.kb_per_split);
   p.atomic = splits > 1 ? 1 : p.atomic;
-  if (nt == 64 && mtiles == 1 && p.kb_per_split > 4) return launch_tc<64, 8, 0>(mA, mB, p, mtiles, splits, st);   // skinny: all K in flight
+  if (nt == 64 && mtiles == 1 && p.kb_per_split > 4 && g_opt_skinny8) return launch_tc<64, 8, 0>(mA, mB, p, mtiles, splits, st);   // skinny: all K in flight
   if (nt == 64) return launch_tc<64, 4, 0>(mA, mB, p, mtiles, splits, st);
   if (mc) return launch_tc<128, 3, 1>(mA, mB, p, mtiles, splits, st);
   return launch_tc<128, 3, 0>(mA, mB, p, mtiles, splits, st);
@@ -675,6 +739,7 @@ int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask
   p.BW = BW; p.BH = BH; p.tiles_w = cdiv(Wo, BW); p.tiles_h = cdiv(Ho, BH);
   p.bias = bias; p.mask = mask; p.out = y; p.ldc = Cout;
   p.out_f32 = 0; p.accumulate = 0; p.relu = relu;
+  p.dbg = g_tc_dbg;
   p.half_w = (mc && BH < 2) ? BW / 2 : 0;
   p.half_h = (mc && BH >= 2) ? BH / 2 : 0;
   const int mtiles = N * p.tiles_w * p.tiles_h;

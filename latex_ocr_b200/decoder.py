@@ -203,7 +203,7 @@ class DecoderWithAttention(nn.Module):
             t["row_loss"] = z(B * T + B * R)
             t["loss"] = z(4)
             t["sreg"] = z(B, max(T, 2))
-            t["work"] = z(int(_lib.lib().lo_attention_workspace_bytes(B, max(A, C))), dtype=torch.uint8)
+            t["work"] = z(int(_lib.lib().lo_decoder_workspace_bytes(B, max(A, C))), dtype=torch.uint8)
             t["dropout_mask"] = z(B, T, D)
             ws["bt"] = (ctypes.c_int32 * T)(*([B] * T))
             self._ws[key] = ws

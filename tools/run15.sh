@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== skinny timing"; timeout 120 python tools/skinny_timing.py 2>&1 | tail -4 | cut -c1-420
+echo "== tests"; timeout -k 10 400 python -m pytest tests -m gpu -q --timeout=120 -p no:cacheprovider --tb=short 2>&1 | tail -8 | cut -c1-300
+echo "== tests dec_streams=2"; LO_OPTS=dec_streams=2 timeout -k 10 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc.py -m gpu -q --timeout=120 -p no:cacheprovider --tb=short 2>&1 | tail -8 | cut -c1-300
+for opts in "dec_streams=1" "dec_streams=2" "dec_streams=2,skinny8=1"; do
+  echo "== bench $opts"
+  LO_OPTS=$opts timeout -k 10 300 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_opt.log 2> gpurun_out/bench_opt.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_opt.log').read().strip().splitlines()[-1])
+    a=d['roofline_all']
+    print("  ms/step %.2f  img/s %.0f  e2e %.2f ms  att %.1f us (%.2f)  conv %.2f ms (%.2f)  dec %.2f ms" % (d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], a['attention']['us_per_launch'], a['attention']['frac'], a['conv']['ms'], a['conv']['frac'], a['phases']['decoder_fwd_bwd_ms']))
+except Exception as e:
+    print("  FAILED", e); print(open('gpurun_out/bench_opt.err').read()[-800:])
+PY
+done

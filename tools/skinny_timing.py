@@ -20,5 +20,5 @@ for (M, N, K) in ((64, 3072, 512), (64, 2048, 512)):
         torch.cuda.synchronize(); e0.record(); run(); e1.record(); torch.cuda.synchronize()
         L.lo_debug_buffer(None)
         d = dbg.cpu().tolist()
-        names = ["start", "setup done", "1st TMA issued", "all TMA issued", "1st full", "last commit", "tmem full seen", "pre-dealloc", "end"]
+        names = ["start", "setup done", "1st TMA issued", "all TMA issued", "1st full", "last commit", "tmem full seen", "pre-dealloc", "end", "epi 1st tmem_ld done", "epi loop done"]
         print("M%d N%d K%d cold=%d  event %.1f us | cycles since start:" % (M, N, K, cold, e0.elapsed_time(e1) * 1e3), {n: d[i] - d[0] for i, n in enumerate(names)})
