@@ -70,6 +70,12 @@ int lo_colsum(const void* X, int dt, float* out, int M, int N, int64_t ld, int a
  * (img2seq_torch.py:115-117); out [N][H/2][W/2][64] */
 int lo_conv1_pool_forward(const float* img, const float* w, const float* bias, void* out, int dt,
                           int N, int H, int W, void* stream);
+/* same with the image as uint8 pixels [N][H][W] (what pad_batch_images produces, model/utils/image.py:27-64): 4x less
+ * host->device traffic; pixel values 0..255 are exact in fp32, so results are identical */
+int lo_conv1_pool_forward_u8(const uint8_t* img, const float* w, const float* bias, void* out, int dt,
+                             int N, int H, int W, void* stream);
+int lo_conv1_pool_wgrad_u8(const uint8_t* img, const float* w, const float* bias, const void* dpool, int dt,
+                           float* dw, float* db, int N, int H, int W, void* stream);
 /* conv1 weight/bias gradient from the POOLED output gradient; recomputes conv1 to find the
  * ReLU mask and pool argmax (first maximum in window scan order, as PyTorch) */
 int lo_conv1_pool_wgrad(const float* img, const float* w, const float* bias, const void* dpool, int dt,

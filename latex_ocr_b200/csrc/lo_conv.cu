@@ -9,8 +9,11 @@ namespace lo {
 // conv1 (Cin = 1) + bias + ReLU + 2x2 max-pool, fused.  Memory-bound: 4 B/pixel in, 64 ch out.
 // thread <-> (pooled position, group of 8 output channels)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) conv1_pool_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+__device__ __forceinline__ float ldpix(const float* p) { return *p; }
+__device__ __forceinline__ float ldpix(const uint8_t* p) { return (float)*p; }
+
+template <typename T, typename TI>
+__global__ void __launch_bounds__(256) conv1_pool_fwd_kernel(const TI* __restrict__ img, const float* __restrict__ w,
                                                               const float* __restrict__ bias, T* __restrict__ out,
                                                               int N, int H, int W) {
   __shared__ float sw[64 * 9];
@@ -27,14 +30,14 @@ __global__ void __launch_bounds__(256) conv1_pool_fwd_kernel(const float* __rest
     const int ho = (int)(p % Hp);
     const int n = (int)(p / Hp);
     float x[4][4];
-    const float* ib = img + (int64_t)n * H * W;
+    const TI* ib = img + (int64_t)n * H * W;
 #pragma unroll
     for (int dy = 0; dy < 4; dy++) {
       const int hi = 2 * ho - 1 + dy;
 #pragma unroll
       for (int dx = 0; dx < 4; dx++) {
         const int wi = 2 * wo - 1 + dx;
-        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? ib[(int64_t)hi * W + wi] : 0.f;
+        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? ldpix(ib + (int64_t)hi * W + wi) : 0.f;
       }
     }
     float o[8];
@@ -61,8 +64,8 @@ __global__ void __launch_bounds__(256) conv1_pool_fwd_kernel(const float* __rest
 
 // conv1 weight gradient from the pooled-output gradient (recompute conv1 -> argmax + ReLU mask).
 // warp <-> 8 channels (blockDim = 256: warp id = channel group), lane <-> pooled position.
-template <typename T>
-__global__ void __launch_bounds__(256) conv1_pool_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ w,
+template <typename T, typename TI>
+__global__ void __launch_bounds__(256) conv1_pool_wgrad_kernel(const TI* __restrict__ img, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const T* __restrict__ dpool,
                                                                 float* __restrict__ dw, float* __restrict__ db,
                                                                 int N, int H, int W) {
@@ -90,14 +93,14 @@ __global__ void __launch_bounds__(256) conv1_pool_wgrad_kernel(const float* __re
     const int ho = (int)(p % Hp);
     const int n = (int)(p / Hp);
     float x[4][4];
-    const float* ib = img + (int64_t)n * H * W;
+    const TI* ib = img + (int64_t)n * H * W;
 #pragma unroll
     for (int dy = 0; dy < 4; dy++) {
       const int hi = 2 * ho - 1 + dy;
 #pragma unroll
       for (int dx = 0; dx < 4; dx++) {
         const int wi = 2 * wo - 1 + dx;
-        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? ib[(int64_t)hi * W + wi] : 0.f;
+        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? ldpix(ib + (int64_t)hi * W + wi) : 0.f;
       }
     }
     float g[8];
@@ -408,29 +411,52 @@ using namespace lo;
 
 extern "C" {
 
-int lo_conv1_pool_forward(const float* img, const float* w, const float* bias, void* out, int dt, int N, int H, int W,
-                          void* stream) {
+static int conv1_fwd(const void* img, int u8, const float* w, const float* bias, void* out, int dt, int N, int H, int W, cudaStream_t st) {
   LO_CHECK_ARG(img && w && bias && out, "null pointer");
   LO_CHECK_ARG(N > 0 && H >= 2 && W >= 2, "shape");
-  cudaStream_t st = (cudaStream_t)stream;
   const int64_t work = (int64_t)N * (H / 2) * (W / 2) * 8;
-  LO_DISPATCH_DT(dt, T, (conv1_pool_fwd_kernel<T><<<grid_for(work, 256), 256, 0, st>>>(img, w, bias, (T*)out, N, H, W)));
+  const int grid = grid_for(work, 256);
+  if (u8) {
+    LO_DISPATCH_DT(dt, T, (conv1_pool_fwd_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, w, bias, (T*)out, N, H, W)));
+  } else {
+    LO_DISPATCH_DT(dt, T, (conv1_pool_fwd_kernel<T, float><<<grid, 256, 0, st>>>((const float*)img, w, bias, (T*)out, N, H, W)));
+  }
   LO_LAUNCH_OK();
   return LO_OK;
 }
 
-int lo_conv1_pool_wgrad(const float* img, const float* w, const float* bias, const void* dpool, int dt, float* dw,
-                        float* db, int N, int H, int W, void* stream) {
+static int conv1_wgrad(const void* img, int u8, const float* w, const float* bias, const void* dpool, int dt, float* dw, float* db,
+                       int N, int H, int W, cudaStream_t st) {
   LO_CHECK_ARG(img && w && bias && dpool && dw && db, "null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
   LO_CUDA(cudaMemsetAsync(dw, 0, 64 * 9 * sizeof(float), st));
   LO_CUDA(cudaMemsetAsync(db, 0, 64 * sizeof(float), st));
   const int64_t npos = (int64_t)N * (H / 2) * (W / 2);
   int grid = (int)((npos + 31) / 32);
   if (grid > 148 * 4) grid = 148 * 4;
-  LO_DISPATCH_DT(dt, T, (conv1_pool_wgrad_kernel<T><<<grid, 256, 0, st>>>(img, w, bias, (const T*)dpool, dw, db, N, H, W)));
+  if (u8) {
+    LO_DISPATCH_DT(dt, T, (conv1_pool_wgrad_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, w, bias, (const T*)dpool, dw, db, N, H, W)));
+  } else {
+    LO_DISPATCH_DT(dt, T, (conv1_pool_wgrad_kernel<T, float><<<grid, 256, 0, st>>>((const float*)img, w, bias, (const T*)dpool, dw, db, N, H, W)));
+  }
   LO_LAUNCH_OK();
   return LO_OK;
+}
+
+int lo_conv1_pool_forward(const float* img, const float* w, const float* bias, void* out, int dt, int N, int H, int W,
+                          void* stream) {
+  return conv1_fwd(img, 0, w, bias, out, dt, N, H, W, (cudaStream_t)stream);
+}
+int lo_conv1_pool_forward_u8(const uint8_t* img, const float* w, const float* bias, void* out, int dt, int N, int H, int W,
+                             void* stream) {
+  return conv1_fwd(img, 1, w, bias, out, dt, N, H, W, (cudaStream_t)stream);
+}
+int lo_conv1_pool_wgrad(const float* img, const float* w, const float* bias, const void* dpool, int dt, float* dw,
+                        float* db, int N, int H, int W, void* stream) {
+  return conv1_wgrad(img, 0, w, bias, dpool, dt, dw, db, N, H, W, (cudaStream_t)stream);
+}
+int lo_conv1_pool_wgrad_u8(const uint8_t* img, const float* w, const float* bias, const void* dpool, int dt, float* dw,
+                           float* db, int N, int H, int W, void* stream) {
+  return conv1_wgrad(img, 1, w, bias, dpool, dt, dw, db, N, H, W, (cudaStream_t)stream);
 }
 
 int lo_conv3x3(const void* x, const void* w, const float* bias, const void* mask, void* y, int dt, int N, int H, int W,

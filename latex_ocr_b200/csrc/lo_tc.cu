@@ -299,105 +299,82 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
       if (te < NT) s_bias[te] = (p.bias && blockIdx.z == 0 && n0 + te < p.N) ? __ldg(p.bias + n0 + te) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    bool row_ok;
+    int64_t row_off;
+    if (p.conv) {
+      const int h = h0 + row / p.BW, w = w0 + row % p.BW;
+      row_ok = (h < p.Ho) && (w < p.Wo);
+      row_off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
+    } else {
+      row_ok = (m0 + row) < p.M;
+      row_off = (int64_t)(m0 + row) * p.ldc;
+    }
     const bool use_mask = p.mask && !p.out_f32 && !p.atomic;
-    // Stores are transposed through shared memory (the pipeline ring is idle once the accumulator is complete): in TMEM
-    // order each thread owns one ROW, so a warp store touched 32 different rows (32 transactions per instruction);
-    // after the transpose a warp instruction covers whole 128 B / 64 B row segments.
-    float* stg = reinterpret_cast<float*>(smem) + quad * (32 * 36);      // 32 rows x 36 floats (pitch keeps 16 B alignment)
     mbar_wait(tmem_full_bar, 0);
     if (dbg && warp == 2 && lane == 0) p.dbg[6] = clock64();
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < NT; c += 32) {
+      uint4 mk4[4];
+      if (use_mask && row_ok) {                 // issue the mask loads of the whole chunk before the TMEM read
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+          if (n0 + c + g * 8 < p.N) mk4[g] = *reinterpret_cast<const uint4*>(p.mask + row_off + n0 + c + g * 8);
+      }
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective
-      if (dbg && warp == 4 && lane == 0 && c == 0) p.dbg[9] = clock64();
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective: no divergence around it
+      if (!row_ok) continue;
 #pragma unroll
-      for (int g = 0; g < 8; g++)
-        *reinterpret_cast<uint4*>(&stg[lane * 36 + g * 4]) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-      __syncwarp();
-      if (p.out_f32 || p.atomic) {
-        // lane -> (row = i*4 + lane/8, 4 columns at (lane%8)*4): one instruction = 4 rows x 128 B
-        const int c4 = (lane & 7) * 4;
-        const int n = n0 + c + c4;
+      for (int g = 0; g < 4; g++) {
+        const int n = n0 + c + g * 8;
+        if (n >= p.N) continue;
+        float f[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[c + g * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[c + g * 8 + 4]);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int r = quad * 32 + i * 4 + (lane >> 3);
-          bool ok;
-          int64_t off;
-          if (p.conv) {
-            const int h = h0 + r / p.BW, w = w0 + r % p.BW;
-            ok = (h < p.Ho) && (w < p.Wo);
-            off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
-          } else {
-            ok = (m0 + r) < p.M;
-            off = (int64_t)(m0 + r) * p.ldc;
-          }
-          if (!ok || n >= p.N) continue;
-          float4 x = *reinterpret_cast<const float4*>(&stg[(i * 4 + (lane >> 3)) * 36 + c4]);
-          const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c + c4]);
-          x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-          float* o = reinterpret_cast<float*>(p.out) + off + n;
-          if (p.atomic) {
-            atomicAdd(o, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
-          } else {
-            if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(o);
-              x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
-            }
-            if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            *reinterpret_cast<float4*>(o) = x;
-          }
-        }
-      } else {
-        // bf16 output: lane -> (row = i*8 + lane/4, 8 columns at (lane%4)*8): one instruction = 8 rows x 64 B
-        const int c8 = (lane & 3) * 8;
-        const int n = n0 + c + c8;
+        for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]) + bb[i];
+        if (p.atomic) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + n;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int rl = i * 8 + (lane >> 2);
-          const int r = quad * 32 + rl;
-          bool ok;
-          int64_t off;
-          if (p.conv) {
-            const int h = h0 + r / p.BW, w = w0 + r % p.BW;
-            ok = (h < p.Ho) && (w < p.Wo);
-            off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
-          } else {
-            ok = (m0 + r) < p.M;
-            off = (int64_t)(m0 + r) * p.ldc;
-          }
-          if (!ok || n >= p.N) continue;
-          float f[8];
-          const float4 x0 = *reinterpret_cast<const float4*>(&stg[rl * 36 + c8]);
-          const float4 x1 = *reinterpret_cast<const float4*>(&stg[rl * 36 + c8 + 4]);
-          const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[c + c8]);
-          const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[c + c8 + 4]);
-          f[0] = x0.x + b0.x; f[1] = x0.y + b0.y; f[2] = x0.z + b0.z; f[3] = x0.w + b0.w;
-          f[4] = x1.x + b1.x; f[5] = x1.y + b1.y; f[6] = x1.z + b1.z; f[7] = x1.w + b1.w;
-          bf16* o = reinterpret_cast<bf16*>(p.out) + off + n;
+          for (int i = 0; i < 8; i++) atomicAdd(o + i, f[i]);
+        } else if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + n;
           if (p.accumulate) {
             float old[8];
             ld8(o, old);
 #pragma unroll
-            for (int q = 0; q < 8; q++) f[q] += old[q];
+            for (int i = 0; i < 8; i++) f[i] += old[i];
           }
           if (p.relu) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) f[q] = fmaxf(f[q], 0.f);
+            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
+          }
+          st8(o, f);
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + row_off + n;
+          if (p.accumulate) {
+            float old[8];
+            ld8(o, old);
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] += old[i];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
           }
           if (use_mask) {
-            float mk[8];
-            ld8(p.mask + off + n, mk);
+            const uint32_t w[4] = {mk4[g].x, mk4[g].y, mk4[g].z, mk4[g].w};
 #pragma unroll
-            for (int q = 0; q < 8; q++) f[q] = mk[q] > 0.f ? f[q] : 0.f;
+            for (int i = 0; i < 4; i++) {
+              if (!(__uint_as_float(w[i] << 16) > 0.f)) f[2 * i] = 0.f;
+              if (!(__uint_as_float(w[i] & 0xffff0000u) > 0.f)) f[2 * i + 1] = 0.f;
+            }
           }
           st8(o, f);
         }
       }
-      __syncwarp();       // the staging tile is rewritten by the next chunk
     }
-    if (dbg && warp == 4 && lane == 0) p.dbg[10] = clock64();
   }
   tc_fence_before();
   if (MC) cluster_sync_all(); else __syncthreads();   // a CTA may not exit while its peer can still multicast into it

@@ -139,21 +139,24 @@ class EncoderCNN(nn.Module):
             self._shadow_fresh = True
 
     def forward_raw(self, img, need_grad=False):
-        """img: CUDA float32 [N,1,H,W] (raw 0..255 like img2seq_torch.py:115-117).  Returns the
+        """img: CUDA float32 or uint8 [N,1,H,W] (raw 0..255 like img2seq_torch.py:115-117; uint8 = 4x less H2D traffic).  Returns the
         encoder output in storage dtype [N,H',W',512] (a workspace buffer, overwritten by the next call)."""
         L = _lib.lib()
         if img.dim() != 4 or img.size(1) != 1:
             raise ValueError("img must be [N,1,H,W]")
         if not img.is_cuda:
             raise _lib.LatexOcrB200Error("EncoderCNN runs on CUDA tensors only (no CPU fallback)")
-        img = img.contiguous().float()
+        if img.dtype != torch.uint8:
+            img = img.float()
+        img = img.contiguous()
         N, _, H, W = img.shape
         ws = self._workspace(N, H, W, need_grad)
         self.sync_shadow()
         st, dt, impl, S = stream_ptr(), _dt(self.precision), self._impl(), self.store
         A = ws["acts"]
         ws["img"] = img
-        check(L.lo_conv1_pool_forward(ptr(img), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), dt, N, H, W, st))
+        conv1 = L.lo_conv1_pool_forward_u8 if img.dtype == torch.uint8 else L.lo_conv1_pool_forward
+        check(conv1(ptr(img), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), dt, N, H, W, st))
         x = A["P0"]
         for idx, cin, cout, pad, pool in _LAYERS[1:]:
             y = A["Y" + idx]
@@ -201,7 +204,8 @@ class EncoderCNN(nn.Module):
                 ysrc = A[src]
                 check(L.lo_maxpool_backward(ptr(ysrc), ptr(A[xin]), ptr(G[xin]), ptr(G[src]), dt, N, ysrc.shape[1], ysrc.shape[2],
                                             ysrc.shape[3], pool_k[0], pool_k[1], st))
-        check(L.lo_conv1_pool_wgrad(ptr(ws["img"]), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
+        wg1 = L.lo_conv1_pool_wgrad_u8 if ws["img"].dtype == torch.uint8 else L.lo_conv1_pool_wgrad
+        check(wg1(ptr(ws["img"]), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
                                     ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))
 
     def forward(self, img):

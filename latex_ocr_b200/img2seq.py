@@ -67,6 +67,12 @@ class Img2SeqModel:
         self.encoder.store.ensure_adam(lr)
         self.decoder.store.ensure_adam(lr)
 
+    def set_lr(self, lr):
+        """Learning rate of both fused Adam optimisers (a device scalar read by the kernel: works under graph replay)."""
+        self.lr = float(lr)
+        self.encoder.store.set_lr(lr)
+        self.decoder.store.set_lr(lr)
+
     def train_mode(self, flag=True):
         self.encoder.train(flag)
         self.decoder.train(flag)
@@ -113,7 +119,7 @@ class Img2SeqModel:
         T = L - 1
         if not self.use_graph:
             mask = self.decoder.make_dropout_mask(N, T)
-            loss = self._step_body(img_d.float(), caps_d, decode_lengths, mask)
+            loss = self._step_body(img_d if img_d.dtype == torch.uint8 else img_d.float(), caps_d, decode_lengths, mask)
         else:
             loss = self._graph_step(img_d, caps_d, decode_lengths)
         if sync:
@@ -121,11 +127,11 @@ class Img2SeqModel:
         return loss
 
     def _graph_step(self, img_d, caps_d, decode_lengths):
-        key = (tuple(img_d.shape), tuple(caps_d.shape), self.decoder.training)
+        key = (tuple(img_d.shape), img_d.dtype, tuple(caps_d.shape), self.decoder.training)
         g = self._graphs.get(key)
         if g is None:
             N, T = caps_d.shape[0], caps_d.shape[1] - 1
-            st = {"img": torch.zeros(img_d.shape, dtype=torch.float32, device=self.device),
+            st = {"img": torch.zeros(img_d.shape, dtype=torch.uint8 if img_d.dtype == torch.uint8 else torch.float32, device=self.device),
                   "caps": torch.zeros(caps_d.shape, dtype=torch.int64, device=self.device)}
             st["img"].copy_(img_d)
             st["caps"].copy_(caps_d)
@@ -171,7 +177,8 @@ class Img2SeqModel:
         nimg = 0
         for i, (img, formula) in enumerate(minibatches(train_set, batch_size)):
             img = pad_batch_images(img)                                            # utils/image.py:47 (255 padding)
-            img = torch.from_numpy(img).float().permute(0, 3, 1, 2)                # img2seq_torch.py:115-117
+            img = torch.from_numpy(img).permute(0, 3, 1, 2)                        # img2seq_torch.py:115-117; kept uint8: conv1
+                                                                                   # casts on the GPU (4x less H2D, same values)
             formula, _ = pad_batch_formulas(formula, self._vocab.id_pad, self._vocab.id_end)
             formula = torch.from_numpy(formula.astype(np.int64))                   # :118
             loss_eval = self.getLoss(img, formula=formula, lr=getattr(lr_schedule, "lr", None),

@@ -217,3 +217,17 @@ def test_attention_kernel_versions_agree_on_a_full_step():
     assert abs(res[0][0] - res[1][0]) / abs(res[0][0]) < 1e-6
     for i in (1, 2):
         assert (res[0][i] - res[1][i]).abs().max().item() <= 1e-4 * res[0][i].abs().max().item() + 1e-8
+
+
+def test_uint8_image_upload_equals_float_path():
+    """pad_batch_images yields uint8; conv1 can take it directly (4x less H2D).  0..255 are exact in fp32 -> same loss."""
+    rm = _oracle()
+    V = 40
+    pe, pd = rm.init_params(V, seed=2)
+    img, formula = rm.synthetic_batch(2, 32, 64, V, 3, 5, seed=3)
+    m1 = build_model(V, pe, pd, "fp32")
+    m2 = build_model(V, pe, pd, "fp32")
+    a = m1.getLoss(img, formula)
+    b = m2.getLoss(img.to(torch.uint8), formula)
+    assert a == b
+    assert torch.equal(m1.encoder.store.grad, m2.encoder.store.grad)
