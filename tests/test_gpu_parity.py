@@ -230,4 +230,5 @@ def test_uint8_image_upload_equals_float_path():
     a = m1.getLoss(img, formula)
     b = m2.getLoss(img.to(torch.uint8), formula)
     assert a == b
-    assert torch.equal(m1.encoder.store.grad, m2.encoder.store.grad)
+    g1, g2 = m1.encoder.store.grad, m2.encoder.store.grad          # (wgrad split-K atomics: equal up to summation order)
+    assert (g1 - g2).abs().max().item() <= 1e-5 * g1.abs().max().item()
