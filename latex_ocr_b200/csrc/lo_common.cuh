@@ -184,6 +184,15 @@ int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, 
                int M, int N, int K, const float* bias, int accumulate, int relu, cudaStream_t st);
 int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
                   const float* bias, int accumulate, int relu, int splits, int atomic_acc, int small_n_tile, cudaStream_t st);
+struct TcLstmEpi {
+  const float* ptab; const int64_t* tok; int64_t tok_stride;
+  const float* hh; int64_t hh_stride;
+  const float* c_prev; float* gates; float* c_out; float* h_out; bf16* h_bf;
+  float* hd; int64_t hd_stride; const float* dmask;
+  int D, V;
+};
+int tc_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st);
+extern int g_opt_fuse_lstm;
 int tc_gemm_tn(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, cudaStream_t st);
 int tc_conv3x3_wgrad(const bf16* x, const bf16* dy, float* dw, int N, int H, int W, int Cin, int Cout, int pad, cudaStream_t st);
 int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask, bf16* y,

@@ -752,10 +752,10 @@ static inline Dims dims(const lo_decoder_args* a) {
 // bf16 staging used when impl == TC: mirrors written by the step kernels feed the tcgen05 GEMMs directly
 struct BfViews {
   bool on;
-  bf16 *dcat, *hall, *gctx, *wet, *onehot, *hd, *dlogits, *wfct;
+  bf16 *dcat, *hall, *gctx, *wet, *onehot, *hd, *dlogits, *wfct, *wil;
 };
 static BfViews bf_views(const lo_decoder_args* a, const Dims& d) {
-  BfViews v{false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  BfViews v{false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (a->impl == LO_IMPL_TC && a->dt == LO_BF16 && a->bfwork && tc_available()) {
     const int64_t TB = (int64_t)d.T * d.B;
     v.on = true;
@@ -767,6 +767,7 @@ static BfViews bf_views(const lo_decoder_args* a, const Dims& d) {
     v.hd = v.onehot + TB * ((d.V + 7) / 8 * 8);
     v.dlogits = v.hd + TB * d.D;
     v.wfct = v.dlogits + TB * d.Vl;
+    v.wil = v.wfct + (int64_t)d.D * d.Vl;
   }
   return v;
 }
@@ -837,13 +838,43 @@ static int upload_dlen(const lo_decoder_args* a, cudaStream_t st) {
   return LO_OK;
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): two bf16 GEMMs then reproduce an fp32-input GEMM to ~2^-17 relative
+__global__ void split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+int g_opt_fuse_lstm = 1;
+// wil[4*j + g][c] = w_ih[g*D + j][E + c]: gate-interleaved copy of the context half of weight_ih, so that one 32-column
+// accumulator chunk of the tcgen05 GEMM holds whole hidden units and the LSTM cell can run in its epilogue
+__global__ void interleave_wih_kernel(const bf16* __restrict__ w_ih, bf16* __restrict__ wil, int D, int E, int C) {
+  const int64_t total = (int64_t)4 * D * (C / 8);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % (C / 8));
+    const int n = (int)(i / (C / 8));        // interleaved row 4*j + g
+    const int j = n >> 2, g = n & 3;
+    *reinterpret_cast<uint4*>(wil + (int64_t)n * C + c8 * 8) =
+        *reinterpret_cast<const uint4*>(w_ih + ((int64_t)g * D + j) * (E + C) + E + c8 * 8);
+  }
+}
+
 static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_t st) {
   const int dt = a->dt;
   const int rpi = a->rows_per_img > 1 ? a->rows_per_img : 1;
   // att1 = enc @ W_e^T + b_e   (hoisted: the reference recomputes it every step, seq2seq_torch.py:186)
   LO_TRY(gemm_nt(a->enc, dt, d.C, a->w_enc_att, dt, d.C, a->att1, dt, d.A, (d.B / rpi) * d.R, d.A, d.C, a->b_enc_att, 0, 0, a->impl, st));
+  const BfViews bv0 = bf_views(a, d);
   // embedding -> gate projection table (replaces embedding lookup + x[:, :E] @ W_ih[:, :E]^T, seq2seq_torch.py:291,:313)
-  LO_TRY(gemm_nt(a->emb, dt, d.E, a->w_ih, dt, d.E + d.C, a->ptab, LO_F32, d.G, d.V, d.G, d.E, a->b_ih, 0, 0, LO_IMPL_SIMT, st));
+  if (bv0.on && d.E % 64 == 0) {
+    LO_TRY(tc_gemm_nt_ex((const bf16*)a->emb, d.E, (const bf16*)a->w_ih, d.E + d.C, a->ptab, LO_F32, d.G, d.V, d.G, d.E, a->b_ih, 0, 0, 1,
+                         0, 0, st));
+  } else {
+    LO_TRY(gemm_nt(a->emb, dt, d.E, a->w_ih, dt, d.E + d.C, a->ptab, LO_F32, d.G, d.V, d.G, d.E, a->b_ih, 0, 0, LO_IMPL_SIMT, st));
+  }
   // init_hidden_state (seq2seq_torch.py:255-265)
   {
     dim3 grid(cdiv(d.C, 256), d.B);
@@ -851,11 +882,31 @@ static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_
     LO_LAUNCH_OK();
   }
   const size_t es = dt == LO_F32 ? 4 : 2;
-  LO_TRY(gemm_nt(a->mean, LO_F32, d.C, a->w_init, dt, d.C, a->hall, LO_F32, d.D, d.B, d.D, d.C, a->b_init, 0, 0, LO_IMPL_SIMT, st));
-  LO_TRY(gemm_nt(a->mean, LO_F32, d.C, (const char*)a->w_init + (size_t)d.D * d.C * es, dt, d.C, a->call, LO_F32, d.D, d.B,
-                 d.D, d.C, a->b_init + d.D, 0, 0, LO_IMPL_SIMT, st));
+  if (bv0.on && d.C % 64 == 0 && d.T >= 2) {
+    // the row means stay fp32-accurate: hi/lo bf16 split (staged in the not-yet-used gctx mirrors of steps 0 and 1)
+    bf16* mean_hi = bv0.gctx;
+    bf16* mean_lo = bv0.gctx + (int64_t)d.B * d.C;
+    split_bf16_kernel<<<cdiv((long)d.B * d.C, 256), 256, 0, st>>>(a->mean, mean_hi, mean_lo, (int64_t)d.B * d.C);
+    LO_LAUNCH_OK();
+    const bf16* w_h = (const bf16*)a->w_init;
+    const bf16* w_c = w_h + (int64_t)d.D * d.C;
+    LO_TRY(tc_gemm_nt_ex(mean_hi, d.C, w_h, d.C, a->hall, LO_F32, d.D, d.B, d.D, d.C, a->b_init, 0, 0, 1, 0, 1, st));
+    LO_TRY(tc_gemm_nt_ex(mean_lo, d.C, w_h, d.C, a->hall, LO_F32, d.D, d.B, d.D, d.C, nullptr, 1, 0, 1, 0, 1, st));
+    LO_TRY(tc_gemm_nt_ex(mean_hi, d.C, w_c, d.C, a->call, LO_F32, d.D, d.B, d.D, d.C, a->b_init + d.D, 0, 0, 1, 0, 1, st));
+    LO_TRY(tc_gemm_nt_ex(mean_lo, d.C, w_c, d.C, a->call, LO_F32, d.D, d.B, d.D, d.C, nullptr, 1, 0, 1, 0, 1, st));
+  } else {
+    LO_TRY(gemm_nt(a->mean, LO_F32, d.C, a->w_init, dt, d.C, a->hall, LO_F32, d.D, d.B, d.D, d.C, a->b_init, 0, 0, LO_IMPL_SIMT, st));
+    LO_TRY(gemm_nt(a->mean, LO_F32, d.C, (const char*)a->w_init + (size_t)d.D * d.C * es, dt, d.C, a->call, LO_F32, d.D, d.B,
+                   d.D, d.C, a->b_init + d.D, 0, 0, LO_IMPL_SIMT, st));
+  }
   const BfViews bv = bf_views(a, d);
-  if (bv.on) LO_TRY(lo_cast(a->hall, LO_F32, bv.hall, LO_BF16, (int64_t)d.B * d.D, (void*)st));
+  if (bv.on) {
+    LO_TRY(lo_cast(a->hall, LO_F32, bv.hall, LO_BF16, (int64_t)d.B * d.D, (void*)st));
+    if (g_opt_fuse_lstm && d.E % 8 == 0 && d.C % 8 == 0) {
+      interleave_wih_kernel<<<148 * 2, 256, 0, st>>>((const bf16*)a->w_ih, bv.wil, d.D, d.E, d.C);
+      LO_LAUNCH_OK();
+    }
+  }
   return LO_OK;
 }
 
@@ -897,6 +948,14 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
                                   bv.on ? bv.gctx + ((int64_t)t * d.B + r0) * d.C : nullptr, nrows, d.R, d.C, rs.work, st,
                                   a->rows_per_img, rs.nsplit));
   // gates_x = (gate*ctx) @ W_ih[:, E:]^T
+  if (bv.on && g_opt_fuse_lstm) {
+    // ... with the LSTM cell fused into the GEMM epilogue (no gates_x round trip, one launch less per step)
+    TcLstmEpi e{a->ptab, tok + r0 * tok_stride, tok_stride, o1 + d.A + d.C, d.O1, c_prev, a->gates + ((int64_t)t * d.B + r0) * d.G,
+                a->call + ((int64_t)(t + 1) * d.B + r0) * d.D, a->hall + ((int64_t)(t + 1) * d.B + r0) * d.D,
+                bv.hall + ((int64_t)(t + 1) * d.B + r0) * d.D, hd_t ? hd_t + r0 * hd_stride : (float*)nullptr, hd_stride,
+                dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, d.D, d.V};
+    return tc_gemm_nt_lstm(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, bv.wil, d.C, nrows, d.D, d.C, e, st);
+  }
   if (bv.on) {
     LO_TRY(tc_gemm_nt_ex(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, (const bf16*)a->w_ih + d.E, d.E + d.C, gtmp, LO_F32, d.G, nrows,
                          d.G, d.C, nullptr, 0, 0, 1, 0, 1, st));
@@ -952,7 +1011,8 @@ int64_t lo_decoder_bfwork_bytes(const lo_decoder_args* a) {
   const int64_t TB = (int64_t)a->T * a->B, O1 = a->A + a->C + 4 * a->D;
   const int64_t Vp = (a->V + 7) / 8 * 8;
   const int64_t Vl = a->ldl > 0 ? a->ldl : a->V;
-  return (TB * (O1 + a->D + a->C + Vp + a->D + Vl) + (int64_t)a->B * a->D + (int64_t)a->A * a->C + (int64_t)a->D * Vl) * 2 + 1024;
+  return (TB * (O1 + a->D + a->C + Vp + a->D + Vl) + (int64_t)a->B * a->D + (int64_t)a->A * a->C + (int64_t)a->D * Vl +
+          (int64_t)4 * a->D * a->C) * 2 + 1024;
 }
 
 int64_t lo_sizeof_decoder_args(void) { return (int64_t)sizeof(lo_decoder_args); }

@@ -145,6 +145,14 @@ struct TcParams {
   int w_evict_last;           // keep the B (weight) tiles in L2: the per-step decoder GEMMs re-read them every step
   int half_w, half_h;         // MC=1 conv: box offset of the second half of the A tile (one of them is 0)
   long long* dbg;             // optional: clock64 stamps of CTA (0,0,0) at the pipeline milestones (lo_debug_buffer)
+  // fused LSTM-cell epilogue (decoder forward): the GEMM's N dimension is gate-interleaved (column 4*j + gate), the
+  // epilogue adds the embedding-table row and the recurrent projection, applies the cell and writes h, c, gates
+  int lstm;
+  const float* l_ptab; const int64_t* l_tok; int64_t l_tok_stride;
+  const float* l_hh; int64_t l_hh_stride;
+  const float* l_cprev; float* l_gates; float* l_c; float* l_h; bf16* l_hbf;
+  float* l_hd; int64_t l_hd_stride; const float* l_dmask;
+  int l_D, l_V;
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -313,6 +321,48 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
     mbar_wait(tmem_full_bar, 0);
     if (dbg && warp == 2 && lane == 0) p.dbg[6] = clock64();
     tc_fence_after();
+    if (p.lstm) {
+      // ---- fused LSTM cell (nn.LSTMCell, gate order i,f,g,o).  The 32x32 accumulator chunk is transposed through the idle
+      // pipeline ring so that a lane owns one hidden unit (4 interleaved gate columns) and consecutive lanes consecutive units
+      float* stg = reinterpret_cast<float*>(smem) + quad * (32 * 36);
+      const int D = p.l_D;
+#pragma unroll 1
+      for (int c = 0; c < NT; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+          *reinterpret_cast<uint4*>(&stg[lane * 36 + g * 4]) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        __syncwarp();
+        const int u = lane & 7;
+        const int j = (n0 + c) / 4 + u;
+#pragma unroll 2
+        for (int i = 0; i < 8; i++) {
+          const int rl = i * 4 + (lane >> 3);
+          const int b = m0 + quad * 32 + rl;
+          if (b >= p.M || j >= D) continue;
+          const float4 a = *reinterpret_cast<const float4*>(&stg[rl * 36 + 4 * u]);
+          int64_t tk = p.l_tok[(int64_t)b * p.l_tok_stride];
+          tk = tk < 0 ? 0 : (tk >= p.l_V ? p.l_V - 1 : tk);
+          const float* pt = p.l_ptab + tk * 4 * D;
+          const float* hh = p.l_hh + (int64_t)b * p.l_hh_stride;
+          const float pi = a.x + pt[j] + hh[j];
+          const float pf = a.y + pt[D + j] + hh[D + j];
+          const float pg = a.z + pt[2 * D + j] + hh[2 * D + j];
+          const float po = a.w + pt[3 * D + j] + hh[3 * D + j];
+          const float ig = sigmoidf_(pi), fg = sigmoidf_(pf), gg = tanhf(pg), og = sigmoidf_(po);
+          const float cn = fg * p.l_cprev[(int64_t)b * D + j] + ig * gg;
+          const float hn = og * tanhf(cn);
+          float* gt = p.l_gates + (int64_t)b * 4 * D;
+          gt[j] = ig; gt[D + j] = fg; gt[2 * D + j] = gg; gt[3 * D + j] = og;
+          p.l_c[(int64_t)b * D + j] = cn;
+          p.l_h[(int64_t)b * D + j] = hn;
+          if (p.l_hbf) p.l_hbf[(int64_t)b * D + j] = __float2bfloat16_rn(hn);
+          if (p.l_hd) p.l_hd[(int64_t)b * p.l_hd_stride + j] = p.l_dmask ? hn * p.l_dmask[(int64_t)b * p.l_hd_stride + j] : hn;
+        }
+        __syncwarp();
+      }
+    } else
 #pragma unroll 1
     for (int c = 0; c < NT; c += 32) {
       uint4 mk4[4];
@@ -649,6 +699,9 @@ static int launch_tc_any(const CUtensorMap& mA, const CUtensorMap& mB, TcParams&
   return launch_tc<128, 3, 0>(mA, mB, p, mtiles, splits, st);
 }
 
+static TcLstmEpi g_lstm_epi;
+static bool g_lstm_epi_on = false;
+
 // splits > 1 (or atomic_acc): fp32 C only, partial sums are ADDED onto C with atomics (C must hold the base values)
 int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
                   const float* bias, int accumulate, int relu, int splits, int atomic_acc, int small_n_tile, cudaStream_t st) {
@@ -677,7 +730,23 @@ int tc_gemm_nt_ex(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* 
   p.out_f32 = (dtC == LO_F32); p.accumulate = accumulate; p.relu = relu; p.atomic = atomic_acc;
   p.w_evict_last = (M <= 128) ? 1 : 0;
   p.dbg = g_tc_dbg;
+  if (g_lstm_epi_on) {
+    const TcLstmEpi& e = g_lstm_epi;
+    p.lstm = 1;
+    p.l_ptab = e.ptab; p.l_tok = e.tok; p.l_tok_stride = e.tok_stride; p.l_hh = e.hh; p.l_hh_stride = e.hh_stride;
+    p.l_cprev = e.c_prev; p.l_gates = e.gates; p.l_c = e.c_out; p.l_h = e.h_out; p.l_hbf = e.h_bf;
+    p.l_hd = e.hd; p.l_hd_stride = e.hd_stride; p.l_dmask = e.dmask; p.l_D = e.D; p.l_V = e.V;
+  }
   return launch_tc_any(mA, mB, p, cdiv(M, TC_BM), splits, NT, st, mc);
+}
+
+// gates = A @ Wil^T (Wil gate-interleaved [4D][K]) followed by the LSTM cell in the epilogue (see TcParams)
+int tc_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st) {
+  g_lstm_epi = e;
+  g_lstm_epi_on = true;
+  const int r = tc_gemm_nt_ex(A, lda, Wil, ldw, e.gates /*unused as C*/, LO_F32, 4 * D, M, 4 * D, K, nullptr, 0, 0, 1, 0, 1, st);
+  g_lstm_epi_on = false;
+  return r;
 }
 
 int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, int dtC, int64_t ldc, int M, int N, int K,
