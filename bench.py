@@ -163,7 +163,7 @@ def main():
         positional_embeddings = True
         lr_init = 1e-3
         lr_method = "adam"
-        cuda_graph = (not args.no_graph) and world == 1
+        cuda_graph = (not args.no_graph) and (world == 1 or os.environ.get("LO_DP_GRAPH", "0") == "1")
     kernels = args.kernels
     if kernels == "tc" and not bs.tc_ready():
         kernels = "simt"
@@ -235,7 +235,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "cfg2: batch %d/GPU, 1x128x512 images, 6-conv encoder + 512-d attention LSTM decoder, vocab 500, "
                                "T=150 teacher-forced steps (PADs trained on, as the reference)" % c["B"],
-                   "global_batch": total_imgs, "parallelism": "dp%d" % world, "kernels": kernels, "cuda_graph": (not args.no_graph) and world == 1,
+                   "global_batch": total_imgs, "parallelism": "dp%d" % world, "kernels": kernels, "cuda_graph": bool(Cfg.cuda_graph),
                    "l2": "per-step working set (>1 GB of feature maps + 114 MB attention stream) exceeds the 126 MB L2; no explicit flush",
                    "loss_after": final_loss},
         "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e,

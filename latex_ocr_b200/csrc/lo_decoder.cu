@@ -848,7 +848,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, bf16* __restrict_
   }
 }
 
-int g_opt_fuse_lstm = 1;
+int g_opt_fuse_lstm = 0;   // measured slower (23.0 vs 20.1 ms/step): 128 epilogue threads cannot hide the dependent global loads
+                           // (tok -> table row, recurrent projection, c) that 32 K threads of lstm_pw_fwd_kernel hide
 // wil[4*j + g][c] = w_ih[g*D + j][E + c]: gate-interleaved copy of the context half of weight_ih, so that one 32-column
 // accumulator chunk of the tcgen05 GEMM holds whole hidden units and the LSTM cell can run in its epilogue
 __global__ void interleave_wih_kernel(const bf16* __restrict__ w_ih, bf16* __restrict__ wil, int D, int E, int C) {

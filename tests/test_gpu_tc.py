@@ -105,3 +105,31 @@ def test_tc_conv3x3_wgrad(N, H, W, Cin, Cout, pad):
     torch.cuda.synchronize()
     assert relerr(dw.permute(0, 3, 1, 2), w.grad.float()) < 2e-5        # bf16 inputs are exact in fp64; fp32 accumulate
     assert relerr(db, dy.double().sum(dim=(0, 2, 3)).float()) < 1e-5
+
+
+@pytest.mark.parametrize("opt", ["fuse_lstm", "dec_streams"])
+def test_optional_decoder_schedules_match_default(opt):
+    """The LSTM-cell-in-GEMM-epilogue variant and the two-chain (two stream) time loop are kept as run-time options
+    (both measured no faster); they must give the default schedule's numbers."""
+    from util import build_model, load_golden
+    from latex_ocr_b200 import _lib
+    from oracle import ref_model as rm
+    _L()
+    V = 60
+    pe, pd = rm.init_params(V, seed=41)
+    img, formula = rm.synthetic_batch(40, 32, 64, V, 4, 6, seed=42)     # B >= 32 so that the two-chain loop engages
+    B, T = formula.shape[0], formula.shape[1] - 1
+    res = {}
+    try:
+        for val in (0 if opt == "fuse_lstm" else 1, 1 if opt == "fuse_lstm" else 2):
+            _lib.set_option(opt, val)
+            m = build_model(V, pe, pd, "bf16", impl="tc")
+            loss = m._step_body(img.cuda(), formula.cuda(), [T] * B, None)
+            torch.cuda.synchronize()
+            res[val] = (loss[0].item(), m.decoder.store.grad.clone())
+    finally:
+        _lib.set_option("fuse_lstm", 0)
+        _lib.set_option("dec_streams", 1)
+    (l0, g0), (l1, g1) = res.values()
+    assert abs(l0 - l1) / abs(l0) < 1e-4
+    assert (g0 - g1).norm().item() / g0.norm().item() < 2e-2
