@@ -78,8 +78,14 @@ class Img2SeqModel:
         self.decoder.train(flag)
 
     # --- the fused train step --------------------------------------------------------------------
-    def _adam(self, store, grad_scale=1.0):
+    def _adam(self, store, grad_scale=1.0, module=None):
         L = _lib.lib()
+        if module is not None:
+            # fine_tune()/fine_tune_embeddings() (seq2seq_torch.py:102-113, :246-253): frozen parameters get no update —
+            # their gradient slices are cleared before the fused Adam (moments stay 0, so the update is exactly 0)
+            for p_ in module.parameters():
+                if not p_.requires_grad and p_.grad is not None:
+                    p_.grad.zero_()
         check(L.lo_adam_step(ptr(store.master), ptr(store.grad), ptr(store.m), ptr(store.v), ptr(store.shadow), store.numel,
                              ptr(store.adam_state), 0.9, 0.999, 1e-8, float(grad_scale), stream_ptr()))
 
@@ -100,8 +106,8 @@ class Img2SeqModel:
         if self.dist is not None:
             self.dist.reduce_async(self.encoder.store.grad)
             self.dist.wait()
-        self._adam(self.decoder.store, scale)
-        self._adam(self.encoder.store, scale)
+        self._adam(self.decoder.store, scale, self.decoder)
+        self._adam(self.encoder.store, scale, self.encoder)
         return ws["t"]["loss"]
 
     def train_step(self, img, formula, sync=False):
@@ -189,8 +195,12 @@ class Img2SeqModel:
                 lr_schedule.update(batch_no=epoch * ((len(train_set) + batch_size - 1) // batch_size) + i)
         self.last_epoch_stats = {"images_per_s": nimg / max(time.time() - t0, 1e-9), "mean_neg_loss": float(np.mean(losses)) if losses else 0.0}
         score = self.last_epoch_stats["mean_neg_loss"]
-        if val_set is not None and hasattr(self, "evaluate"):
-            pass
+        if val_set is not None and self._vocab is not None:
+            scores = self.evaluate(config, val_set)                                  # img2seq_torch.py:128-132
+            score = scores["perplexity"]
+            self.last_epoch_stats.update(scores)
+            if lr_schedule is not None:
+                lr_schedule.update(score=score)
         return score
 
     def train(self, config, train_set, val_set, lr_schedule):
@@ -220,6 +230,46 @@ class Img2SeqModel:
         beam = int(beam_size or getattr(self._config, "beam_size", 5))
         ids, _ = decode.beam_decode(self, images, start_id, end_id, beam, L)
         return [decode.truncate_end(ids[:, k].tolist(), end_id) for k in range(beam)]
+
+    def evaluate(self, config, test_set, start_id=None):
+        """Evaluation with the TF path's semantics (img2seq.py:198-254; the torch path's own evaluate is broken, SURVEY
+        quirk Q6): teacher-forced perplexity exp(sum CE / n_tokens) over the real tokens (+END), and BLEU-4 / edit distance /
+        exact match of the decoded formulas.  Returns the score dict with ``perplexity`` negated like img2seq.py:252 so that
+        'higher is better' model selection works."""
+        from . import decode, metrics
+        from .data import minibatches, pad_batch_formulas, pad_batch_images
+        self.train_mode(False)
+        end_id, pad_id = self._vocab.id_end, self._vocab.id_pad
+        start_id = pad_id if start_id is None else start_id
+        refs, hyps = [], []
+        ce_sum, n_tok = 0.0, 0
+        decoding = getattr(self._config, "decoding", "greedy")
+        L = int(getattr(self._config, "max_length_formula", 150))
+        for imgs, formulas in minibatches(test_set, config.batch_size):
+            img = torch.from_numpy(pad_batch_images(imgs)).permute(0, 3, 1, 2).contiguous()
+            formula, length = pad_batch_formulas(formulas, pad_id, end_id)
+            formula_t = torch.from_numpy(formula.astype(np.int64))
+            lens = torch.from_numpy(length.astype(np.int64)).unsqueeze(1)
+            # teacher-forced scores over the true lengths (START-prefixed inputs, targets = tokens then END)
+            inp = torch.cat([torch.full((formula_t.shape[0], 1), start_id, dtype=torch.int64), formula_t], dim=1)
+            enc = self.encoder(img.to(self.device))
+            preds, caps, dl, _, _ = self.decoder(enc, inp.to(self.device), lens + 1)
+            tgt = caps[:, 1:]
+            for b, n in enumerate(dl):
+                lp = torch.log_softmax(preds[b, :n].float(), dim=-1)                 # host-side metric arithmetic (plumbing)
+                ce_sum += float(-lp.gather(1, tgt[b, :n].unsqueeze(1)).sum().item())
+                n_tok += int(n)
+            if decoding == "greedy":
+                ids = decode.greedy_decode(self, img, start_id, end_id, L)
+                hyp = decode.truncate_end(ids.tolist(), end_id)
+            else:
+                ids, _ = decode.beam_decode(self, img, start_id, end_id, int(getattr(self._config, "beam_size", 5)), L)
+                hyp = decode.truncate_end(ids[:, 0].tolist(), end_id)
+            refs += [list(map(int, f)) for f in formulas]
+            hyps += hyp
+        scores = metrics.score(refs, hyps)
+        scores["perplexity"] = -float(np.exp(ce_sum / max(n_tok, 1)))
+        return scores
 
     # --- checkpoints: state_dict round-trips with the reference modules ----------------------------
     def state_dict(self):

@@ -54,3 +54,30 @@ def test_predict_batch_surface():
     out = m.predict_batch(img, decoding="beam_search", beam_size=2)
     assert len(out) == 2 and all(len(h) == img.shape[0] for h in out)
     assert all(29 not in seq for seq in out[0])        # truncated at END
+
+
+def test_train_epoch_and_evaluate_surface():
+    """_run_train_epoch / evaluate with the reference's data conventions (lists of HWC uint8 arrays + token-id lists)."""
+    import numpy as np
+    from latex_ocr_b200.data import SimpleVocab
+    from latex_ocr_b200.img2seq import Img2SeqModel
+    from latex_ocr_b200.lr_schedule import LRSchedule
+    from util import Cfg
+    rng = np.random.RandomState(0)
+    V = 30
+    vocab = SimpleVocab(V)
+    data = [(rng.randint(0, 256, (32, 64 + 16 * (i % 2), 1)).astype(np.uint8), list(rng.randint(0, V - 3, 3 + i % 3))) for i in range(6)]
+    # same-shape batches like the reference's bucketing (data_generator.py:84-122)
+    data.sort(key=lambda d: d[0].shape)
+    cfg = Cfg(batch_size=3, n_epochs=1, max_length_formula=6, decoding="greedy")
+    m = Img2SeqModel(cfg, vocab=vocab, device="cuda", precision="fp32").build_train()
+    sched = LRSchedule(lr_init=1e-3, apply_to=m)
+    score = m.train(cfg, data, data, sched)
+    assert score < 0 and np.isfinite(score)                      # negated perplexity
+    s = m.last_epoch_stats
+    assert {"BLEU-4", "ExactMatchScore", "EditDistance", "perplexity", "images_per_s"} <= set(s)
+    # frozen encoder: fine_tune(False) leaves every conv weight untouched by the fused Adam
+    before = m.encoder.store.master.clone()
+    m.encoder.fine_tune(False)
+    m._run_train_epoch(cfg, data, None, 0, None)
+    assert torch.equal(before, m.encoder.store.master)
