@@ -225,6 +225,12 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
  */
 int lo_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n,
                  float* state_dev, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* Same update restricted to n_ranges element ranges {offset, count} (host array of 2*n_ranges int64) of the flat buffers:
+ * parameters outside the ranges are frozen (requires_grad=False after fine_tune(), seq2seq_torch.py:102-113, :246-253 —
+ * torch.optim.Adam skips them: no moment decay, no update).  One step-counter increment for the whole call. */
+int lo_adam_step_ranges(float* p, const float* g, float* m, float* v, void* shadow_bf16, const int64_t* ranges,
+                        int n_ranges, float* state_dev, float beta1, float beta2, float eps, float grad_scale,
+                        void* stream);
 int lo_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, void* stream);
 
 #ifdef __cplusplus

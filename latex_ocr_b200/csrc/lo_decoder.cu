@@ -938,7 +938,10 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
   const char* enc = (const char*)a->enc + (size_t)(r0 / rpi) * d.R * d.C * es;
   // [att2 | gate_pre | hh_pre] = h_prev @ [W_d; W_beta; W_hh]^T + b   (seq2seq_torch.py:187, :311, LSTMCell hh part)
   const BfViews bv = bf_views(a, d);
-  if (bv.on) {
+  if (bv.on && g_opt_skinny_mma && nrows <= 64) {
+    LO_TRY(skinny_gemm_nt(bv.hall + ((int64_t)t * d.B + r0) * d.D, d.D, (const bf16*)a->wcat1, d.D, o1, d.O1, nrows, d.O1, d.D, a->bcat1, 1,
+                          0, st));
+  } else if (bv.on) {
     LO_TRY(tc_gemm_nt_ex(bv.hall + ((int64_t)t * d.B + r0) * d.D, d.D, (const bf16*)a->wcat1, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D,
                          a->bcat1, 0, 0, 1, 0, 1, st));
   } else {
@@ -957,7 +960,10 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
                 dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, d.D, d.V};
     return tc_gemm_nt_lstm(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, bv.wil, d.C, nrows, d.D, d.C, e, st);
   }
-  if (bv.on) {
+  if (bv.on && g_opt_skinny_mma && nrows <= 64) {
+    LO_TRY(skinny_gemm_nt(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, (const bf16*)a->w_ih + d.E, d.E + d.C, gtmp, d.G, nrows, d.G, d.C,
+                          nullptr, 1, 0, st));
+  } else if (bv.on) {
     LO_TRY(tc_gemm_nt_ex(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, (const bf16*)a->w_ih + d.E, d.E + d.C, gtmp, LO_F32, d.G, nrows,
                          d.G, d.C, nullptr, 0, 0, 1, 0, 1, st));
   } else {
@@ -1183,7 +1189,10 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
                        bv.on ? dcat_bf_t + d.A + d.C : (bf16*)nullptr, bv.on ? dxh : (float*)nullptr, d.C, nrows, d.D));
     LO_LAUNCH_OK();
     // [dgctx | dh_prev] = dG @ [W_ih[:, E:] | W_hh]
-    if (bv.on) {
+    if (bv.on && g_opt_skinny_mma && nrows <= 64) {
+      LO_TRY(skinny_gemm_nt(dcat_bf_t + d.A + d.C, d.O1, (const bf16*)a->wbwd1, d.G, dxh, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 4, 1,
+                            st));
+    } else if (bv.on) {
       LO_TRY(tc_gemm_nt_ex(dcat_bf_t + d.A + d.C, d.O1, (const bf16*)a->wbwd1, d.G, dxh, LO_F32, d.C + d.D, nrows, d.C + d.D, d.G,
                            nullptr, 0, 0, 4, 1, 1, st));
     } else {
@@ -1221,7 +1230,10 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     LO_LAUNCH_OK();
     }
     // dh_prev += [datt2 | dgate_pre] @ [W_d ; W_beta]
-    if (bv.on) {
+    if (bv.on && g_opt_skinny_mma && nrows <= 64) {
+      LO_TRY(skinny_gemm_nt(dcat_bf_t, d.O1, (const bf16*)a->wbwd2, d.A + d.C, dxh + d.C, d.C + d.D, nrows, d.D, d.A + d.C, nullptr, 4, 1,
+                            st));
+    } else if (bv.on) {
       LO_TRY(tc_gemm_nt_ex(dcat_bf_t, d.O1, (const bf16*)a->wbwd2, d.A + d.C, dxh + d.C, LO_F32, d.C + d.D, nrows, d.D, d.A + d.C,
                            nullptr, 0, 0, 4, 1, 1, st));
     } else {

@@ -51,6 +51,24 @@ int lo_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16
   return LO_OK;
 }
 
+int lo_adam_step_ranges(float* p, const float* g, float* m, float* v, void* shadow_bf16, const int64_t* ranges, int n_ranges,
+                        float* state_dev, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  LO_CHECK_ARG(p && g && m && v && state_dev && ranges && n_ranges >= 0, "null pointer / n_ranges");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int r = 0; r < n_ranges; r++) {
+    const int64_t off = ranges[2 * r], n = ranges[2 * r + 1];
+    LO_CHECK_ARG(off >= 0 && n > 0, "range");
+    int grid = (int)((n + 1023) / 1024);
+    if (grid > 148 * 8) grid = 148 * 8;
+    adam_kernel<<<grid, 256, 0, st>>>(p + off, g + off, m + off, v + off, shadow_bf16 ? (bf16*)shadow_bf16 + off : nullptr, n, state_dev, beta1,
+                                      beta2, eps, grad_scale);
+    LO_LAUNCH_OK();
+  }
+  adam_bump_kernel<<<1, 1, 0, st>>>(state_dev);
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
 int lo_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, void* stream) {
   LO_CHECK_ARG(src && dst && n > 0, "null pointer / n");
   cudaStream_t st = (cudaStream_t)stream;

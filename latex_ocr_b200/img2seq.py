@@ -78,16 +78,37 @@ class Img2SeqModel:
         self.decoder.train(flag)
 
     # --- the fused train step --------------------------------------------------------------------
+    @staticmethod
+    def _trainable_ranges(store, module):
+        """Contiguous {offset, count} ranges of the flat store owned by parameters with requires_grad=True, or None when
+        nothing is frozen."""
+        frozen = {p_._lo_store_name for p_ in module.parameters() if not p_.requires_grad}
+        if not frozen:
+            return None
+        ranges = []
+        for name, (off, n, _) in sorted(store.offsets.items(), key=lambda kv: kv[1][0]):
+            if name in frozen:
+                continue
+            if ranges and ranges[-1][0] + ranges[-1][1] == off:
+                ranges[-1][1] += n
+            else:
+                ranges.append([off, n])
+        return ranges
+
     def _adam(self, store, grad_scale=1.0, module=None):
         L = _lib.lib()
-        if module is not None:
-            # fine_tune()/fine_tune_embeddings() (seq2seq_torch.py:102-113, :246-253): frozen parameters get no update —
-            # their gradient slices are cleared before the fused Adam (moments stay 0, so the update is exactly 0)
-            for p_ in module.parameters():
-                if not p_.requires_grad and p_.grad is not None:
-                    p_.grad.zero_()
-        check(L.lo_adam_step(ptr(store.master), ptr(store.grad), ptr(store.m), ptr(store.v), ptr(store.shadow), store.numel,
-                             ptr(store.adam_state), 0.9, 0.999, 1e-8, float(grad_scale), stream_ptr()))
+        ranges = self._trainable_ranges(store, module) if module is not None else None
+        if ranges is None:
+            check(L.lo_adam_step(ptr(store.master), ptr(store.grad), ptr(store.m), ptr(store.v), ptr(store.shadow), store.numel,
+                                 ptr(store.adam_state), 0.9, 0.999, 1e-8, float(grad_scale), stream_ptr()))
+            return
+        # fine_tune()/fine_tune_embeddings() (seq2seq_torch.py:102-113, :246-253): torch.optim.Adam skips parameters without a
+        # gradient, so frozen slices see neither moment decay nor an update
+        import ctypes
+        flat = [x for r in ranges for x in r]
+        arr = (ctypes.c_int64 * max(len(flat), 1))(*flat)
+        check(L.lo_adam_step_ranges(ptr(store.master), ptr(store.grad), ptr(store.m), ptr(store.v), ptr(store.shadow), arr, len(ranges),
+                                    ptr(store.adam_state), 0.9, 0.999, 1e-8, float(grad_scale), stream_ptr()))
 
     def _step_body(self, img, caps, decode_lengths, dropout_mask):
         """encoder fwd -> decoder fwd + loss -> decoder bwd -> encoder bwd -> (grad all-reduce) -> Adam x2.
@@ -133,7 +154,8 @@ class Img2SeqModel:
         return loss
 
     def _graph_step(self, img_d, caps_d, decode_lengths):
-        key = (tuple(img_d.shape), img_d.dtype, tuple(caps_d.shape), self.decoder.training)
+        frozen = tuple(p_._lo_store_name for m_ in (self.encoder, self.decoder) for p_ in m_.parameters() if not p_.requires_grad)
+        key = (tuple(img_d.shape), img_d.dtype, tuple(caps_d.shape), self.decoder.training, frozen)
         g = self._graphs.get(key)
         if g is None:
             N, T = caps_d.shape[0], caps_d.shape[1] - 1

@@ -80,4 +80,5 @@ class ParamHolder(nn.Module):
             gv = gv.permute(*permute)
         p = nn.Parameter(v, requires_grad=True)
         p.grad = gv
+        p._lo_store_name = sname
         self.register_parameter(pname, p)

@@ -231,3 +231,42 @@ def test_adam_matches_torch():
     assert (p - ref.detach()).abs().max().item() < 2e-6
     assert state[0].item() == 3.0
     assert relerr(shadow.float(), p) < 1e-2
+
+
+def test_adam_ranges_skip_frozen_slices():
+    """lo_adam_step_ranges == torch.optim.Adam over the un-frozen parameters only (frozen: no update, no moment decay)."""
+    import ctypes
+    _lib, L = _L()
+    torch.manual_seed(8)
+    sizes = (300, 1000, 77, 2048)
+    frozen = (True, False, False, True)
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    n = offs[-1]
+    p = torch.randn(n, device="cuda")
+    p0 = p.clone()
+    refs = [p[offs[i]:offs[i + 1]].clone().requires_grad_(True) for i in range(4)]
+    opt = torch.optim.Adam([r for r, f in zip(refs, frozen) if not f], lr=2e-3)
+    m = torch.randn(n, device="cuda").abs() * 1e-3          # stale moments on frozen slices must survive untouched
+    v = torch.randn(n, device="cuda").abs() * 1e-3
+    m[offs[1]:offs[3]] = 0
+    v[offs[1]:offs[3]] = 0
+    m0, v0 = m.clone(), v.clone()
+    state = torch.tensor([0.0, 2e-3], device="cuda")
+    ranges = (ctypes.c_int64 * 2)(offs[1], sizes[1] + sizes[2])
+    for _ in range(3):
+        g = torch.randn(n, device="cuda")
+        for i in (1, 2):
+            refs[i].grad = g[offs[i]:offs[i + 1]].clone()
+        opt.step()
+        _lib.check(L.lo_adam_step_ranges(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), None, ranges, 1, _lib.ptr(state),
+                                         0.9, 0.999, 1e-8, 1.0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for i in range(4):
+        sl = slice(offs[i], offs[i + 1])
+        if frozen[i]:
+            assert torch.equal(p[sl], p0[sl]) and torch.equal(m[sl], m0[sl]) and torch.equal(v[sl], v0[sl])
+        else:
+            assert (p[sl] - refs[i].detach()).abs().max().item() < 2e-6
+    assert state[0].item() == 3.0

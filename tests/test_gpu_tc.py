@@ -33,6 +33,32 @@ def test_tc_gemm_nt(M, N, K, out_dtype):
     assert relerr(C.float(), ref.float()) < tol
 
 
+@pytest.mark.parametrize("M,N,K,acc", [(64, 3072, 512, 0), (64, 2048, 512, 0), (64, 1024, 2048, 1), (64, 512, 1024, 1), (40, 1024, 576, 0),
+                                         (1, 200, 64, 1), (17, 30, 2112, 0)])
+def test_skinny_mma_gemm(M, N, K, acc):
+    """The decoder's per-step GEMM shapes (M = batch <= 64 rows, fp32 out) through the mma.sync kernel (lo_skinny.cu) and
+    through the tcgen05 kernel (option skinny_mma=0): both against float64."""
+    _lib, L = _L()
+    torch.manual_seed(1)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    b = torch.randn(N, device="cuda")
+    base = torch.randn(M, N, device="cuda")
+    ref = (A.double() @ W.double().t() + b.double() + (base.double() if acc else 0)).float()
+    try:
+        for opt in (1, 0):
+            if opt == 0 and (K % 64 or N % 8):
+                continue                                   # tcgen05 path constraints
+            _lib.set_option("skinny_mma", opt)
+            C = base.clone()
+            _lib.check(L.lo_gemm(_lib.ptr(A), 1, _lib.ptr(W), 1, _lib.ptr(C), _lib.dt_of(C), M, N, K, K, 1, 1, K, N, 1, 0, 0, 0, _lib.ptr(b), acc, 0,
+                                 1, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            assert relerr(C, ref) < 1e-5, opt
+    finally:
+        _lib.set_option("skinny_mma", 1)
+
+
 @pytest.mark.parametrize("N,H,W,Cin,Cout,pad", [(2, 8, 128, 64, 128, 1), (2, 16, 64, 128, 256, 1), (3, 16, 64, 512, 512, 0),
                                                  (2, 14, 62, 512, 512, 2), (1, 6, 30, 256, 64, 1), (2, 9, 13, 64, 72, 1)])
 def test_tc_conv3x3(N, H, W, Cin, Cout, pad):
@@ -107,7 +133,7 @@ def test_tc_conv3x3_wgrad(N, H, W, Cin, Cout, pad):
     assert relerr(db, dy.double().sum(dim=(0, 2, 3)).float()) < 1e-5
 
 
-@pytest.mark.parametrize("opt", ["fuse_lstm", "dec_streams"])
+@pytest.mark.parametrize("opt", ["fuse_lstm", "dec_streams", "skinny_mma"])
 def test_optional_decoder_schedules_match_default(opt):
     """The LSTM-cell-in-GEMM-epilogue variant and the two-chain (two stream) time loop are kept as run-time options
     (both measured no faster); they must give the default schedule's numbers."""
@@ -121,7 +147,7 @@ def test_optional_decoder_schedules_match_default(opt):
     B, T = formula.shape[0], formula.shape[1] - 1
     res = {}
     try:
-        for val in (0 if opt == "fuse_lstm" else 1, 1 if opt == "fuse_lstm" else 2):
+        for val in {"fuse_lstm": (0, 1), "dec_streams": (1, 2), "skinny_mma": (1, 0)}[opt]:
             _lib.set_option(opt, val)
             m = build_model(V, pe, pd, "bf16", impl="tc")
             loss = m._step_body(img.cuda(), formula.cuda(), [T] * B, None)
@@ -130,6 +156,7 @@ def test_optional_decoder_schedules_match_default(opt):
     finally:
         _lib.set_option("fuse_lstm", 0)
         _lib.set_option("dec_streams", 1)
+        _lib.set_option("skinny_mma", 1)
     (l0, g0), (l1, g1) = res.values()
     assert abs(l0 - l1) / abs(l0) < 1e-4
     assert (g0 - g1).norm().item() / g0.norm().item() < 2e-2
