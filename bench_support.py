@@ -109,6 +109,36 @@ def kernel_probes(model, c, pk):
             "ms": ms_conv, "algorithmic_flops": flops, "peak_source": pk["src"] + " (sustained cuBLAS bf16)"}
     conv["frac"] = conv["achieved"] / conv["peak"]
 
+    # the tcgen05 kernels alone (layers 2-6: forward, data gradient, weight gradient + bias-gradient column sums) — what SURVEY §8-d
+    # calls the tensor-pipe figure (conv1 / pools / masks are memory-bound CUDA-core kernels and are excluded here)
+    from latex_ocr_b200.encoder import _LAYERS
+    Aa, Gg, S = enc_ws["acts"], enc_ws["grads"], enc.store
+    impl = enc._impl()
+    cfgl = {l[0]: l for l in _LAYERS}
+    plan = (("14", "P11"), ("11", "P8"), ("8", "Y6"), ("6", "P3"), ("3", "P0"))
+    fwd_in = {"3": "P0", "6": "P3", "8": "Y6", "11": "P8", "14": "P11"}
+
+    def conv_tc():
+        for idx, cin, cout, pad, pool in _LAYERS[1:]:
+            x = Aa[fwd_in[idx]]
+            _lib.check(L.lo_conv3x3(_lib.ptr(x), _lib.ptr(S.w("cnn.%s.weight" % idx)), _lib.ptr(S.f32("cnn.%s.bias" % idx)), None,
+                                    _lib.ptr(Aa["Y" + idx]), dt, B, x.shape[1], x.shape[2], cin, cout, pad, 1, impl, st))
+        for idx, xin in plan:
+            _, cin, cout, pad, pool = cfgl[idx]
+            x, dy = Aa[xin], Gg["Y" + idx]
+            _lib.check(L.lo_conv3x3_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(S.g("cnn.%s.weight" % idx)), _lib.ptr(S.g("cnn.%s.bias" % idx)),
+                                          dt, B, x.shape[1], x.shape[2], cin, cout, pad, impl, st))
+            mask = Aa[xin] if xin.startswith("Y") else None
+            _lib.check(L.lo_conv3x3(_lib.ptr(dy), _lib.ptr(enc_ws["wflip"][idx]), None, _lib.ptr(mask), _lib.ptr(Gg[xin]), dt, B, dy.shape[1],
+                                    dy.shape[2], cout, cin, 2 - pad, 0, impl, st))
+
+    ms_tc = _time_ms(conv_tc, 3)
+    flops_tc = B * 3 * 2 * 9.296e9     # layers 2-6: 9.296 GMAC/image, x3 passes (fwd, dgrad, wgrad)
+    conv_tc_r = {"kernel": "tcgen05 conv kernels only: tc_gemm_conv_kernel (fwd + dgrad) and tc_wgrad_kernel, layers 2-6", "bound": "tensor",
+                 "achieved": flops_tc / (ms_tc * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "traffic": None, "ms": ms_tc,
+                 "algorithmic_flops": flops_tc, "peak_source": pk["src"] + " (sustained cuBLAS bf16)"}
+    conv_tc_r["frac"] = conv_tc_r["achieved"] / conv_tc_r["peak"]
+
     def dec_all():
         _lib.check(L.lo_decoder_forward(ctypes.byref(a), 1, st))
         _lib.check(L.lo_decoder_backward(ctypes.byref(a), st))
@@ -116,7 +146,7 @@ def kernel_probes(model, c, pk):
     ms_dec = _time_ms(dec_all, 2)
     extra = {"decoder_fwd_bwd_ms": ms_dec, "encoder_fwd_bwd_ms": ms_conv, "attention_fwd_us_per_step": ms_att * 1e3}
     dominant = conv if ms_conv >= T * ms_att * 2 else att
-    return {"dominant": dominant, "all": {"attention": att, "conv": conv, "phases": extra}}
+    return {"dominant": dominant, "all": {"attention": att, "conv": conv, "conv_tensor_kernels": conv_tc_r, "phases": extra}}
 
 
 def cpu_threads():

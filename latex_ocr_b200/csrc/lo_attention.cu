@@ -75,9 +75,13 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     }
     fence_barrier_init();
   }
-  pdl_wait();
-  pdl_trigger();
   __syncthreads();
+  // PDL: the producer's bulk copies read only loop-invariant tensors (att1, enc: written long before the preceding kernel), so they
+  // are issued BEFORE griddepcontrol.wait and overlap the tail of the preceding launch; consumers wait before touching its results.
+  if (wid != AP_CWARPS) {
+    pdl_wait();
+    pdl_trigger();
+  }
 
   float m = -INFINITY, l = 0.f;
   float acc[NV * 8];
@@ -101,6 +105,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
         bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
       }
     }
+    __syncwarp();
+    pdl_wait();          // the producer warp joins the combine below, which reads the preceding kernel's results
   } else {
     // ===== consumer warps =====
     float a2[NV * 8], wv[NV * 8];
@@ -316,9 +322,13 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     }
     fence_barrier_init();
   }
-  pdl_wait();
-  pdl_trigger();
   __syncthreads();
+  // PDL: the producer's bulk copies read only loop-invariant tensors (att1, enc: written long before the preceding kernel), so they
+  // are issued BEFORE griddepcontrol.wait and overlap the tail of the preceding launch; consumers wait before touching its results.
+  if (wid != AP_CWARPS) {
+    pdl_wait();
+    pdl_trigger();
+  }
   float macc[NV * 8], wacc[NV * 8];     // wacc: d w_full partial = sum_r de_r * relu(att1_r + att2)   (full_att.weight gradient)
 #pragma unroll
   for (int i = 0; i < NV * 8; i++) { macc[i] = 0.f; wacc[i] = 0.f; }
@@ -339,6 +349,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
         bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
       }
     }
+    __syncwarp();
+    pdl_wait();          // the producer warp joins the combine below, which reads the preceding kernel's results
   } else {
     float a2[NV * 8], dc[NV * 8];
     float sdot = 0.f;

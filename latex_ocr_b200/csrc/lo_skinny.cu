@@ -44,16 +44,17 @@ __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict_
   const int k0 = blockIdx.y * kc;
   const int kn = min(kc, K - k0);                            // multiple of 16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_wait();
-  pdl_trigger();
   const int cpr = kn / 8;                                    // 16-byte chunks per row
-  for (int i = tid; i < 64 * cpr; i += 128) {
-    const int r = i / cpr, c = i % cpr;
-    cp_async16(sA + r * SK_PITCH + c * 8, A + (int64_t)r * lda + k0 + c * 8, r < M);
-  }
+  // PDL: the weight slice never depends on the preceding launch -> fetch it before griddepcontrol.wait
   for (int i = tid; i < SK_NT * cpr; i += 128) {
     const int r = i / cpr, c = i % cpr;
-    cp_async16(sW + r * SK_PITCH + c * 8, W + (int64_t)(n0 + r) * ldw + k0 + c * 8, n0 + r < N);
+    cp_async16(sW + r * SK_PITCH + c * 8, W + (int64_t)min(n0 + r, N - 1) * ldw + k0 + c * 8, n0 + r < N);
+  }
+  pdl_wait();
+  pdl_trigger();
+  for (int i = tid; i < 64 * cpr; i += 128) {
+    const int r = i / cpr, c = i % cpr;
+    cp_async16(sA + r * SK_PITCH + c * 8, A + (int64_t)min(r, M - 1) * lda + k0 + c * 8, r < M);
   }
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
