@@ -219,6 +219,68 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
                     int64_t* parents, int32_t* fin_hist, float* logp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * TensorFlow-flavour decoder: the Genthial attention cell of
+ * model/components/attention_cell.py:58-89 + attention_mechanism.py:43-94,145-153, driven like
+ * model/decoder.py:24-72 (teacher forcing = tf.nn.dynamic_rnn over [start_token ; E[formula[:, :-1]]]),
+ * masked cross-entropy of model/img2seq.py:68-71, hand-derived backward, greedy / beam decode.
+ *   per step:  [i j f o] = [emb_{t-1}; o_{t-1}; h_{t-1}] K + b        (TF LSTMCell, forget_bias 1)
+ *              e_r = beta . tanh(att_img_r + h_t W_h) ; alpha = softmax ; ctx = sum alpha_r img_r
+ *              o_t = tanh(h_t o_W_h + ctx o_W_c) ; logits_t = o_t y_W_o
+ * Parameter storage is [out][in] (K-major for the forward GEMMs; the Python side exposes TF-shaped
+ * [in][out] views of the same memory).  Shapes: B rows, T steps (buffer capacity), R regions, C channels,
+ * A=dim_e (A <= C; att_img is stored zero-padded to C columns so that the attention kernels of the torch
+ * flavour serve both), D=num_units, O=dim_o, E=dim_embeddings, V=vocab.
+ */
+typedef struct lo_tfdec_args {
+  int32_t B, T, R, C, A, D, O, E, V;
+  int32_t dt;              /* storage of enc / att_img / weight shadows */
+  int32_t impl;            /* LO_IMPL_SIMT | LO_IMPL_TC */
+  int32_t ldl;             /* row stride of logits / dlogits (>= V, multiple of 8) */
+  int32_t rows_per_img;    /* decode only: beam size (consecutive rows share one image); 0/1 otherwise */
+  float inv_n_words;       /* 1 / sum(lengths): the loss is the mean over valid tokens */
+  const void* enc;         /* big [B/rows_per_img][R][C] */
+  const int64_t* formula;  /* [B][formula_stride] target ids; step t consumes formula[:, t-1], predicts formula[:, t] */
+  int64_t formula_stride;
+  const int32_t* lengths;  /* device [B]: valid tokens per row incl. END (sequence_mask, img2seq.py:69) */
+  const float* keep_h;     /* optional [T][B][D] dropout multipliers for new_h (attention_cell.py:72), pre-scaled by 1/keep */
+  const float* keep_o;     /* optional [T][B][O] for new_o (:83) */
+  /* parameters: weight shadows in `dt`, biases / beta fp32 */
+  const void* w_img;       /* [A][C]          att_img.kernel^T */
+  const void* w_cat2;      /* [A+O][D]        att_h.kernel^T rows, then o_W_h^T rows */
+  const float* beta;       /* [A]             att_beta */
+  const void* w_lstm;      /* [4D][E+O+D]     lstm.kernel^T (gate rows i, j, f, o) */
+  const float* b_lstm;     /* [4D] */
+  const void* w_oc;        /* [O][C]          o_W_c^T */
+  const void* w_y;         /* [V][O]          y_W_o^T */
+  const void* w_init;      /* [2D+O][C]       W_c_0^T, W_h_0^T, W_o_0^T */
+  const float* b_init;     /* [2D+O] */
+  const void* emb;         /* [V+1][E]        embedding_table rows, then start_token */
+  /* parameter gradients, fp32, same layouts */
+  float* g_w_img; float* g_w_cat2; float* g_beta; float* g_w_lstm; float* g_b_lstm; float* g_w_oc; float* g_w_y;
+  float* g_w_init; float* g_b_init; float* g_emb;
+  /* results */
+  float* logits;           /* [T][B][ldl] time-major */
+  float* alphas;           /* [B][T][R] */
+  float* loss;             /* [4]: mean CE over valid tokens (x2), 0, n_words — ce_words (img2seq.py:74) = loss[0] * loss[3] */
+  float* denc;             /* f32 [B][R][C] gradient w.r.t. the encoder output */
+  void* ws;                /* lo_tfdec_workspace_bytes(args) bytes, zero-initialised once by the caller */
+} lo_tfdec_args;
+
+int64_t lo_sizeof_tfdec_args(void);
+int64_t lo_tfdec_workspace_bytes(const lo_tfdec_args* a);
+/* all T steps + logits; with_loss: masked CE into loss[] (and d logits kept for the backward) */
+int lo_tfdec_forward(const lo_tfdec_args* a, int with_loss, void* stream);
+/* backward of loss[0]: fills every g_* and denc (requires lo_tfdec_forward(with_loss=1) state in ws) */
+int lo_tfdec_backward(const lo_tfdec_args* a, void* stream);
+/* greedy decode (greedy_decoder_cell.py:38-66 + dynamic_decode.py:38-61): tokens [B][max_steps], fin_hist (optional)
+ * [B][max_steps] finished flags after each step; max_steps <= T */
+int lo_tfdec_greedy(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t* tokens, int32_t* fin_hist, void* stream);
+/* beam search (beam_search_decoder_cell.py:98-187): B = n_img*beam rows, rows_per_img = beam; ids/parents/fin_hist
+ * [n_img][max_steps][beam], logp [n_img][beam] */
+int lo_tfdec_beam(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents, int32_t* fin_hist,
+                  float* logp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimiser: torch.optim.Adam defaults (img2seq_torch.py:86-87, :168-170) on one flat buffer.
  * state_dev: float[2] = {step (as float), lr}; step is incremented on the device so the call is
  * graph-replayable.  shadow (optional) receives the bf16 copy of the updated parameters.

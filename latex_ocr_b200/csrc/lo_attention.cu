@@ -31,6 +31,23 @@ __device__ __forceinline__ uint64_t make_policy(int kind) {
   return kind == 1 ? l2_policy_evict_last() : (kind == 2 ? l2_policy_evict_first() : l2_policy_evict_normal());
 }
 
+// score non-linearity: ACT 0 = ReLU (torch flavour, seq2seq_torch.py:188), 1 = tanh (Genthial cell, attention_mechanism.py:82)
+template <int ACT, bool APPROX>
+__device__ __forceinline__ float att_act(float x) {
+  if constexpr (ACT == 0) return fmaxf(x, 0.f);
+  else if constexpr (APPROX) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  } else return tanhf(x);
+}
+// derivative given the pre-activation (ReLU) / the activation value (tanh)
+template <int ACT>
+__device__ __forceinline__ float att_dact(float pre, float post) {
+  if constexpr (ACT == 0) return pre > 0.f ? 1.f : 0.f;
+  else return 1.f - post * post;
+}
+
 template <typename T, int NV>
 struct ApCfg {
   static constexpr int CH = NV * 256;
@@ -41,7 +58,7 @@ struct ApCfg {
   static constexpr int SMEM = AP_STAGES * STAGE_BYTES + 128;
 };
 
-template <typename T, int NV, bool CL>
+template <typename T, int NV, bool CL, int ACT>
 __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
@@ -133,11 +150,11 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
           float v[8];
           ld8(sa + (size_t)ra * CH + (j * 32 + lane) * 8, v);
 #pragma unroll
-          for (int q = 0; q < 8; q++) e0 = fmaf(wv[j * 8 + q], fmaxf(v[q] + a2[j * 8 + q], 0.f), e0);
+          for (int q = 0; q < 8; q++) e0 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(v[q] + a2[j * 8 + q]), e0);
           if (two) {
             ld8(sa + (size_t)rb * CH + (j * 32 + lane) * 8, v);
 #pragma unroll
-            for (int q = 0; q < 8; q++) e1 = fmaf(wv[j * 8 + q], fmaxf(v[q] + a2[j * 8 + q], 0.f), e1);
+            for (int q = 0; q < 8; q++) e1 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(v[q] + a2[j * 8 + q]), e1);
           }
         }
         e0 = warp_sum(e0);
@@ -236,6 +253,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
         gate_pre[(int64_t)b * gate_stride + c] = g;
         gctx[(int64_t)b * CH + c] = g * t;
         if (gctx_bf) gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(g * t);
+      } else if (gctx_bf) {
+        gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(t);      // no gate (Genthial cell): bf16 mirror of the context itself
       }
     }
     // ... and normalises the attention weights of its own rows (scores never leave shared memory)
@@ -287,12 +306,14 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
       gate_pre[(int64_t)b * gate_stride + c] = g;
       gctx[(int64_t)b * CH + c] = g * t;
       if (gctx_bf) gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(g * t);
+    } else if (gctx_bf) {
+      gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(t);
     }
   }
   for (int r = threadIdx.x; r < R; r += AP_THREADS) alb[r] = expf(__ldcg(alb + r) - Mg) * invL;
 }
 
-template <typename T, int NV, bool CL>
+template <typename T, int NV, bool CL, int ACT>
 __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, const float* __restrict__ gate,
     int64_t o1_stride, const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride,
@@ -359,22 +380,23 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
       const int c0 = (j * 32 + lane) * 8;
       float g[8], cx[8], dg[8], gp[8];
       ld8(att2 + (int64_t)b * o1_stride + c0, a2 + j * 8);
-      ld8(gate + (int64_t)b * o1_stride + c0, g);
+      if (gate) ld8(gate + (int64_t)b * o1_stride + c0, g);
       ld8(ctx + (int64_t)b * CH + c0, cx);
       ld8(dgctx + (int64_t)b * dg_stride + c0, dg);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
+        if (!gate) g[i] = 1.f;                             // Genthial cell: the context is used ungated
         dc[j * 8 + i] = dg[i] * g[i];
         sdot = fmaf(dc[j * 8 + i], cx[i], sdot);
         gp[i] = dg[i] * cx[i] * g[i] * (1.f - g[i]);
       }
       if (sp == 0 && wid == 0) {
-        st8(dgp + (int64_t)b * dcat_stride + c0, gp);
+        if (dgp) st8(dgp + (int64_t)b * dcat_stride + c0, gp);
         if (dgp_bf) st8(dgp_bf + (int64_t)b * dcat_stride + c0, gp);
-        st8(dctx_out + (int64_t)b * CH + c0, dc + j * 8);
+        if (dctx_out) st8(dctx_out + (int64_t)b * CH + c0, dc + j * 8);
       }
     }
-    const float sall = warp_sum(sdot) + sreg[(int64_t)b * sreg_stride];
+    const float sall = warp_sum(sdot) + (sreg ? sreg[(int64_t)b * sreg_stride] : 0.f);
     const float* alb = alpha + (int64_t)b * alpha_stride;
     float* deb = de + (int64_t)b * alpha_stride;
     const float* drb = dreg + (int64_t)b * dreg_stride;
@@ -405,8 +427,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
         }
         d0 = warp_sum(d0);
         d1 = warp_sum(d1);
-        const float de0 = alb[row + ra] * (d0 + drb[row + ra] - sall);
-        const float de1 = two ? alb[row + rb] * (d1 + drb[row + rb] - sall) : 0.f;
+        const float de0 = alb[row + ra] * (d0 + (dreg ? drb[row + ra] : 0.f) - sall);
+        const float de1 = two ? alb[row + rb] * (d1 + (dreg ? drb[row + rb] : 0.f) - sall) : 0.f;
         if (lane == 0) {
           deb[row + ra] = de0;
           if (two) deb[row + rb] = de1;
@@ -418,16 +440,18 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const float pre = v[q] + a2[j * 8 + q];
-            macc[j * 8 + q] += (pre > 0.f) ? de0 : 0.f;
-            wacc[j * 8 + q] = fmaf(de0, fmaxf(pre, 0.f), wacc[j * 8 + q]);
+            const float post = att_act<ACT, sizeof(T) == 2>(pre);
+            macc[j * 8 + q] = fmaf(de0, att_dact<ACT>(pre, post), macc[j * 8 + q]);
+            wacc[j * 8 + q] = fmaf(de0, post, wacc[j * 8 + q]);
           }
           if (two) {
             ld8(sa + (size_t)rb * CH + (j * 32 + lane) * 8, v);
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const float pre = v[q] + a2[j * 8 + q];
-              macc[j * 8 + q] += (pre > 0.f) ? de1 : 0.f;
-              wacc[j * 8 + q] = fmaf(de1, fmaxf(pre, 0.f), wacc[j * 8 + q]);
+              const float post = att_act<ACT, sizeof(T) == 2>(pre);
+              macc[j * 8 + q] = fmaf(de1, att_dact<ACT>(pre, post), macc[j * 8 + q]);
+              wacc[j * 8 + q] = fmaf(de1, post, wacc[j * 8 + q]);
             }
           }
         }
@@ -554,30 +578,35 @@ static inline bool use_cluster(int ns, int R) {
   return g_opt_att_cluster && ns >= 2 && ns <= 8 && ((R + ns - 1) / ns) * 4 <= 16 * 1024;
 }
 
-template <typename T, int NV>
-static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
+template <typename T, int NV, int ACT>
+static int fwd_launch_a(const AttFwdArgs& x, cudaStream_t st) {
   using C = ApCfg<T, NV>;
   constexpr int SM_MAX = C::SMEM + 16 * 1024;
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
   const int rpi = x.rows_per_img > 1 ? x.rows_per_img : 1;
   if (use_cluster(ns, x.R)) {
     const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, true>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc, x.att2,
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, true, ACT>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc, x.att2,
                        x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R, ns,
                        (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
   } else {
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, false>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1, (const T*)x.enc,
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1, (const T*)x.enc,
                        x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R,
                        ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
   }
   LO_LAUNCH_OK();
   return LO_OK;
+}
+
+template <typename T, int NV>
+static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
+  return x.act == 1 ? fwd_launch_a<T, NV, 1>(x, st) : fwd_launch_a<T, NV, 0>(x, st);
 }
 
 int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st) {
@@ -591,13 +620,13 @@ int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st) {
   return fwd_launch<bf16, 4>(x, st);
 }
 
-template <typename T, int NV>
-static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
+template <typename T, int NV, int ACT>
+static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
   using C = ApCfg<T, NV>;
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
@@ -606,13 +635,18 @@ static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
       x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,       \
       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, x.dwf_part
   if (use_cluster(ns, x.R)) {
-    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, true>, dim3(ns, x.B), (size_t)C::SMEM, ns, st, LO_BWD_ARGS));
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, true, ACT>, dim3(ns, x.B), (size_t)C::SMEM, ns, st, LO_BWD_ARGS));
   } else {
-    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, false>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, LO_BWD_ARGS));
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, LO_BWD_ARGS));
   }
 #undef LO_BWD_ARGS
   LO_LAUNCH_OK();
   return LO_OK;
+}
+
+template <typename T, int NV>
+static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
+  return x.act == 1 ? bwd_launch_a<T, NV, 1>(x, st) : bwd_launch_a<T, NV, 0>(x, st);
 }
 
 int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st) {

@@ -158,6 +158,7 @@ struct AttFwdArgs {
   void* work;
   int rows_per_img;
   int nsplit_hint;
+  int act;             // 0 ReLU score (torch flavour), 1 tanh (Genthial cell)
 };
 struct AttBwdArgs {
   const void *att1, *enc;
@@ -170,6 +171,7 @@ struct AttBwdArgs {
   void* work;
   float* dwf_part;     // [B][A] running sum over the time loop of the full_att.weight gradient contributions (optional)
   int nsplit_hint;
+  int act;
 };
 extern int g_opt_att_pipe;
 extern int g_opt_conv_mc;

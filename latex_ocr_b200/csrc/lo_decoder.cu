@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_bwd_kernel(
 //   dwf[a]      += sum_{b,r,t} de[b,t,r] * relu(att1[b,r,a] + att2[t,b,a])
 // grid (A/64, ceil(R/32), B), 128 threads, thread tile 4(r) x 4(a), time chunks of 32 staged in smem.
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool WACC>
+template <typename T, bool WACC, int ACT = 0>
 __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, const float* __restrict__ out1,
                                                      int64_t o1_row, int64_t o1_step, const float* __restrict__ de,
                                                      const float* __restrict__ wf, T* __restrict__ datt1,
@@ -331,9 +331,16 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const float pre = x[i][j] + a2v[j];
-          const bool on = pre > 0.f;
-          acc[i][j] += on ? dv[i] : 0.f;
-          if (WACC) wacc[j] = fmaf(dv[i], on ? pre : 0.f, wacc[j]);   // (never 0 * -inf: padded rows carry pre = -inf)
+          if constexpr (ACT == 0) {
+            const bool on = pre > 0.f;
+            acc[i][j] += on ? dv[i] : 0.f;
+            if (WACC) wacc[j] = fmaf(dv[i], on ? pre : 0.f, wacc[j]);   // (never 0 * -inf: padded rows carry pre = -inf)
+          } else {
+            // tanh score (Genthial cell); padded rows: tanh(-inf) = -1 -> derivative 0, dv = 0
+            const float post = tanhf(pre);
+            acc[i][j] = fmaf(dv[i], 1.f - post * post, acc[i][j]);
+            if (WACC) wacc[j] = fmaf(dv[i], post, wacc[j]);
+          }
         }
     }
     __syncthreads();
@@ -1414,3 +1421,6 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
 }
 
 }  // extern "C"
+
+// TensorFlow-flavour (Genthial) decoder: same translation unit, shares the kernels above
+#include "lo_tfdecoder.cuh"

@@ -28,6 +28,15 @@ def test_argument_validation_without_gpu():
     assert b"null pointer" in L.lo_last_error()
     assert L.lo_attention_workspace_bytes(64, 512) == 4096 + 64 * 16 * 514 * 4
     assert L.lo_decoder_forward(None, 0, None) == -1
+    from latex_ocr_b200 import tf_decoder
+    L = tf_decoder._bind()
+    assert L.lo_sizeof_tfdec_args() == ctypes.sizeof(tf_decoder.TfDecArgs)
+    assert L.lo_tfdec_forward(None, 0, None) == -1
+    a = tf_decoder.TfDecArgs()
+    a.B, a.T, a.R, a.C, a.A, a.D, a.O, a.E, a.V, a.dt = 64, 150, 868, 512, 256, 512, 512, 80, 500, 1
+    assert L.lo_tfdec_workspace_bytes(ctypes.byref(a)) > 0
+    a.C = 300                                            # unsupported channel count is refused before any GPU work
+    assert L.lo_tfdec_forward(ctypes.byref(a), 0, None) == -1 and b"channels" in L.lo_last_error()
 
 
 def test_cpu_tensors_are_refused():

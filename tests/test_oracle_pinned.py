@@ -96,3 +96,29 @@ def test_restatement_matches_live_reference():
     out_ref = dec(enc(img), formula, lengths)
     out = rm.decoder_forward(pd, rm.encoder_forward(pe, img), formula, lengths)
     assert torch.equal(out[0], out_ref[0]) and torch.equal(out[3], out_ref[3]) and out[2] == out_ref[2]
+
+
+def test_tf_flavour_oracle_self_consistency():
+    """oracle/ref_tf_model.py (parity unpinned, see its header): structural checks that do not need TensorFlow —
+    beam 1 == greedy, the masked CE equals its definition, dropout multipliers of 1 are the identity."""
+    from oracle import ref_tf_model as tfm
+    V = 25
+    p = tfm.init_params_tf(V, seed=2)
+    p["y_W_o"] = p["y_W_o"] * 4.0
+    g = torch.Generator().manual_seed(0)
+    enc = torch.relu(torch.randn(2, 9, 512, generator=g))
+    formula = torch.randint(0, V, (2, 5), generator=g)
+    logits, alphas = tfm.decoder_train_logits(p, enc, formula)
+    assert logits.shape == (2, 5, V) and torch.allclose(alphas.sum(-1), torch.ones(2, 5), atol=1e-5)
+    ones = torch.ones(2, 5, 512)
+    l2, _ = tfm.decoder_train_logits(p, enc, formula, ones, ones)
+    assert torch.equal(logits, l2)
+    lengths = torch.tensor([5, 2])
+    loss, ce_words, n_words = tfm.masked_ce(logits, formula, lengths)
+    lp = torch.log_softmax(logits, -1)
+    want = -(lp[0, torch.arange(5), formula[0]].sum() + lp[1, torch.arange(2), formula[1, :2]].sum())
+    assert abs(ce_words.item() - want.item()) < 1e-4 and n_words.item() == 7 and abs(loss.item() - want.item() / 7) < 1e-5
+    gr = tfm.greedy_decode(p, enc, end_id=V - 1, max_iter=7)
+    bm, _ = tfm.beam_decode(p, enc, end_id=V - 1, beam=1, max_iter=7)
+    n = min(gr.shape[1], bm.shape[1])
+    assert torch.equal(gr[:, :n], bm[:, :n, 0])
