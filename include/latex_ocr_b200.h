@@ -80,6 +80,14 @@ int lo_conv1_pool_wgrad_u8(const uint8_t* img, const float* w, const float* bias
  * ReLU mask and pool argmax (first maximum in window scan order, as PyTorch) */
 int lo_conv1_pool_wgrad(const float* img, const float* w, const float* bias, const void* dpool, int dt,
                         float* dw, float* db, int N, int H, int W, void* stream);
+/* the same two kernels with the pixel normalisation x' = x * scale + offset applied to in-bounds pixels (zero padding stays
+ * zero in the normalised space): the TF flavour feeds (img - 128) / 128 (model/encoder.py:26-27) -> scale 1/128, offset -1.
+ * img: fp32 or uint8 [N][H][W] (img_is_u8). */
+int lo_conv1_pool_forward_norm(const void* img, int img_is_u8, float scale, float offset, const float* w,
+                               const float* bias, void* out, int dt, int N, int H, int W, void* stream);
+int lo_conv1_pool_wgrad_norm(const void* img, int img_is_u8, float scale, float offset, const float* w,
+                             const float* bias, const void* dpool, int dt, float* dw, float* db, int N, int H, int W,
+                             void* stream);
 /* y = [relu](conv3x3(x, w, pad) + bias) [* (mask > 0)] ; x [N][H][W][Cin], y [N][H+2pad-2][W+2pad-2][Cout];
  * pad in {0,1,2}.  mask (optional, same shape/dtype as y) implements the ReLU backward when this
  * call computes a data gradient.  bias may be NULL. */

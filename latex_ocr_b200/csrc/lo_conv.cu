@@ -15,7 +15,7 @@ __device__ __forceinline__ float ldpix(const uint8_t* p) { return (float)*p; }
 template <typename T, typename TI>
 __global__ void __launch_bounds__(256) conv1_pool_fwd_kernel(const TI* __restrict__ img, const float* __restrict__ w,
                                                               const float* __restrict__ bias, T* __restrict__ out,
-                                                              int N, int H, int W) {
+                                                              int N, int H, int W, float pscale, float poff) {
   __shared__ float sw[64 * 9];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) conv1_pool_fwd_kernel(const TI* __restric
 #pragma unroll
       for (int dx = 0; dx < 4; dx++) {
         const int wi = 2 * wo - 1 + dx;
-        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? ldpix(ib + (int64_t)hi * W + wi) : 0.f;
+        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? fmaf(ldpix(ib + (int64_t)hi * W + wi), pscale, poff) : 0.f;
       }
     }
     float o[8];
@@ -68,7 +68,7 @@ template <typename T, typename TI>
 __global__ void __launch_bounds__(256) conv1_pool_wgrad_kernel(const TI* __restrict__ img, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const T* __restrict__ dpool,
                                                                 float* __restrict__ dw, float* __restrict__ db,
-                                                                int N, int H, int W) {
+                                                                int N, int H, int W, float pscale, float poff) {
   __shared__ float sw[64 * 9];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) conv1_pool_wgrad_kernel(const TI* __restr
 #pragma unroll
       for (int dx = 0; dx < 4; dx++) {
         const int wi = 2 * wo - 1 + dx;
-        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? ldpix(ib + (int64_t)hi * W + wi) : 0.f;
+        x[dy][dx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? fmaf(ldpix(ib + (int64_t)hi * W + wi), pscale, poff) : 0.f;
       }
     }
     float g[8];
@@ -411,22 +411,23 @@ using namespace lo;
 
 extern "C" {
 
-static int conv1_fwd(const void* img, int u8, const float* w, const float* bias, void* out, int dt, int N, int H, int W, cudaStream_t st) {
+static int conv1_fwd(const void* img, int u8, const float* w, const float* bias, void* out, int dt, int N, int H, int W, cudaStream_t st,
+                     float pscale = 1.f, float poff = 0.f) {
   LO_CHECK_ARG(img && w && bias && out, "null pointer");
   LO_CHECK_ARG(N > 0 && H >= 2 && W >= 2, "shape");
   const int64_t work = (int64_t)N * (H / 2) * (W / 2) * 8;
   const int grid = grid_for(work, 256);
   if (u8) {
-    LO_DISPATCH_DT(dt, T, (conv1_pool_fwd_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, w, bias, (T*)out, N, H, W)));
+    LO_DISPATCH_DT(dt, T, (conv1_pool_fwd_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, w, bias, (T*)out, N, H, W, pscale, poff)));
   } else {
-    LO_DISPATCH_DT(dt, T, (conv1_pool_fwd_kernel<T, float><<<grid, 256, 0, st>>>((const float*)img, w, bias, (T*)out, N, H, W)));
+    LO_DISPATCH_DT(dt, T, (conv1_pool_fwd_kernel<T, float><<<grid, 256, 0, st>>>((const float*)img, w, bias, (T*)out, N, H, W, pscale, poff)));
   }
   LO_LAUNCH_OK();
   return LO_OK;
 }
 
 static int conv1_wgrad(const void* img, int u8, const float* w, const float* bias, const void* dpool, int dt, float* dw, float* db,
-                       int N, int H, int W, cudaStream_t st) {
+                       int N, int H, int W, cudaStream_t st, float pscale = 1.f, float poff = 0.f) {
   LO_CHECK_ARG(img && w && bias && dpool && dw && db, "null pointer");
   LO_CUDA(cudaMemsetAsync(dw, 0, 64 * 9 * sizeof(float), st));
   LO_CUDA(cudaMemsetAsync(db, 0, 64 * sizeof(float), st));
@@ -434,9 +435,9 @@ static int conv1_wgrad(const void* img, int u8, const float* w, const float* bia
   int grid = (int)((npos + 31) / 32);
   if (grid > 148 * 4) grid = 148 * 4;
   if (u8) {
-    LO_DISPATCH_DT(dt, T, (conv1_pool_wgrad_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, w, bias, (const T*)dpool, dw, db, N, H, W)));
+    LO_DISPATCH_DT(dt, T, (conv1_pool_wgrad_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, w, bias, (const T*)dpool, dw, db, N, H, W, pscale, poff)));
   } else {
-    LO_DISPATCH_DT(dt, T, (conv1_pool_wgrad_kernel<T, float><<<grid, 256, 0, st>>>((const float*)img, w, bias, (const T*)dpool, dw, db, N, H, W)));
+    LO_DISPATCH_DT(dt, T, (conv1_pool_wgrad_kernel<T, float><<<grid, 256, 0, st>>>((const float*)img, w, bias, (const T*)dpool, dw, db, N, H, W, pscale, poff)));
   }
   LO_LAUNCH_OK();
   return LO_OK;
@@ -457,6 +458,15 @@ int lo_conv1_pool_wgrad(const float* img, const float* w, const float* bias, con
 int lo_conv1_pool_wgrad_u8(const uint8_t* img, const float* w, const float* bias, const void* dpool, int dt, float* dw,
                            float* db, int N, int H, int W, void* stream) {
   return conv1_wgrad(img, 1, w, bias, dpool, dt, dw, db, N, H, W, (cudaStream_t)stream);
+}
+
+int lo_conv1_pool_forward_norm(const void* img, int img_is_u8, float scale, float offset, const float* w, const float* bias, void* out,
+                               int dt, int N, int H, int W, void* stream) {
+  return conv1_fwd(img, img_is_u8, w, bias, out, dt, N, H, W, (cudaStream_t)stream, scale, offset);
+}
+int lo_conv1_pool_wgrad_norm(const void* img, int img_is_u8, float scale, float offset, const float* w, const float* bias,
+                             const void* dpool, int dt, float* dw, float* db, int N, int H, int W, void* stream) {
+  return conv1_wgrad(img, img_is_u8, w, bias, dpool, dt, dw, db, N, H, W, (cudaStream_t)stream, scale, offset);
 }
 
 int lo_conv3x3(const void* x, const void* w, const float* bias, const void* mask, void* y, int dt, int N, int H, int W,

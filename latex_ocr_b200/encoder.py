@@ -52,6 +52,11 @@ class EncoderCNN(nn.Module):
             raise NotImplementedError("precision must be 'fp32' or 'bf16'")
         self.impl = impl if impl is not None else getattr(config, "conv_impl", "simt")
         self.tdtype = torch.float32 if self.precision == "fp32" else torch.bfloat16
+        # pixel normalisation fused into conv1: None = raw 0..255 floats (torch flavour, img2seq_torch.py:115-117);
+        # "tf" = (img - 128) / 128 (TF flavour, model/encoder.py:26-27)
+        self.input_norm = getattr(config, "input_norm", None)
+        if self.input_norm not in (None, "tf"):
+            raise NotImplementedError("input_norm=%r" % (self.input_norm,))
         specs = []
         for idx, cin, cout, _, _ in _LAYERS:
             specs.append(("cnn.%s.weight" % idx, (cout, 3, 3, cin)))
@@ -155,8 +160,12 @@ class EncoderCNN(nn.Module):
         st, dt, impl, S = stream_ptr(), _dt(self.precision), self._impl(), self.store
         A = ws["acts"]
         ws["img"] = img
-        conv1 = L.lo_conv1_pool_forward_u8 if img.dtype == torch.uint8 else L.lo_conv1_pool_forward
-        check(conv1(ptr(img), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), dt, N, H, W, st))
+        if self.input_norm == "tf":
+            check(L.lo_conv1_pool_forward_norm(ptr(img), int(img.dtype == torch.uint8), 1.0 / 128.0, -1.0, ptr(S.f32("cnn.0.weight")),
+                                               ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), dt, N, H, W, st))
+        else:
+            conv1 = L.lo_conv1_pool_forward_u8 if img.dtype == torch.uint8 else L.lo_conv1_pool_forward
+            check(conv1(ptr(img), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), dt, N, H, W, st))
         x = A["P0"]
         for idx, cin, cout, pad, pool in _LAYERS[1:]:
             y = A["Y" + idx]
@@ -204,6 +213,11 @@ class EncoderCNN(nn.Module):
                 ysrc = A[src]
                 check(L.lo_maxpool_backward(ptr(ysrc), ptr(A[xin]), ptr(G[xin]), ptr(G[src]), dt, N, ysrc.shape[1], ysrc.shape[2],
                                             ysrc.shape[3], pool_k[0], pool_k[1], st))
+        if self.input_norm == "tf":
+            check(L.lo_conv1_pool_wgrad_norm(ptr(ws["img"]), int(ws["img"].dtype == torch.uint8), 1.0 / 128.0, -1.0,
+                                             ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
+                                             ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))
+            return
         wg1 = L.lo_conv1_pool_wgrad_u8 if ws["img"].dtype == torch.uint8 else L.lo_conv1_pool_wgrad
         check(wg1(ptr(ws["img"]), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
                                     ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))
