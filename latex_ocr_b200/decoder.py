@@ -93,13 +93,13 @@ class Attention(nn.Module):
 
 class DecoderWithAttention(nn.Module):
     def __init__(self, attention_dim, embed_dim, decoder_dim, vocab_size, encoder_dim=512, dropout=0.5,
-                 device="cuda", precision="bf16", impl="simt"):
+                 device="cuda", precision="bf16", impl=None):
         super().__init__()
         self.encoder_dim, self.attention_dim = encoder_dim, attention_dim
         self.embed_dim, self.decoder_dim, self.vocab_size = embed_dim, decoder_dim, vocab_size
         self.dropout_p = dropout
         self.precision = precision
-        self.impl = impl
+        self.impl = impl if impl is not None else ("tc" if precision == "bf16" else "simt")
         self.alpha_c = 1.0                      # img2seq_torch.py:157
         self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
         A, E, D, V, C = attention_dim, embed_dim, decoder_dim, vocab_size, encoder_dim

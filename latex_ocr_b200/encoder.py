@@ -50,7 +50,7 @@ class EncoderCNN(nn.Module):
         self.precision = precision or getattr(config, "precision", "bf16")
         if self.precision not in ("fp32", "bf16"):
             raise NotImplementedError("precision must be 'fp32' or 'bf16'")
-        self.impl = impl if impl is not None else getattr(config, "conv_impl", "simt")
+        self.impl = impl if impl is not None else getattr(config, "conv_impl", "tc" if self.precision == "bf16" else "simt")
         self.tdtype = torch.float32 if self.precision == "fp32" else torch.bfloat16
         # pixel normalisation fused into conv1: None = raw 0..255 floats (torch flavour, img2seq_torch.py:115-117);
         # "tf" = (img - 128) / 128 (TF flavour, model/encoder.py:26-27)

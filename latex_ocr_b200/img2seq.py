@@ -30,7 +30,8 @@ class Img2SeqModel:
             raise _lib.LatexOcrB200Error("latex_ocr_b200 runs on CUDA devices only (device=%r)" % (dev,))
         self.device = torch.device(dev)
         self.precision = precision or getattr(config, "precision", "bf16")
-        self.impl = impl or getattr(config, "impl", "simt")
+        # kernels: "tc" = tcgen05/TMA convolutions and GEMMs (bf16 storage only), "simt" = CUDA-core twins (fp32 tight-parity mode)
+        self.impl = impl or getattr(config, "impl", "tc" if self.precision == "bf16" else "simt")
         self._n_tok = n_tok if n_tok is not None else (vocab.n_tok if vocab is not None else None)
         self.encoder = None
         self.decoder = None

@@ -99,7 +99,7 @@ class Decoder(nn.Module):
             raise NotImplementedError("beam-search diversity penalty (div_gamma != 1 and div_prob != 0)")
         self.max_length_formula = int(getattr(config, "max_length_formula", 150))
         self.precision = precision or getattr(config, "precision", "bf16")
-        self.impl = impl if impl is not None else getattr(config, "conv_impl", "simt")
+        self.impl = impl if impl is not None else getattr(config, "conv_impl", "tc" if self.precision == "bf16" else "simt")
         self.tdtype = torch.float32 if self.precision == "fp32" else torch.bfloat16
         self.store = FlatStore(tf_decoder_specs(self.V, self.C, self.A, self.D, self.O, self.E), device,
                                bf16_shadow=(self.precision == "bf16"))
