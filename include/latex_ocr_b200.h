@@ -88,6 +88,16 @@ int lo_conv1_pool_forward_norm(const void* img, int img_is_u8, float scale, floa
 int lo_conv1_pool_wgrad_norm(const void* img, int img_is_u8, float scale, float offset, const float* w,
                              const float* bias, const void* dpool, int dt, float* dw, float* db, int N, int H, int W,
                              void* stream);
+/* General strided convolution = im2col + lo_gemm: the 'cnn' encoder variant's Conv2d(512,512,(2,4),stride=2,padding=1)
+ * (seq2seq_torch.py:80).  col [N*Ho*Wo][R*S*C], taps-major, C % 8 == 0; forward y = relu(col W^T + b) with W [Cout][R][S][C];
+ * weight gradient dW = dy^T col; data gradient dcol = dy W then lo_col2im (a gather over the windows covering each input
+ * pixel, optional ReLU mask of the producing layer). */
+int lo_im2col(const void* x, void* col, int dt, int N, int H, int W, int C, int R, int S, int stride, int pad,
+              void* stream);
+int lo_col2im(const void* dcol, const void* mask, void* dx, int dt, int N, int H, int W, int C, int R, int S,
+              int stride, int pad, void* stream);
+/* out[n][k] = in[k][n] for k < K, n < N */
+int lo_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int dt, int K, int N, void* stream);
 /* y = [relu](conv3x3(x, w, pad) + bias) [* (mask > 0)] ; x [N][H][W][Cin], y [N][H+2pad-2][W+2pad-2][Cout];
  * pad in {0,1,2}.  mask (optional, same shape/dtype as y) implements the ReLU backward when this
  * call computes a data gradient.  bias may be NULL. */

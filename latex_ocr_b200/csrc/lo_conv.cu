@@ -405,6 +405,80 @@ static inline int grid_for(int64_t work, int threads) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// General strided convolution as im2col + GEMM: the 'cnn' encoder variant's Conv2d(512, 512, (2,4), stride 2, padding 1)
+// (seq2seq_torch.py:80).  col [N*Ho*Wo][R*S*C] (tap-major like the 3x3 kernels' K order), 8 channels per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C, int R, int S, int stride,
+                              int pad, int Ho, int Wo) {
+  const int C8 = C / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * R * S * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    int64_t q = i / C8;
+    const int s = (int)(q % S); q /= S;
+    const int r = (int)(q % R); q /= R;
+    const int wo = (int)(q % Wo); q /= Wo;
+    const int ho = (int)(q % Ho);
+    const int n = (int)(q / Ho);
+    const int hi = ho * stride - pad + r, wi = wo * stride - pad + s;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) ld8(x + (((int64_t)n * H + hi) * W + wi) * C + c8 * 8, v);
+    st8(col + i * 8, v);
+  }
+}
+// dx[n][hi][wi][c] = sum over the windows (ho,r), (wo,s) that cover (hi,wi) of dcol[n][ho][wo][r][s][c]  [* (mask > 0)]  — a gather
+template <typename T>
+__global__ void col2im_kernel(const T* __restrict__ dcol, const T* __restrict__ mask, T* __restrict__ dx, int N, int H, int W, int C,
+                              int R, int S, int stride, int pad, int Ho, int Wo) {
+  const int C8 = C / 8;
+  const int64_t total = (int64_t)N * H * W * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    int64_t q = i / C8;
+    const int wi = (int)(q % W); q /= W;
+    const int hi = (int)(q % H);
+    const int n = (int)(q / H);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < R; r++) {
+      const int hn = hi + pad - r;
+      if (hn < 0 || hn % stride) continue;
+      const int ho = hn / stride;
+      if (ho >= Ho) continue;
+      for (int s2 = 0; s2 < S; s2++) {
+        const int wn = wi + pad - s2;
+        if (wn < 0 || wn % stride) continue;
+        const int wo = wn / stride;
+        if (wo >= Wo) continue;
+        float v[8];
+        ld8(dcol + (((((int64_t)n * Ho + ho) * Wo + wo) * R + r) * S + s2) * C + c8 * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += v[k];
+      }
+    }
+    if (mask) {
+      float m[8];
+      ld8(mask + i * 8, m);
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] = m[k] > 0.f ? acc[k] : 0.f;
+    }
+    st8(dx + i * 8, acc);
+  }
+}
+// out[n][k] = in[k][n]
+template <typename T>
+__global__ void transpose2d_kernel(const T* __restrict__ in, int64_t ld_in, T* __restrict__ out, int64_t ld_out, int K, int Nn) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (k0 + i < K && n0 + threadIdx.x < Nn) tile[i][threadIdx.x] = ldf(in + (int64_t)(k0 + i) * ld_in + n0 + threadIdx.x);
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (n0 + i < Nn && k0 + threadIdx.x < K) stf(out + (int64_t)(n0 + i) * ld_out + k0 + threadIdx.x, tile[threadIdx.x][i]);
+}
+
 }  // namespace lo
 
 using namespace lo;
@@ -467,6 +541,37 @@ int lo_conv1_pool_forward_norm(const void* img, int img_is_u8, float scale, floa
 int lo_conv1_pool_wgrad_norm(const void* img, int img_is_u8, float scale, float offset, const float* w, const float* bias,
                              const void* dpool, int dt, float* dw, float* db, int N, int H, int W, void* stream) {
   return conv1_wgrad(img, img_is_u8, w, bias, dpool, dt, dw, db, N, H, W, (cudaStream_t)stream, scale, offset);
+}
+
+int lo_im2col(const void* x, void* col, int dt, int N, int H, int W, int C, int R, int S, int stride, int pad, void* stream) {
+  LO_CHECK_ARG(x && col && N > 0 && C % 8 == 0 && R > 0 && S > 0 && stride > 0 && pad >= 0, "null pointer / shape (C%8)");
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  LO_CHECK_ARG(Ho > 0 && Wo > 0, "empty output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t work = (int64_t)N * Ho * Wo * R * S * (C / 8);
+  LO_DISPATCH_DT(dt, T, (im2col_kernel<T><<<grid_for(work, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, R, S, stride, pad, Ho, Wo)));
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+int lo_col2im(const void* dcol, const void* mask, void* dx, int dt, int N, int H, int W, int C, int R, int S, int stride, int pad,
+              void* stream) {
+  LO_CHECK_ARG(dcol && dx && N > 0 && C % 8 == 0 && R > 0 && S > 0 && stride > 0 && pad >= 0, "null pointer / shape (C%8)");
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  LO_CHECK_ARG(Ho > 0 && Wo > 0, "empty output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t work = (int64_t)N * H * W * (C / 8);
+  LO_DISPATCH_DT(dt, T, (col2im_kernel<T><<<grid_for(work, 256), 256, 0, st>>>((const T*)dcol, (const T*)mask, (T*)dx, N, H, W, C, R, S,
+                                                                                  stride, pad, Ho, Wo)));
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+int lo_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int dt, int K, int N, void* stream) {
+  LO_CHECK_ARG(in && out && K > 0 && N > 0 && ld_in >= N && ld_out >= K, "null pointer / shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  LO_DISPATCH_DT(dt, T, (transpose2d_kernel<T><<<dim3(cdiv(N, 32), cdiv(K, 32)), dim3(32, 8), 0, st>>>((const T*)in, ld_in, (T*)out, ld_out,
+                                                                                                          K, N)));
+  LO_LAUNCH_OK();
+  return LO_OK;
 }
 
 int lo_conv3x3(const void* x, const void* w, const float* bias, const void* mask, void* y, int dt, int N, int H, int W,

@@ -118,6 +118,13 @@ int gemm(const void* A, int dtA, const void* B, int dtB, void* C, int dtC, const
     return tc_gemm_nt_ex((const bf16*)A, d.sam, (const bf16*)B, d.sbn, C, dtC, d.ldc, d.M, d.N, d.K, d.bias, d.accumulate, d.relu, 1, 0,
                          d.M <= 64 ? 1 : 0, st);
   }
+  // C = A^T B with both operands stored [K][.] (weight gradients): tcgen05 MN-major kernel, split-K atomics onto a cleared C
+  if (impl == LO_IMPL_TC && dtA == LO_BF16 && dtB == LO_BF16 && dtC == LO_F32 && d.sam == 1 && d.sbn == 1 && d.batch == 1 && !d.bias &&
+      !d.relu && !d.accumulate && d.sak % 8 == 0 && d.sbk % 8 == 0 && d.M >= 64 && d.N >= 64 && ((uintptr_t)A & 15) == 0 &&
+      ((uintptr_t)B & 15) == 0 && tc_available()) {
+    LO_CUDA(cudaMemset2DAsync(C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, st));
+    return tc_gemm_tn((const bf16*)A, d.sak, (const bf16*)B, d.sbk, (float*)C, d.ldc, d.M, d.N, d.K, st);
+  }
   // split-K only for fp32 outputs without ReLU when the tile grid would leave most SMs idle and K is long
   int splitk = 1;
   if (dtC == LO_F32 && !d.relu && d.K >= 2048) {

@@ -18,6 +18,15 @@ from .params import FlatStore, ParamHolder
 # (sequential index, Cin, Cout, pad, pool after)    seq2seq_torch.py:35-56
 _LAYERS = (("0", 1, 64, 1, (2, 2)), ("3", 64, 128, 1, (2, 2)), ("6", 128, 256, 1, None),
            ("8", 256, 256, 1, (2, 1)), ("11", 256, 512, 1, (1, 2)), ("14", 512, 512, 0, None))
+# 'cnn' variant (seq2seq_torch.py:58-86): the two asymmetric pools are replaced by Conv2d(512,512,(2,4),stride 2,padding 1)+ReLU
+# (index 12; a 6th tuple element gives kernel (R,S) and stride of a non-3x3 layer, run as im2col + GEMM)
+_LAYERS_CNN = (("0", 1, 64, 1, (2, 2)), ("3", 64, 128, 1, (2, 2)), ("6", 128, 256, 1, None), ("8", 256, 256, 1, None),
+               ("10", 256, 512, 1, None), ("12", 512, 512, 1, None, (2, 4, 2)), ("14", 512, 512, 0, None))
+
+
+def _geom(layer):
+    """(R, S, stride) of a layer tuple."""
+    return layer[5] if len(layer) > 5 else (3, 3, 1)
 
 
 def timing_signal_table(channels, height, width, device):
@@ -44,9 +53,9 @@ class EncoderCNN(nn.Module):
         super().__init__()
         self._config = config
         name = getattr(config, "encoder_cnn", "vanilla")
-        if name != "vanilla":
-            # seq2seq_torch.py:58-86 'cnn' variant (strided (2,4) conv) is not on the north-star path
-            raise NotImplementedError("encoder_cnn=%r: only the 'vanilla' stack is implemented" % name)
+        if name not in ("vanilla", "cnn"):
+            raise NotImplementedError("encoder_cnn=%r: 'vanilla' and 'cnn' are the reference's stacks" % name)   # seq2seq_torch.py:31-86
+        self.layers = _LAYERS if name == "vanilla" else _LAYERS_CNN
         self.precision = precision or getattr(config, "precision", "bf16")
         if self.precision not in ("fp32", "bf16"):
             raise NotImplementedError("precision must be 'fp32' or 'bf16'")
@@ -58,12 +67,14 @@ class EncoderCNN(nn.Module):
         if self.input_norm not in (None, "tf"):
             raise NotImplementedError("input_norm=%r" % (self.input_norm,))
         specs = []
-        for idx, cin, cout, _, _ in _LAYERS:
-            specs.append(("cnn.%s.weight" % idx, (cout, 3, 3, cin)))
+        for l in self.layers:
+            idx, cin, cout = l[:3]
+            R, S_, _ = _geom(l)
+            specs.append(("cnn.%s.weight" % idx, (cout, R, S_, cin)))
             specs.append(("cnn.%s.bias" % idx, (cout,)))
         self.store = FlatStore(specs, device, bf16_shadow=(self.precision == "bf16"))
         self.cnn = nn.ModuleDict()
-        for idx, cin, cout, _, _ in _LAYERS:
+        for idx in (l[0] for l in self.layers):
             h = ParamHolder()
             h.bind("weight", self.store, "cnn.%s.weight" % idx, permute=(0, 3, 1, 2))
             h.bind("bias", self.store, "cnn.%s.bias" % idx)
@@ -75,8 +86,10 @@ class EncoderCNN(nn.Module):
     # nn.Conv2d default init (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)))
     def reset_parameters(self):
         with torch.no_grad():
-            for idx, cin, cout, _, _ in _LAYERS:
-                b = 1.0 / math.sqrt(cin * 9)
+            for l in self.layers:
+                idx, cin = l[0], l[1]
+                R, S_, _ = _geom(l)
+                b = 1.0 / math.sqrt(cin * R * S_)
                 self.cnn[idx].weight.uniform_(-b, b)
                 self.cnn[idx].bias.uniform_(-b, b)
         self._shadow_fresh = False
@@ -95,8 +108,10 @@ class EncoderCNN(nn.Module):
 
     def out_hw(self, H, W):
         h, w = H, W
-        for _, _, _, pad, pool in _LAYERS:
-            h, w = h + 2 * pad - 2, w + 2 * pad - 2
+        for l in self.layers:
+            pad, pool = l[3], l[4]
+            R, S_, stride = _geom(l)
+            h, w = (h + 2 * pad - R) // stride + 1, (w + 2 * pad - S_) // stride + 1
             if pool:
                 h, w = h // pool[0], w // pool[1]
         return h, w
@@ -110,8 +125,13 @@ class EncoderCNN(nn.Module):
             ws = {"acts": {}, "grads": None}
             h, w = H, W
             shapes = {}
-            for idx, cin, cout, pad, pool in _LAYERS:
-                h, w = h + 2 * pad - 2, w + 2 * pad - 2
+            for l in self.layers:
+                idx, cin, cout, pad, pool = l[:5]
+                R, S_, stride = _geom(l)
+                if (R, S_, stride) != (3, 3, 1):
+                    ws["col" + idx] = torch.empty(N * ((h + 2 * pad - R) // stride + 1) * ((w + 2 * pad - S_) // stride + 1), R * S_ * cin,
+                                                  dtype=td, device=dev)
+                h, w = (h + 2 * pad - R) // stride + 1, (w + 2 * pad - S_) // stride + 1
                 if idx == "0":
                     h, w = h // 2, w // 2
                     shapes["P0"] = (N, h, w, cout)
@@ -131,8 +151,8 @@ class EncoderCNN(nn.Module):
         if need_grad and ws["grads"] is None:
             dev, td = self.store.device, self.tdtype
             ws["grads"] = {k: torch.empty(s, dtype=td, device=dev) for k, s in ws["shapes"].items()}
-            ws["wflip"] = {idx: torch.empty(cin * 9 * cout, dtype=td, device=dev)
-                           for idx, cin, cout, _, _ in _LAYERS if idx != "0"}
+            ws["wflip"] = {l[0]: torch.empty(l[1] * _geom(l)[0] * _geom(l)[1] * l[2], dtype=td, device=dev)
+                           for l in self.layers if l[0] != "0"}
         return ws
 
     def _impl(self):
@@ -167,10 +187,20 @@ class EncoderCNN(nn.Module):
             conv1 = L.lo_conv1_pool_forward_u8 if img.dtype == torch.uint8 else L.lo_conv1_pool_forward
             check(conv1(ptr(img), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), dt, N, H, W, st))
         x = A["P0"]
-        for idx, cin, cout, pad, pool in _LAYERS[1:]:
+        for l in self.layers[1:]:
+            idx, cin, cout, pad, pool = l[:5]
+            R, S_, stride = _geom(l)
             y = A["Y" + idx]
-            check(L.lo_conv3x3(ptr(x), ptr(S.w("cnn.%s.weight" % idx)), ptr(S.f32("cnn.%s.bias" % idx)), None, ptr(y), dt,
-                               N, x.shape[1], x.shape[2], cin, cout, pad, 1, impl, st))
+            if (R, S_, stride) == (3, 3, 1):
+                check(L.lo_conv3x3(ptr(x), ptr(S.w("cnn.%s.weight" % idx)), ptr(S.f32("cnn.%s.bias" % idx)), None, ptr(y), dt,
+                                   N, x.shape[1], x.shape[2], cin, cout, pad, 1, impl, st))
+            else:
+                # general strided conv: im2col + GEMM with bias + ReLU in the epilogue
+                col = ws["col" + idx]
+                M, K = col.shape
+                check(L.lo_im2col(ptr(x), ptr(col), dt, N, x.shape[1], x.shape[2], cin, R, S_, stride, pad, st))
+                check(L.lo_gemm(ptr(col), dt, ptr(S.w("cnn.%s.weight" % idx)), dt, ptr(y), dt, M, cout, K, K, 1, 1, K, cout, 1, 0, 0, 0,
+                                ptr(S.f32("cnn.%s.bias" % idx)), 0, 1, impl, st))
             x = y
             if pool:
                 p = A["P" + idx]
@@ -189,27 +219,46 @@ class EncoderCNN(nn.Module):
         ws = self._workspace(N, H, W, True)
         st, dt, impl, S = stream_ptr(), _dt(self.precision), self._impl(), self.store
         A, G = ws["acts"], ws["grads"]
-        for idx, cin, cout, _, _ in _LAYERS[1:]:
-            check(L.lo_conv_weight_flip(ptr(S.w("cnn.%s.weight" % idx)), ptr(ws["wflip"][idx]), dt, cin, cout, st))
-        y6 = A["Y14"]
-        check(L.lo_relu_mask_cast(ptr(denc), ptr(y6), ptr(G["Y14"]), dt, y6.numel(), st))
-        # walk the stack backwards: (conv idx, its input activation key, gradient key of its output)
-        plan = (("14", "P11"), ("11", "P8"), ("8", "Y6"), ("6", "P3"), ("3", "P0"))
-        cfg = {l[0]: l for l in _LAYERS}
-        for idx, xin in plan:
-            _, cin, cout, pad, pool = cfg[idx]
+        for l in self.layers[1:]:
+            idx, cin, cout = l[:3]
+            R, S_, stride = _geom(l)
+            if (R, S_, stride) == (3, 3, 1):
+                check(L.lo_conv_weight_flip(ptr(S.w("cnn.%s.weight" % idx)), ptr(ws["wflip"][idx]), dt, cin, cout, st))
+            else:                                           # [Cout][K] -> [K][Cout] for dcol = dy @ W
+                check(L.lo_transpose(ptr(S.w("cnn.%s.weight" % idx)), R * S_ * cin, ptr(ws["wflip"][idx]), cout, dt, cout, R * S_ * cin, st))
+        last = "Y" + self.layers[-1][0]
+        y6 = A[last]
+        check(L.lo_relu_mask_cast(ptr(denc), ptr(y6), ptr(G[last]), dt, y6.numel(), st))
+        # walk the stack backwards: (layer, key of its input activation = the previous layer's pooled or plain output)
+        plan = []
+        for i in range(len(self.layers) - 1, 0, -1):
+            prev = self.layers[i - 1]
+            plan.append((self.layers[i], ("P" if prev[4] else "Y") + prev[0]))
+        cfg = {l[0]: l for l in self.layers}
+        for l, xin in plan:
+            idx, cin, cout, pad, pool = l[:5]
+            R, S_, stride = _geom(l)
             x = A[xin]
             dy = G["Y" + idx]
-            check(L.lo_conv3x3_wgrad(ptr(x), ptr(dy), ptr(S.g("cnn.%s.weight" % idx)), ptr(S.g("cnn.%s.bias" % idx)), dt,
-                                     N, x.shape[1], x.shape[2], cin, cout, pad, impl, st))
-            # data gradient = conv3x3(dy, flipped weights, pad' = 2 - pad); ReLU mask fused when the producer is a conv
-            mask = A[xin] if xin.startswith("Y") else None
-            check(L.lo_conv3x3(ptr(dy), ptr(ws["wflip"][idx]), None, ptr(mask), ptr(G[xin]), dt,
-                               N, dy.shape[1], dy.shape[2], cout, cin, 2 - pad, 0, impl, st))
+            mask = A[xin] if xin.startswith("Y") else None   # ReLU mask fused when the producer is a conv
+            if (R, S_, stride) == (3, 3, 1):
+                check(L.lo_conv3x3_wgrad(ptr(x), ptr(dy), ptr(S.g("cnn.%s.weight" % idx)), ptr(S.g("cnn.%s.bias" % idx)), dt,
+                                         N, x.shape[1], x.shape[2], cin, cout, pad, impl, st))
+                # data gradient = conv3x3(dy, flipped weights, pad' = 2 - pad)
+                check(L.lo_conv3x3(ptr(dy), ptr(ws["wflip"][idx]), None, ptr(mask), ptr(G[xin]), dt,
+                                   N, dy.shape[1], dy.shape[2], cout, cin, 2 - pad, 0, impl, st))
+            else:
+                col = ws["col" + idx]                       # still holds im2col(x) from the forward
+                M, K = col.shape
+                check(L.lo_gemm(ptr(dy), dt, ptr(col), dt, ptr(S.g("cnn.%s.weight" % idx)), _lib.LO_F32, cout, K, M, 1, cout, K, 1, K, 1,
+                                0, 0, 0, None, 0, 0, impl, st))                                    # dW = dy^T col
+                check(L.lo_colsum(ptr(dy), dt, ptr(S.g("cnn.%s.bias" % idx)), M, cout, cout, 0, st))
+                check(L.lo_gemm(ptr(dy), dt, ptr(ws["wflip"][idx]), dt, ptr(col), dt, M, K, cout, cout, 1, 1, cout, K, 1, 0, 0, 0, None,
+                                0, 0, impl, st))                                                   # dcol = dy W  (col reused)
+                check(L.lo_col2im(ptr(col), ptr(mask), ptr(G[xin]), dt, N, x.shape[1], x.shape[2], cin, R, S_, stride, pad, st))
             if xin.startswith("P") and xin != "P0":
                 src = "Y" + xin[1:]
-                pidx = xin[1:]
-                pool_k = cfg[pidx][4]
+                pool_k = cfg[xin[1:]][4]
                 ysrc = A[src]
                 check(L.lo_maxpool_backward(ptr(ysrc), ptr(A[xin]), ptr(G[xin]), ptr(G[src]), dt, N, ysrc.shape[1], ysrc.shape[2],
                                             ysrc.shape[3], pool_k[0], pool_k[1], st))

@@ -43,6 +43,7 @@ class Img2SeqModel:
         self.impl = impl if impl is not None else getattr(config, "conv_impl", "tc" if self.precision == "bf16" else "simt")
         self.encoder = self.decoder = None
         self.lr = None
+        self.dist = None          # set by latex_ocr_b200.dist.attach(model): data-parallel gradient all-reduce
         self.last_epoch_stats = {}
 
     # img2seq.py:33-53 / :55-66: the TF graph is replaced by the two modules
@@ -102,8 +103,21 @@ class Img2SeqModel:
             kp, T = float(dropout), formula_t.shape[1]
             keep_h = (torch.rand(N, T, self.decoder.D, device=self.device) < kp).float() / kp
             keep_o = (torch.rand(N, T, self.decoder.O, device=self.device) < kp).float() / kp
-        loss, denc = self.decoder.loss_and_backward(enc, formula_t, length_t, keep_h, keep_o)
+        n_words = None
+        if self.dist is not None and self.dist.world_size > 1:
+            # the loss is a mean over valid tokens: all-reduce the token count (one scalar), then the SUM of the rank
+            # gradients is the gradient of the global mean
+            import torch.distributed as tdist
+            nw = torch.tensor([float(length_t.sum())], device=self.device)
+            tdist.all_reduce(nw, group=self.dist.group)
+            n_words = float(nw.item())
+        loss, denc = self.decoder.loss_and_backward(enc, formula_t, length_t, keep_h, keep_o, n_words)
+        if self.dist is not None:
+            self.dist.reduce_async(self.decoder.store.grad)             # flies while the encoder backward runs
         self.encoder.backward_raw(tuple(img.shape), denc.view(N, enc.shape[1], enc.shape[2], enc.shape[3]))
+        if self.dist is not None:
+            self.dist.reduce_async(self.encoder.store.grad)
+            self.dist.wait()
         scale = 1.0
         if self.clip > 0:                                                   # tf.clip_by_global_norm (img2seq.py:116-121)
             gn = float(torch.sqrt(self.encoder.store.grad.pow(2).sum() + self.decoder.store.grad.pow(2).sum()))

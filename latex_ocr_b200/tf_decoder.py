@@ -212,7 +212,7 @@ class Decoder(nn.Module):
             assert ws[name].shape == (T, B, width)
             setattr(a, name, ws[name].data_ptr())
 
-    def run_forward(self, enc, formula, lengths=None, keep_h=None, keep_o=None):
+    def run_forward(self, enc, formula, lengths=None, keep_h=None, keep_o=None, n_words=None):
         """enc [N,R,C] or [N,H,W,C]; formula int64 [N,T]; lengths [N] (incl. END) enables the loss.  Returns the workspace dict
         (``logits`` [T,N,ldl] time-major, ``alphas`` [N,T,R], ``loss``)."""
         enc = self._enc(enc)
@@ -226,7 +226,8 @@ class Decoder(nn.Module):
         if with_loss:
             lens = torch.as_tensor(lengths, dtype=torch.int32)
             ws["lengths"].copy_(lens)
-            a.inv_n_words = 1.0 / float(int(lens.sum()))
+            # data parallel: n_words = token count of the GLOBAL batch, so that summing rank gradients gives the global mean
+            a.inv_n_words = 1.0 / float(n_words if n_words is not None else int(lens.sum()))
         self._keep(a, ws, keep_h, keep_o, T, B)
         check(L.lo_tfdec_forward(ctypes.byref(a), 1 if with_loss else 0, stream_ptr()))
         return ws
@@ -240,11 +241,11 @@ class Decoder(nn.Module):
             ws = self.run_forward(enc, formula, None, keep_h, keep_o)
             return ws["logits"][:, :, :self.V].permute(1, 0, 2).contiguous()
 
-    def loss_and_backward(self, enc, formula, lengths, keep_h=None, keep_o=None):
+    def loss_and_backward(self, enc, formula, lengths, keep_h=None, keep_o=None, n_words=None):
         """Returns (loss tensor [4] on the device: mean CE, mean CE, 0, n_words; d loss / d enc [N,R,C] fp32).  Parameter
         gradients land in ``self.store.grad`` (the ``.grad`` of every parameter)."""
         with torch.no_grad():
-            ws = self.run_forward(enc, formula, lengths, keep_h, keep_o)
+            ws = self.run_forward(enc, formula, lengths, keep_h, keep_o, n_words)
             denc = self.run_backward(ws)
             return ws["loss"], denc
 

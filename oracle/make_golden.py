@@ -89,13 +89,35 @@ def run_case(name, c):
           "bytes", os.path.getsize(os.path.join(OUT, name + ".pt")))
 
 
+def run_cnn_variant():
+    """Encoder-only fixture for encoder_cnn='cnn' (seq2seq_torch.py:58-86): output and the gradients of sum(out * G)."""
+    c = dict(B=2, H=32, W=80, V=20, pseed=15, dseed=25, gseed=35)
+    pe, _ = rm.init_params(c["V"], seed=c["pseed"], encoder_cnn="cnn")
+    enc, _ = ref_shim.build_reference_models(c["V"], encoder_cnn="cnn")
+    enc.load_state_dict(pe)
+    img, _ = rm.synthetic_batch(c["B"], c["H"], c["W"], c["V"], 3, 4, seed=c["dseed"])
+    out = enc(img)
+    G = torch.randn(out.shape, generator=torch.Generator().manual_seed(c["gseed"]))
+    (out * G).sum().backward()
+    rec = dict(case=c, torch=torch.__version__, enc_out=out.detach().clone(),
+               grad_enc=summarize({k: v.grad for k, v in enc.named_parameters()}))
+    assert (rm.encoder_forward(pe, img, encoder_cnn="cnn") - out).abs().max().item() == 0.0
+    torch.save(rec, os.path.join(OUT, "cnn_variant.pt"))
+    print("cnn_variant", tuple(out.shape), "bytes", os.path.getsize(os.path.join(OUT, "cnn_variant.pt")))
+
+
 def main():
     if not ref_shim.reference_available():
         sys.exit("reference tree not available; golden files can only be regenerated in the build container")
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         run_case(name, c)
+    if not only or "cnn_variant" in only:
+        run_cnn_variant()
 
 
 if __name__ == "__main__":

@@ -57,12 +57,25 @@ def timing_signal_nd(channels, height, width, dtype=torch.float32,
     return table.to(dtype)
 
 
-def encoder_forward(p, img, positional=True, keep=None):
-    """EncoderCNN.forward, 'vanilla' stack: seq2seq_torch.py:31-57, 88-100.
+# 'cnn' variant (seq2seq_torch.py:58-86): no asymmetric pools, Conv2d(512,512,(2,4),stride 2,padding 1)+ReLU instead
+CNN_LAYERS = (
+    ("cnn.0", 1, (2, 2)),
+    ("cnn.3", 1, (2, 2)),
+    ("cnn.6", 1, None),
+    ("cnn.8", 1, None),
+    ("cnn.10", 1, None),
+    ("cnn.12", 1, None),      # kernel (2,4), stride 2
+    ("cnn.14", 0, None),
+)
+
+
+def encoder_forward(p, img, positional=True, keep=None, encoder_cnn="vanilla"):
+    """EncoderCNN.forward: 'vanilla' stack seq2seq_torch.py:31-57, 'cnn' stack :58-86, forward :88-100.
     img [N,1,H,W] raw 0..255 floats (img2seq_torch.py:115-117) -> [N,H',W',512]."""
     x = img
-    for name, pad, pool in VANILLA_LAYERS:
-        x = F.relu(F.conv2d(x, p[name + ".weight"], p[name + ".bias"], stride=1, padding=pad))
+    for name, pad, pool in (VANILLA_LAYERS if encoder_cnn == "vanilla" else CNN_LAYERS):
+        stride = 2 if (encoder_cnn == "cnn" and name == "cnn.12") else 1
+        x = F.relu(F.conv2d(x, p[name + ".weight"], p[name + ".bias"], stride=stride, padding=pad))
         if keep is not None:
             keep[name] = x
         if pool is not None:
@@ -351,7 +364,7 @@ def synthetic_batch(B, H, W, V, tmin, tmax, seed=1234, id_pad=None, id_end=None)
 
 
 def init_params(V, seed=0, attention_dim=512, embed_dim=512, decoder_dim=512, encoder_dim=512,
-                dtype=torch.float32):
+                dtype=torch.float32, encoder_cnn="vanilla"):
     """Random-init parameter dicts with the reference's shapes and init rules
     (nn.Conv2d/nn.Linear/nn.LSTMCell defaults; init_weights seq2seq_torch.py:230-236)."""
     gen = torch.Generator().manual_seed(seed)
@@ -361,9 +374,13 @@ def init_params(V, seed=0, attention_dim=512, embed_dim=512, decoder_dim=512, en
 
     pe = {}
     cin = 1
-    for name, cout in (("cnn.0", 64), ("cnn.3", 128), ("cnn.6", 256), ("cnn.8", 256), ("cnn.11", 512), ("cnn.14", 512)):
-        b = 1.0 / math.sqrt(cin * 9)
-        pe[name + ".weight"] = U((cout, cin, 3, 3), b)
+    convs = ((("cnn.0", 64, (3, 3)), ("cnn.3", 128, (3, 3)), ("cnn.6", 256, (3, 3)), ("cnn.8", 256, (3, 3)), ("cnn.11", 512, (3, 3)),
+              ("cnn.14", 512, (3, 3))) if encoder_cnn == "vanilla" else
+             (("cnn.0", 64, (3, 3)), ("cnn.3", 128, (3, 3)), ("cnn.6", 256, (3, 3)), ("cnn.8", 256, (3, 3)), ("cnn.10", 512, (3, 3)),
+              ("cnn.12", 512, (2, 4)), ("cnn.14", 512, (3, 3))))
+    for name, cout, (kh, kw) in convs:
+        b = 1.0 / math.sqrt(cin * kh * kw)
+        pe[name + ".weight"] = U((cout, cin, kh, kw), b)
         pe[name + ".bias"] = U((cout,), b)
         cin = cout
     pd = {}

@@ -232,3 +232,31 @@ def test_uint8_image_upload_equals_float_path():
     assert a == b
     g1, g2 = m1.encoder.store.grad, m2.encoder.store.grad          # (wgrad split-K atomics: equal up to summation order)
     assert (g1 - g2).abs().max().item() <= 1e-5 * g1.abs().max().item()
+
+
+def test_cnn_variant_encoder_vs_golden():
+    """encoder_cnn='cnn' (seq2seq_torch.py:58-86: Conv2d(512,512,(2,4),stride 2,padding 1) instead of the two asymmetric pools):
+    output and the gradients of sum(out * G) against the reference's own run (tests/golden/cnn_variant.pt); fp32 tight, and the
+    bf16/tcgen05 path (im2col + tensor-core GEMMs) against the fp32 one."""
+    from latex_ocr_b200.encoder import EncoderCNN
+    from util import Cfg
+    rm = _oracle()
+    rec = load_golden("cnn_variant")
+    c = rec["case"]
+    pe, _ = rm.init_params(c["V"], seed=c["pseed"], encoder_cnn="cnn")
+    img, _ = rm.synthetic_batch(c["B"], c["H"], c["W"], c["V"], 3, 4, seed=c["dseed"])
+    G = torch.randn(rec["enc_out"].shape, generator=torch.Generator().manual_seed(c["gseed"]))
+    grads = {}
+    for precision, impl, tol in (("fp32", "simt", 1e-4), ("bf16", "tc", 3e-2)):
+        enc = EncoderCNN(Cfg(encoder_cnn="cnn"), device="cuda", precision=precision, impl=impl)
+        assert set(enc.state_dict()) == set(pe)
+        enc.load_state_dict(pe)
+        out = enc.forward_raw(img.cuda(), need_grad=True).float()
+        assert out.shape == rec["enc_out"].shape
+        assert relerr(out, rec["enc_out"]) < tol
+        enc.backward_raw(tuple(img.shape), G.cuda().contiguous())
+        torch.cuda.synchronize()
+        grads[precision] = {k: p.grad.detach().float().cpu().clone() for k, p in enc.named_parameters()}
+    for k, g in grads["fp32"].items():
+        _check_summary(k, g, rec["grad_enc"][k], 1e-3)
+        assert relerr(grads["bf16"][k], g) < 6e-2, k
