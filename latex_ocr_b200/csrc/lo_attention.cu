@@ -400,11 +400,30 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     const float* alb = alpha + (int64_t)b * alpha_stride;
     float* deb = de + (int64_t)b * alpha_stride;
     const float* drb = dreg + (int64_t)b * dreg_stride;
+    // per-row scalars (alpha, d reg) are fetched one stage ahead: a dependent global load after the warp reduction would sit on
+    // the critical path of every stage
+    float pa0 = 0.f, pa1 = 0.f, pd0 = 0.f, pd1 = 0.f;
+    auto prefetch = [&](int i) {
+      const int row = r0 + i * C::ROWS;
+      const int rows = min(C::ROWS, r1 - row);
+      const int ra = wid, rb = wid + AP_CWARPS;
+      if (i < nst && ra < rows) {
+        pa0 = alb[row + ra];
+        pd0 = dreg ? drb[row + ra] : 0.f;
+        if (C::RPW == 2 && rb < rows) {
+          pa1 = alb[row + rb];
+          pd1 = dreg ? drb[row + rb] : 0.f;
+        }
+      }
+    };
+    prefetch(0);
     for (int i = 0; i < nst; i++) {
       const int s = i % AP_STAGES;
       const uint32_t ph = (i / AP_STAGES) & 1;
       const int row = r0 + i * C::ROWS;
       const int rows = min(C::ROWS, r1 - row);
+      const float al0 = pa0, al1 = pa1, dr0 = pd0, dr1 = pd1;
+      prefetch(i + 1);
       mbar_wait(full_bar + s, ph);
       const T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
       const T* se = sa + C::HALF_ELEMS;
@@ -427,8 +446,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
         }
         d0 = warp_sum(d0);
         d1 = warp_sum(d1);
-        const float de0 = alb[row + ra] * (d0 + (dreg ? drb[row + ra] : 0.f) - sall);
-        const float de1 = two ? alb[row + rb] * (d1 + (dreg ? drb[row + rb] : 0.f) - sall) : 0.f;
+        const float de0 = al0 * (d0 + dr0 - sall);
+        const float de1 = two ? al1 * (d1 + dr1 - sall) : 0.f;
         if (lane == 0) {
           deb[row + ra] = de0;
           if (two) deb[row + rb] = de1;

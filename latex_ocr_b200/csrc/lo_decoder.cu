@@ -965,6 +965,8 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
                 a->call + ((int64_t)(t + 1) * d.B + r0) * d.D, a->hall + ((int64_t)(t + 1) * d.B + r0) * d.D,
                 bv.hall + ((int64_t)(t + 1) * d.B + r0) * d.D, hd_t ? hd_t + r0 * hd_stride : (float*)nullptr, hd_stride,
                 dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, d.D, d.V};
+    if (g_opt_skinny_mma && nrows <= 64 && d.C <= 512)
+      return skinny_gemm_nt_lstm(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, bv.wil, d.C, nrows, d.D, d.C, e, st);
     return tc_gemm_nt_lstm(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, bv.wil, d.C, nrows, d.D, d.C, e, st);
   }
   if (bv.on && g_opt_skinny_mma && nrows <= 64) {
