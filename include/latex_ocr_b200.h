@@ -40,6 +40,10 @@ int64_t lo_launch_count(void);
 /* tuning knobs: "att_pipe" (1: TMA-pipelined attention kernels, 0: register-streaming), "att_policy_enc" /
  * "att_policy_att1" (L2 policy 0 normal, 1 evict_last, 2 evict_first), "att_nsplit" (0 = automatic) */
 int lo_set_option(const char* name, int value);
+/* L2 persistence: access-policy window of `stream` over [base, base+bytes) (hits persist, misses stream) with the
+ * persisting carve-out sized to fit; bytes = 0 resets.  The attention kernels honour it with att_policy_enc/att1 = 3
+ * (bulk copies without an explicit cache hint). */
+int lo_set_l2_window(const void* base, int64_t bytes, float hit_ratio, void* stream);
 /* development aid: device buffer (>= 16 int64) that CTA (0,0,0) of the tcgen05 NT GEMM stamps with clock64 at its
  * pipeline milestones; NULL disables */
 int lo_debug_buffer(void* p);

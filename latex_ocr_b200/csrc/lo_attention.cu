@@ -118,8 +118,10 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
         const uint32_t bytes = (uint32_t)rows * CH * (uint32_t)sizeof(T);
         T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
         mbar_expect_tx(full_bar + s, 2 * bytes);
-        bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
-        bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
+        if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CH, bytes, full_bar + s);
+        else bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
+        if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s);
+        else bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
       }
     }
     __syncwarp();
@@ -366,8 +368,10 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
         const uint32_t bytes = (uint32_t)rows * CH * (uint32_t)sizeof(T);
         T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
         mbar_expect_tx(full_bar + s, 2 * bytes);
-        bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
-        bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
+        if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CH, bytes, full_bar + s);
+        else bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
+        if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s);
+        else bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
       }
     }
     __syncwarp();
@@ -683,6 +687,32 @@ int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st) {
 
 namespace lo { extern long long* g_tc_dbg; }
 extern "C" int lo_debug_buffer(void* p) { lo::g_tc_dbg = (long long*)p; return LO_OK; }
+
+// L2 persistence experiment: access-policy window of `stream` over [base, base+bytes) (hit -> persisting, miss -> streaming) and
+// the persisting carve-out sized to fit; bytes = 0 resets both.  Attention loads honour it with att_policy_* = 3 (no cache hint).
+extern "C" int lo_set_l2_window(const void* base, int64_t bytes, float hit_ratio, void* stream) {
+  int dev = 0, max_persist = 0, max_window = 0;
+  LO_CUDA(cudaGetDevice(&dev));
+  LO_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  LO_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  cudaStreamAttrValue v{};
+  if (bytes <= 0 || !base) {
+    v.accessPolicyWindow.num_bytes = 0;
+    LO_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v));
+    LO_CUDA(cudaCtxResetPersistingL2Cache());
+    return LO_OK;
+  }
+  const size_t carve = (size_t)(bytes < max_persist ? bytes : max_persist);
+  LO_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+  v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+  v.accessPolicyWindow.num_bytes = (size_t)(bytes < max_window ? bytes : max_window);
+  v.accessPolicyWindow.hitRatio = hit_ratio;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  LO_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v));
+  lo::fail(LO_OK, "l2 window%s: carve %ld B (device max %ld B)", "", (long)carve, (long)max_persist);      // readable via lo_last_error()
+  return LO_OK;
+}
 
 extern "C" int lo_set_option(const char* name, int value) {
   if (!name) return LO_EINVAL;
