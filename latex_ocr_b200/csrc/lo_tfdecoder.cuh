@@ -444,19 +444,19 @@ int lo_tfdec_backward(const lo_tfdec_args* a, void* stream) {
   const size_t es = dt == LO_F32 ? 4 : 2;
   const int TB = d.T * d.B;
   const dim3 tb(32, 8);
-  // transposed shadows for the backward GEMMs (dX = dY W needs W as [in][out] = the TF layout)
-  LO_DISPATCH_DT(dt, T, {
-    const T* wc2 = (const T*)a->w_cat2;
-    transpose_kernel<T><<<dim3(cdiv(d.D, 32), cdiv(d.O, 32)), tb, 0, st>>>(wc2 + (int64_t)d.A * d.D, d.D, (T*)w.wb4, d.O, d.O, d.D);
-    transpose_kernel<T><<<dim3(cdiv(d.C, 32), cdiv(d.O, 32)), tb, 0, st>>>((const T*)a->w_oc, d.C, (T*)w.wb4 + (int64_t)d.D * d.O, d.O, d.O,
-                                                                            d.C);
-    transpose_kernel<T><<<dim3(cdiv(d.D, 32), cdiv(d.A, 32)), tb, 0, st>>>(wc2, d.D, (T*)w.wb5, d.A, d.A, d.D);
-    transpose_kernel<T><<<dim3(cdiv(d.XH, 32), cdiv(d.G, 32)), tb, 0, st>>>((const T*)a->w_lstm + d.E, d.LW, (T*)w.wb6, d.G, d.G, d.XH);
-    transpose_kernel<T><<<dim3(cdiv(d.O, 32), cdiv(d.V, 32)), tb, 0, st>>>((const T*)a->w_y, d.O, (T*)w.wbY, d.Vl, d.V, d.O);
-    transpose_kernel<T><<<dim3(cdiv(d.C, 32), cdiv(d.A, 32)), tb, 0, st>>>((const T*)a->w_img, d.C, (T*)w.wimgT, d.A, d.A, d.C);
-  });
-  LO_LAUNCH_OK();
-  g_launches += 5;
+  // transposed shadows for the backward GEMMs (dX = dY W needs W as [in][out] = the TF layout); out[n][k] = in[k][n]
+  auto transpose = [&](const void* in, int64_t off_in, int64_t ld_in, void* out, int64_t off_out, int64_t ld_out, int K, int N) -> int {
+    LO_DISPATCH_DT(dt, T, (transpose_kernel<T><<<dim3(cdiv(N, 32), cdiv(K, 32)), tb, 0, st>>>((const T*)in + off_in, ld_in, (T*)out + off_out,
+                                                                                                ld_out, K, N)));
+    LO_LAUNCH_OK();
+    return LO_OK;
+  };
+  LO_TRY(transpose(a->w_cat2, (int64_t)d.A * d.D, d.D, w.wb4, 0, d.O, d.O, d.D));             // o_W_h^T [O][D] -> [D][O]
+  LO_TRY(transpose(a->w_oc, 0, d.C, w.wb4, (int64_t)d.D * d.O, d.O, d.O, d.C));               // o_W_c^T [O][C] -> [C][O]
+  LO_TRY(transpose(a->w_cat2, 0, d.D, w.wb5, 0, d.A, d.A, d.D));                              // att_h^T [A][D] -> [D][A]
+  LO_TRY(transpose(a->w_lstm, d.E, d.LW, w.wb6, 0, d.G, d.G, d.XH));                          // K[E:]^T [4D][O+D] -> [O+D][4D]
+  LO_TRY(transpose(a->w_y, 0, d.O, w.wbY, 0, d.Vl, d.V, d.O));                                // y_W_o^T [V][O] -> [O][Vl]
+  LO_TRY(transpose(a->w_img, 0, d.C, w.wimgT, 0, d.A, d.A, d.C));                             // W_img^T [A][C] -> [C][A]
   // d o (logit path) for every step at once: dlogits @ y_W_o^T
   LO_TRY(tf_nt(a, w.dlogits, w.dlogits_bf, d.Vl, w.wbY, d.Vl, w.dologit, d.O, TB, d.O, d.Vl, nullptr, 0, st));
   LO_CUDA(cudaMemsetAsync(w.dxh, 0, (size_t)d.B * d.XH * 4, st));
