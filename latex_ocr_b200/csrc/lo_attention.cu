@@ -569,6 +569,10 @@ int att_pipe_splits(int B, int hint = 0) {
   return s;
 }
 
+// optional L2 access-policy window attached to every attention launch (lo_set_l2_window): as a LAUNCH attribute it is also
+// recorded in CUDA-graph kernel nodes, which a stream attribute is not
+static cudaAccessPolicyWindow g_att_window{};
+
 // launch with (optional) cluster dimension {ns,1,1} and the PDL attribute
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_att(void (*kernel)(KArgs...), dim3 grid, size_t smem, int cluster_x, cudaStream_t st, Args... args) {
@@ -577,8 +581,13 @@ static cudaError_t launch_att(void (*kernel)(KArgs...), dim3 grid, size_t smem, 
   cfg.blockDim = dim3(AP_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  if (g_att_window.num_bytes) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow = g_att_window;
+    n++;
+  }
   if (g_opt_pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
@@ -698,6 +707,7 @@ extern "C" int lo_set_l2_window(const void* base, int64_t bytes, float hit_ratio
   cudaStreamAttrValue v{};
   if (bytes <= 0 || !base) {
     v.accessPolicyWindow.num_bytes = 0;
+    lo::g_att_window = v.accessPolicyWindow;
     LO_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v));
     LO_CUDA(cudaCtxResetPersistingL2Cache());
     return LO_OK;
@@ -709,6 +719,7 @@ extern "C" int lo_set_l2_window(const void* base, int64_t bytes, float hit_ratio
   v.accessPolicyWindow.hitRatio = hit_ratio;
   v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  lo::g_att_window = v.accessPolicyWindow;
   LO_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v));
   lo::fail(LO_OK, "l2 window%s: carve %ld B (device max %ld B)", "", (long)carve, (long)max_persist);      // readable via lo_last_error()
   return LO_OK;
