@@ -109,8 +109,8 @@ def kernel_probes(model, c, pk):
             "ms": ms_conv, "algorithmic_flops": flops, "peak_source": pk["src"] + " (sustained cuBLAS bf16)"}
     conv["frac"] = conv["achieved"] / conv["peak"]
 
-    # the tcgen05 kernels alone (layers 2-6: forward, data gradient, weight gradient + bias-gradient column sums) — what SURVEY §8-d
-    # calls the tensor-pipe figure (conv1 / pools / masks are memory-bound CUDA-core kernels and are excluded here)
+    # the tcgen05 kernels alone (layers 2-6: forward, data gradient, weight gradient) — what SURVEY §8-d calls the tensor-pipe
+    # figure (conv1 / pools / masks / bias-gradient column sums are memory-bound CUDA-core kernels and are excluded here)
     from latex_ocr_b200.encoder import _LAYERS
     Aa, Gg, S = enc_ws["acts"], enc_ws["grads"], enc.store
     impl = enc._impl()
@@ -126,7 +126,8 @@ def kernel_probes(model, c, pk):
         for idx, xin in plan:
             _, cin, cout, pad, pool = cfgl[idx]
             x, dy = Aa[xin], Gg["Y" + idx]
-            _lib.check(L.lo_conv3x3_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(S.g("cnn.%s.weight" % idx)), _lib.ptr(S.g("cnn.%s.bias" % idx)),
+            # db = NULL: the bias-gradient column sums are memory-bound CUDA-core kernels, not part of the tensor-pipe figure
+            _lib.check(L.lo_conv3x3_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(S.g("cnn.%s.weight" % idx)), None,
                                           dt, B, x.shape[1], x.shape[2], cin, cout, pad, impl, st))
             mask = Aa[xin] if xin.startswith("Y") else None
             _lib.check(L.lo_conv3x3(_lib.ptr(dy), _lib.ptr(enc_ws["wflip"][idx]), None, _lib.ptr(mask), _lib.ptr(Gg[xin]), dt, B, dy.shape[1],

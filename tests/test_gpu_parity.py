@@ -257,8 +257,15 @@ def test_cnn_variant_encoder_vs_golden():
         enc.backward_raw(tuple(img.shape), G.cuda().contiguous())
         torch.cuda.synchronize()
         grads[precision] = {k: p.grad.detach().float().cpu().clone() for k, p in enc.named_parameters()}
-    # 5e-3: the random upstream gradient G makes single ReLU / pool-argmax flips (fp32 summation order) visible in conv1's sums
+    # the random upstream gradient G makes single ReLU / pool-argmax flips (fp32 summation order) visible in the sums: big tensors
+    # through their summaries at 5e-3, small ones (biases) norm-wise at 1e-2
     for k, g in grads["fp32"].items():
-        _check_summary(k, g, rec["grad_enc"][k], 5e-3)
+        want = rec["grad_enc"][k]
+        if isinstance(want, dict):
+            _check_summary(k, g, want, 5e-3)
+        else:
+            err = ((g.double() - want.double()).norm() / want.double().norm()).item()
+            print("cnn variant fp32", k, "rel. norm error %.2e" % err)
+            assert err < 1e-2, (k, err)
         b = grads["bf16"][k]
         assert ((b - g).norm() / g.norm()).item() < 0.15, k      # bf16 storage through 7 layers + mask flips: norm-wise 15 %
