@@ -1355,11 +1355,16 @@ int lo_decoder_greedy_hist(const lo_decoder_args* a, int64_t start_id, int64_t e
   LO_LAUNCH_OK();
   LO_CUDA(cudaMemsetAsync(finished, 0, (size_t)d.B * 4, st));
   LO_TRY(forward_prologue(a, d, st));
+  const BfViews bvg = bf_views(a, d);
   for (int t = 0; t < max_steps; t++) {
     LO_TRY(forward_step(a, d, t, Rows{0, d.B, a->work, 0}, next_tok, 1, nullptr, 0, nullptr, st));
     // logits_t = fc(h_t)   (no dropout at decode time)
-    LO_TRY(gemm_nt(a->hall + (int64_t)(t + 1) * d.B * d.D, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D,
-                   a->b_fc, 0, 0, LO_IMPL_SIMT, st));
+    if (bvg.on)      // bf16 mirror of h_t: mma.sync kernel for <= 64 rows (the dispatcher falls back to CUDA cores otherwise)
+      LO_TRY(gemm_nt(bvg.hall + (int64_t)(t + 1) * d.B * d.D, LO_BF16, d.D, a->w_fc, LO_BF16, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D,
+                     a->b_fc, 0, 0, LO_IMPL_TC, st));
+    else
+      LO_TRY(gemm_nt(a->hall + (int64_t)(t + 1) * d.B * d.D, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D,
+                     a->b_fc, 0, 0, LO_IMPL_SIMT, st));
     argmax_kernel<<<cdiv(d.B, 8), 256, 0, st>>>(a->logits, d.V, tokens + t, max_steps, next_tok, finished, end_id, d.B);
     LO_LAUNCH_OK();
     if (fin_hist) {
