@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/dp_check.py : N-rank data-parallel step == single-process step on the global batch.
+"""torchrun --nproc-per-node N tests/manual/dp_check.py : N-rank data-parallel step == single-process step on the global batch.
 Each rank takes its shard of a global batch; gradients are all-reduced (NCCL) bucket by bucket; rank 0 also runs the
 global batch alone (no dist) and compares the post-Adam parameters and the pre-Adam (averaged) gradients."""
 import os
@@ -7,7 +7,7 @@ import sys
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from util import build_model  # noqa: E402
