@@ -87,3 +87,52 @@ def test_timing_signal_table_matches_oracle():
     from oracle import ref_model as rm
     t = timing_signal_table(512, 6, 30, "cpu")
     assert torch.equal(t, rm.timing_signal_nd(512, 6, 30).permute(1, 2, 0).contiguous())
+
+
+def test_tf_decoder_variable_layout_and_adjacency():
+    """TF-flavour Decoder (host side only): variables carry the TF names and shapes, load_tf_variables round-trips the oracle's
+    dict, and the flat store keeps the blocks adjacent that the kernels address as one matrix (lo_tfdec_args comments)."""
+    from latex_ocr_b200.tf_decoder import Decoder
+    from oracle import ref_tf_model as tfm
+    from util import Cfg
+    V = 37
+    cfg = Cfg(attn_cell_config={"num_units": 512, "dim_e": 256, "dim_o": 512, "dim_embeddings": 80}, decoding="beam_search", beam_size=3)
+    dec = Decoder(cfg, V, V - 1, device="cpu", precision="bf16")
+    p = tfm.init_params_tf(V, seed=4)
+    sd = dec.state_dict()
+    assert set(sd) == set(p)
+    for k, v in p.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    dec.load_tf_variables(p)
+    for k, v in p.items():
+        assert torch.equal(dec.state_dict()[k], v), k
+    S = dec.store
+    off = {k: S.offsets[k][0] for k in S.offsets}
+    n = {k: S.offsets[k][1] for k in S.offsets}
+    for a, b in (("att_h.kernel", "o_W_h"), ("W_c_0", "W_h_0"), ("W_h_0", "W_o_0"), ("b_c_0", "b_h_0"), ("b_h_0", "b_o_0"),
+                 ("embedding_table", "start_token")):
+        assert off[a] + n[a] == off[b], (a, b)
+    # storage is [out][in]: the TF-shaped parameter is a transposed view of it
+    assert torch.equal(S.f32("lstm.kernel").t(), p["lstm.kernel"])
+    assert dec._tiles == 3 and dec.max_length_formula == 150
+    with pytest.raises(_lib.LatexOcrB200Error):
+        dec.decode(torch.zeros(1, 4, 512))                      # CPU tensor: refused, no fallback
+
+
+def test_encoder_variants_state_dict_surface():
+    """'vanilla' and 'cnn' stacks (seq2seq_torch.py:31-86) expose the reference's state_dict keys and OIHW shapes."""
+    from latex_ocr_b200.encoder import EncoderCNN
+    from oracle import ref_model as rm
+    from util import Cfg
+    for variant in ("vanilla", "cnn"):
+        pe, _ = rm.init_params(10, seed=1, encoder_cnn=variant)
+        enc = EncoderCNN(Cfg(encoder_cnn=variant), device="cpu", precision="fp32")
+        sd = enc.state_dict()
+        assert set(sd) == set(pe)
+        for k, v in pe.items():
+            assert tuple(sd[k].shape) == tuple(v.shape), (variant, k)
+        enc.load_state_dict(pe)
+        assert all(torch.equal(enc.state_dict()[k], v) for k, v in pe.items())
+    assert EncoderCNN(Cfg(encoder_cnn="cnn"), device="cpu", precision="fp32").out_hw(128, 512) == (15, 62)
+    with pytest.raises(NotImplementedError):
+        EncoderCNN(Cfg(encoder_cnn="resnet"), device="cpu")
