@@ -250,8 +250,8 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
  *              o_t = tanh(h_t o_W_h + ctx o_W_c) ; logits_t = o_t y_W_o
  * Parameter storage is [out][in] (K-major for the forward GEMMs; the Python side exposes TF-shaped
  * [in][out] views of the same memory).  Shapes: B rows, T steps (buffer capacity), R regions, C channels,
- * A=dim_e (A <= C; att_img is stored zero-padded to C columns so that the attention kernels of the torch
- * flavour serve both), D=num_units, O=dim_o, E=dim_embeddings, V=vocab.
+ * A=dim_e ((A, C) equal or (256, 512): the instantiated widths of the attention kernels), D=num_units, O=dim_o,
+ * E=dim_embeddings, V=vocab.
  */
 typedef struct lo_tfdec_args {
   int32_t B, T, R, C, A, D, O, E, V;

@@ -48,24 +48,29 @@ __device__ __forceinline__ float att_dact(float pre, float post) {
   else return 1.f - post * post;
 }
 
-template <typename T, int NV>
+// NVA / NVC: 256-element groups per att1 row / per enc row (the torch flavour has A = C; the Genthial cell dim_e = 256 < C = 512)
+template <typename T, int NVA, int NVC>
 struct ApCfg {
-  static constexpr int CH = NV * 256;
-  static constexpr int RPW = (sizeof(T) == 2 && NV <= 2) ? 2 : 1;       // rows per consumer warp per stage
+  static constexpr int CHA = NVA * 256;
+  static constexpr int CHC = NVC * 256;
+  static constexpr int NVM = NVA > NVC ? NVA : NVC;
+  static constexpr int RPW = (sizeof(T) == 2 && NVM <= 2) ? 2 : 1;      // rows per consumer warp per stage
   static constexpr int ROWS = AP_CWARPS * RPW;
-  static constexpr int HALF_ELEMS = ROWS * CH;                          // att1 part | enc part
-  static constexpr int STAGE_BYTES = 2 * HALF_ELEMS * (int)sizeof(T);
+  static constexpr int HALF_A = ROWS * CHA;                             // att1 part
+  static constexpr int HALF_C = ROWS * CHC;                             // enc part
+  static constexpr int STAGE_ELEMS = HALF_A + HALF_C;
+  static constexpr int STAGE_BYTES = STAGE_ELEMS * (int)sizeof(T);
   static constexpr int SMEM = AP_STAGES * STAGE_BYTES + 128;
 };
 
-template <typename T, int NV, bool CL, int ACT>
+template <typename T, int NVA, int NVC, bool CL, int ACT>
 __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
     float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
     int* __restrict__ counters, float* __restrict__ partials, int pol_enc, int pol_att1, int rpi) {
-  using C = ApCfg<T, NV>;
-  constexpr int CH = C::CH;
+  using C = ApCfg<T, NVA, NVC>;
+  constexpr int CHA = C::CHA, CHC = C::CHC;
   extern __shared__ __align__(128) uint8_t ap_smem[];
   T* ring = reinterpret_cast<T*>(ap_smem);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + AP_STAGES * C::STAGE_BYTES);
@@ -81,8 +86,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   const int rps = (R + nsplit - 1) / nsplit;
   const int r0 = sp * rps, r1 = min(R, r0 + rps);
   const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
-  const T* a1b = att1 + (int64_t)(b / rpi) * R * CH;      // beam search: rpi consecutive rows attend over one image
-  const T* eb = enc + (int64_t)(b / rpi) * R * CH;
+  const T* a1b = att1 + (int64_t)(b / rpi) * R * CHA;      // beam search: rpi consecutive rows attend over one image
+  const T* eb = enc + (int64_t)(b / rpi) * R * CHC;
   float* alb = alpha + (int64_t)b * alpha_stride;
 
   if (threadIdx.x == 0) {
@@ -101,9 +106,9 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   }
 
   float m = -INFINITY, l = 0.f;
-  float acc[NV * 8];
+  float acc[NVC * 8];
 #pragma unroll
-  for (int i = 0; i < NV * 8; i++) acc[i] = 0.f;
+  for (int i = 0; i < NVC * 8; i++) acc[i] = 0.f;
 
   if (wid == AP_CWARPS) {
     // ===== producer warp: one lane issues the bulk copies =====
@@ -115,22 +120,22 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
         mbar_wait(empty_bar + s, ph ^ 1);
         const int row = r0 + i * C::ROWS;
         const int rows = min(C::ROWS, r1 - row);
-        const uint32_t bytes = (uint32_t)rows * CH * (uint32_t)sizeof(T);
-        T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
-        mbar_expect_tx(full_bar + s, 2 * bytes);
-        if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CH, bytes, full_bar + s);
-        else bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
-        if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s);
-        else bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
+        const uint32_t bytes_a = (uint32_t)rows * CHA * (uint32_t)sizeof(T), bytes_c = (uint32_t)rows * CHC * (uint32_t)sizeof(T);
+        T* sa = ring + (size_t)s * C::STAGE_ELEMS;
+        mbar_expect_tx(full_bar + s, bytes_a + bytes_c);
+        if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s);
+        else bulk_g2s(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s, pa);
+        if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_A, eb + (int64_t)row * CHC, bytes_c, full_bar + s);
+        else bulk_g2s(sa + C::HALF_A, eb + (int64_t)row * CHC, bytes_c, full_bar + s, pe);
       }
     }
     __syncwarp();
     pdl_wait();          // the producer warp joins the combine below, which reads the preceding kernel's results
   } else {
     // ===== consumer warps =====
-    float a2[NV * 8], wv[NV * 8];
+    float a2[NVA * 8], wv[NVA * 8];
 #pragma unroll
-    for (int j = 0; j < NV; j++) {
+    for (int j = 0; j < NVA; j++) {
       ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
       ld8(wf + (j * 32 + lane) * 8, wv + j * 8);
     }
@@ -140,21 +145,21 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
       const int row = r0 + i * C::ROWS;
       const int rows = min(C::ROWS, r1 - row);
       mbar_wait(full_bar + s, ph);
-      const T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
-      const T* se = sa + C::HALF_ELEMS;
+      const T* sa = ring + (size_t)s * C::STAGE_ELEMS;
+      const T* se = sa + C::HALF_A;
       const int ra = wid, rb = wid + AP_CWARPS;
       const bool one = ra < rows;
       const bool two = (C::RPW == 2) && (rb < rows);
       if (one) {
         float e0 = 0.f, e1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < NV; j++) {
+        for (int j = 0; j < NVA; j++) {
           float v[8];
-          ld8(sa + (size_t)ra * CH + (j * 32 + lane) * 8, v);
+          ld8(sa + (size_t)ra * CHA + (j * 32 + lane) * 8, v);
 #pragma unroll
           for (int q = 0; q < 8; q++) e0 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(v[q] + a2[j * 8 + q]), e0);
           if (two) {
-            ld8(sa + (size_t)rb * CH + (j * 32 + lane) * 8, v);
+            ld8(sa + (size_t)rb * CHA + (j * 32 + lane) * 8, v);
 #pragma unroll
             for (int q = 0; q < 8; q++) e1 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(v[q] + a2[j * 8 + q]), e1);
           }
@@ -176,13 +181,13 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
         const float p1 = two ? expf(e1 - mn) : 0.f;
         l = l * sc + p0 + p1;
 #pragma unroll
-        for (int j = 0; j < NV; j++) {
+        for (int j = 0; j < NVC; j++) {
           float u[8];
-          ld8(se + (size_t)ra * CH + (j * 32 + lane) * 8, u);
+          ld8(se + (size_t)ra * CHC + (j * 32 + lane) * 8, u);
 #pragma unroll
           for (int q = 0; q < 8; q++) acc[j * 8 + q] = fmaf(p0, u[q], acc[j * 8 + q] * sc);
           if (two) {
-            ld8(se + (size_t)rb * CH + (j * 32 + lane) * 8, u);
+            ld8(se + (size_t)rb * CHC + (j * 32 + lane) * 8, u);
 #pragma unroll
             for (int q = 0; q < 8; q++) acc[j * 8 + q] = fmaf(p1, u[q], acc[j * 8 + q]);
           }
@@ -194,13 +199,13 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     }
   }
   __syncthreads();     // every TMA write has landed and been consumed: the ring can be reused for the combine
-  float* s_acc = reinterpret_cast<float*>(ap_smem);          // [AP_CWARPS][CH]
+  float* s_acc = reinterpret_cast<float*>(ap_smem);          // [AP_CWARPS][CHC]
   if (wid < AP_CWARPS) {
     if (lane == 0) { s_m[wid] = m; s_l[wid] = l; }
 #pragma unroll
-    for (int j = 0; j < NV; j++)
+    for (int j = 0; j < NVC; j++)
 #pragma unroll
-      for (int i = 0; i < 8; i++) s_acc[wid * CH + (j * 32 + lane) * 8 + i] = acc[j * 8 + i];
+      for (int i = 0; i < 8; i++) s_acc[wid * CHC + (j * 32 + lane) * 8 + i] = acc[j * 8 + i];
   }
   __syncthreads();
   float M = -INFINITY;
@@ -216,12 +221,12 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   if constexpr (CL) {
     // ===== cluster combine: the nsplit CTAs of this batch row exchange (M, L, acc) through distributed shared memory =====
     cg::cluster_group cluster = cg::this_cluster();
-    float* s_part = s_acc + AP_CWARPS * CH;                 // [CH] combined accumulator of this CTA (still inside the ring)
+    float* s_part = s_acc + AP_CWARPS * CHC;                 // [CHC] combined accumulator of this CTA (still inside the ring)
     __shared__ float s_MLp[2];
-    for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    for (int c = threadIdx.x; c < CHC; c += AP_THREADS) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < AP_CWARPS; w++) t = fmaf(s_acc[w * CH + c], wsc[w], t);
+      for (int w = 0; w < AP_CWARPS; w++) t = fmaf(s_acc[w * CHC + c], wsc[w], t);
       s_part[c] = t;
     }
     if (threadIdx.x == 0) { s_MLp[0] = M; s_MLp[1] = L; }
@@ -242,21 +247,21 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     }
     const float invL = 1.0f / Lg;
     // this CTA finalises its slice of the channels ...
-    const int cps = (CH + nsplit - 1) / nsplit;
-    for (int c = sp * cps + threadIdx.x; c < min(CH, (sp + 1) * cps); c += AP_THREADS) {
+    const int cps = (CHC + nsplit - 1) / nsplit;
+    for (int c = sp * cps + threadIdx.x; c < min(CHC, (sp + 1) * cps); c += AP_THREADS) {
       float t = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; q++)
         if (q < nsplit) t = fmaf(cluster.map_shared_rank(s_part, q)[c], scl[q], t);
       t *= invL;
-      ctx[(int64_t)b * CH + c] = t;
+      ctx[(int64_t)b * CHC + c] = t;
       if (gate_pre) {
         const float g = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
         gate_pre[(int64_t)b * gate_stride + c] = g;
-        gctx[(int64_t)b * CH + c] = g * t;
-        if (gctx_bf) gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(g * t);
+        gctx[(int64_t)b * CHC + c] = g * t;
+        if (gctx_bf) gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(g * t);
       } else if (gctx_bf) {
-        gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(t);      // no gate (Genthial cell): bf16 mirror of the context itself
+        gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(t);      // no gate (Genthial cell): bf16 mirror of the context itself
       }
     }
     // ... and normalises the attention weights of its own rows (scores never leave shared memory)
@@ -264,11 +269,11 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     cluster.sync();                                          // peers may still be reading this CTA's shared memory
     return;
   }
-  float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
-  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CHC + 2);
+  for (int c = threadIdx.x; c < CHC; c += AP_THREADS) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < AP_CWARPS; w++) t = fmaf(s_acc[w * CH + c], wsc[w], t);
+    for (int w = 0; w < AP_CWARPS; w++) t = fmaf(s_acc[w * CHC + c], wsc[w], t);
     part[2 + c] = t;
   }
   if (threadIdx.x == 0) { part[0] = M; part[1] = L; }
@@ -282,40 +287,40 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const float* pb = partials + (int64_t)b * nsplit * (CH + 2);
+  const float* pb = partials + (int64_t)b * nsplit * (CHC + 2);
   if (threadIdx.x == 0) {
     float Mg = -INFINITY;
-    for (int s = 0; s < nsplit; s++) Mg = fmaxf(Mg, __ldcg(pb + (int64_t)s * (CH + 2)));
+    for (int s = 0; s < nsplit; s++) Mg = fmaxf(Mg, __ldcg(pb + (int64_t)s * (CHC + 2)));
     float Lg = 0.f;
     for (int s = 0; s < nsplit; s++) {
-      const float ms = __ldcg(pb + (int64_t)s * (CH + 2));
+      const float ms = __ldcg(pb + (int64_t)s * (CHC + 2));
       const float scl = (ms == -INFINITY) ? 0.f : expf(ms - Mg);
       s_scale[s] = scl;
-      Lg += __ldcg(pb + (int64_t)s * (CH + 2) + 1) * scl;
+      Lg += __ldcg(pb + (int64_t)s * (CHC + 2) + 1) * scl;
     }
     s_ML[0] = Mg;
     s_ML[1] = 1.0f / Lg;
   }
   __syncthreads();
   const float Mg = s_ML[0], invL = s_ML[1];
-  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+  for (int c = threadIdx.x; c < CHC; c += AP_THREADS) {
     float t = 0.f;
-    for (int s = 0; s < nsplit; s++) t = fmaf(__ldcg(pb + (int64_t)s * (CH + 2) + 2 + c), s_scale[s], t);
+    for (int s = 0; s < nsplit; s++) t = fmaf(__ldcg(pb + (int64_t)s * (CHC + 2) + 2 + c), s_scale[s], t);
     t *= invL;
-    ctx[(int64_t)b * CH + c] = t;
+    ctx[(int64_t)b * CHC + c] = t;
     if (gate_pre) {
       const float g = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
       gate_pre[(int64_t)b * gate_stride + c] = g;
-      gctx[(int64_t)b * CH + c] = g * t;
-      if (gctx_bf) gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(g * t);
+      gctx[(int64_t)b * CHC + c] = g * t;
+      if (gctx_bf) gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(g * t);
     } else if (gctx_bf) {
-      gctx_bf[(int64_t)b * CH + c] = __float2bfloat16_rn(t);
+      gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(t);
     }
   }
   for (int r = threadIdx.x; r < R; r += AP_THREADS) alb[r] = expf(__ldcg(alb + r) - Mg) * invL;
 }
 
-template <typename T, int NV, bool CL, int ACT>
+template <typename T, int NVA, int NVC, bool CL, int ACT>
 __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, const float* __restrict__ gate,
     int64_t o1_stride, const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride,
@@ -324,8 +329,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     float* __restrict__ dgp, int64_t dcat_stride, bf16* __restrict__ datt2_bf, bf16* __restrict__ dgp_bf,
     float* __restrict__ dctx_out, int R, int nsplit, int* __restrict__ counters, float* __restrict__ partials, int pol_enc,
     int pol_att1, float* __restrict__ dwf_part) {
-  using C = ApCfg<T, NV>;
-  constexpr int CH = C::CH;
+  using C = ApCfg<T, NVA, NVC>;
+  constexpr int CHA = C::CHA, CHC = C::CHC;
   extern __shared__ __align__(128) uint8_t ap_smem[];
   T* ring = reinterpret_cast<T*>(ap_smem);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + AP_STAGES * C::STAGE_BYTES);
@@ -336,8 +341,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
   const int rps = (R + nsplit - 1) / nsplit;
   const int r0 = sp * rps, r1 = min(R, r0 + rps);
   const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
-  const T* a1b = att1 + (int64_t)b * R * CH;
-  const T* eb = enc + (int64_t)b * R * CH;
+  const T* a1b = att1 + (int64_t)b * R * CHA;
+  const T* eb = enc + (int64_t)b * R * CHC;
   if (threadIdx.x == 0) {
     for (int s = 0; s < AP_STAGES; s++) {
       mbar_init(full_bar + s, 1);
@@ -352,9 +357,9 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     pdl_wait();
     pdl_trigger();
   }
-  float macc[NV * 8], wacc[NV * 8];     // wacc: d w_full partial = sum_r de_r * relu(att1_r + att2)   (full_att.weight gradient)
+  float macc[NVA * 8], wacc[NVA * 8];     // wacc: d w_full partial = sum_r de_r * relu(att1_r + att2)   (full_att.weight gradient)
 #pragma unroll
-  for (int i = 0; i < NV * 8; i++) { macc[i] = 0.f; wacc[i] = 0.f; }
+  for (int i = 0; i < NVA * 8; i++) { macc[i] = 0.f; wacc[i] = 0.f; }
 
   if (wid == AP_CWARPS) {
     if (lane == 0) {
@@ -365,27 +370,28 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
         mbar_wait(empty_bar + s, ph ^ 1);
         const int row = r0 + i * C::ROWS;
         const int rows = min(C::ROWS, r1 - row);
-        const uint32_t bytes = (uint32_t)rows * CH * (uint32_t)sizeof(T);
-        T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
-        mbar_expect_tx(full_bar + s, 2 * bytes);
-        if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CH, bytes, full_bar + s);
-        else bulk_g2s(sa, a1b + (int64_t)row * CH, bytes, full_bar + s, pa);
-        if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s);
-        else bulk_g2s(sa + C::HALF_ELEMS, eb + (int64_t)row * CH, bytes, full_bar + s, pe);
+        const uint32_t bytes_a = (uint32_t)rows * CHA * (uint32_t)sizeof(T), bytes_c = (uint32_t)rows * CHC * (uint32_t)sizeof(T);
+        T* sa = ring + (size_t)s * C::STAGE_ELEMS;
+        mbar_expect_tx(full_bar + s, bytes_a + bytes_c);
+        if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s);
+        else bulk_g2s(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s, pa);
+        if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_A, eb + (int64_t)row * CHC, bytes_c, full_bar + s);
+        else bulk_g2s(sa + C::HALF_A, eb + (int64_t)row * CHC, bytes_c, full_bar + s, pe);
       }
     }
     __syncwarp();
     pdl_wait();          // the producer warp joins the combine below, which reads the preceding kernel's results
   } else {
-    float a2[NV * 8], dc[NV * 8];
+    float a2[NVA * 8], dc[NVC * 8];
     float sdot = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; j++) {
+    for (int j = 0; j < NVA; j++) ld8(att2 + (int64_t)b * o1_stride + (j * 32 + lane) * 8, a2 + j * 8);
+#pragma unroll
+    for (int j = 0; j < NVC; j++) {
       const int c0 = (j * 32 + lane) * 8;
       float g[8], cx[8], dg[8], gp[8];
-      ld8(att2 + (int64_t)b * o1_stride + c0, a2 + j * 8);
       if (gate) ld8(gate + (int64_t)b * o1_stride + c0, g);
-      ld8(ctx + (int64_t)b * CH + c0, cx);
+      ld8(ctx + (int64_t)b * CHC + c0, cx);
       ld8(dgctx + (int64_t)b * dg_stride + c0, dg);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
       if (sp == 0 && wid == 0) {
         if (dgp) st8(dgp + (int64_t)b * dcat_stride + c0, gp);
         if (dgp_bf) st8(dgp_bf + (int64_t)b * dcat_stride + c0, gp);
-        if (dctx_out) st8(dctx_out + (int64_t)b * CH + c0, dc + j * 8);
+        if (dctx_out) st8(dctx_out + (int64_t)b * CHC + c0, dc + j * 8);
       }
     }
     const float sall = warp_sum(sdot) + (sreg ? sreg[(int64_t)b * sreg_stride] : 0.f);
@@ -429,21 +435,21 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
       const float al0 = pa0, al1 = pa1, dr0 = pd0, dr1 = pd1;
       prefetch(i + 1);
       mbar_wait(full_bar + s, ph);
-      const T* sa = ring + (size_t)s * 2 * C::HALF_ELEMS;
-      const T* se = sa + C::HALF_ELEMS;
+      const T* sa = ring + (size_t)s * C::STAGE_ELEMS;
+      const T* se = sa + C::HALF_A;
       const int ra = wid, rb = wid + AP_CWARPS;
       const bool one = ra < rows;
       const bool two = (C::RPW == 2) && (rb < rows);
       if (one) {
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < NV; j++) {
+        for (int j = 0; j < NVC; j++) {
           float u[8];
-          ld8(se + (size_t)ra * CH + (j * 32 + lane) * 8, u);
+          ld8(se + (size_t)ra * CHC + (j * 32 + lane) * 8, u);
 #pragma unroll
           for (int q = 0; q < 8; q++) d0 = fmaf(dc[j * 8 + q], u[q], d0);
           if (two) {
-            ld8(se + (size_t)rb * CH + (j * 32 + lane) * 8, u);
+            ld8(se + (size_t)rb * CHC + (j * 32 + lane) * 8, u);
 #pragma unroll
             for (int q = 0; q < 8; q++) d1 = fmaf(dc[j * 8 + q], u[q], d1);
           }
@@ -457,9 +463,9 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
           if (two) deb[row + rb] = de1;
         }
 #pragma unroll
-        for (int j = 0; j < NV; j++) {
+        for (int j = 0; j < NVA; j++) {
           float v[8];
-          ld8(sa + (size_t)ra * CH + (j * 32 + lane) * 8, v);
+          ld8(sa + (size_t)ra * CHA + (j * 32 + lane) * 8, v);
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const float pre = v[q] + a2[j * 8 + q];
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
             wacc[j * 8 + q] = fmaf(de0, post, wacc[j * 8 + q]);
           }
           if (two) {
-            ld8(sa + (size_t)rb * CH + (j * 32 + lane) * 8, v);
+            ld8(sa + (size_t)rb * CHA + (j * 32 + lane) * 8, v);
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const float pre = v[q] + a2[j * 8 + q];
@@ -484,57 +490,57 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
     }
   }
   __syncthreads();
-  float* s_acc = reinterpret_cast<float*>(ap_smem);            // [8][CH] mask sums | [2][CH] CTA totals | [8][CH] w_full sums
-  float* s_part = s_acc + AP_CWARPS * CH;
-  float* s_wacc = s_part + 2 * CH;
+  float* s_acc = reinterpret_cast<float*>(ap_smem);            // [8][CHA] mask sums | [2][CHA] CTA totals | [8][CHA] w_full sums
+  float* s_part = s_acc + AP_CWARPS * CHA;
+  float* s_wacc = s_part + 2 * CHA;
   if (wid < AP_CWARPS) {
 #pragma unroll
-    for (int j = 0; j < NV; j++)
+    for (int j = 0; j < NVA; j++)
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        s_acc[wid * CH + (j * 32 + lane) * 8 + i] = macc[j * 8 + i];
-        s_wacc[wid * CH + (j * 32 + lane) * 8 + i] = wacc[j * 8 + i];
+        s_acc[wid * CHA + (j * 32 + lane) * 8 + i] = macc[j * 8 + i];
+        s_wacc[wid * CHA + (j * 32 + lane) * 8 + i] = wacc[j * 8 + i];
       }
   }
   __syncthreads();
   if constexpr (CL) {
     cg::cluster_group cluster = cg::this_cluster();
-    for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
       float t = 0.f, u = 0.f;
 #pragma unroll
-      for (int w = 0; w < AP_CWARPS; w++) { t += s_acc[w * CH + c]; u += s_wacc[w * CH + c]; }
+      for (int w = 0; w < AP_CWARPS; w++) { t += s_acc[w * CHA + c]; u += s_wacc[w * CHA + c]; }
       s_part[c] = t;
-      s_part[CH + c] = u;
+      s_part[CHA + c] = u;
     }
     cluster.sync();
-    const int cps = (CH + nsplit - 1) / nsplit;
-    for (int c = sp * cps + threadIdx.x; c < min(CH, (sp + 1) * cps); c += AP_THREADS) {
+    const int cps = (CHA + nsplit - 1) / nsplit;
+    for (int c = sp * cps + threadIdx.x; c < min(CHA, (sp + 1) * cps); c += AP_THREADS) {
       float t = 0.f, u = 0.f;
       for (int q = 0; q < nsplit; q++) {                       // fixed order -> deterministic
         const float* rp = cluster.map_shared_rank(s_part, q);
         t += rp[c];
-        u += rp[CH + c];
+        u += rp[CHA + c];
       }
       datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
       if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
-      if (dwf_part) dwf_part[(int64_t)b * CH + c] += u;       // one writer per (b, c): plain accumulate over the time loop
+      if (dwf_part) dwf_part[(int64_t)b * CHA + c] += u;       // one writer per (b, c): plain accumulate over the time loop
     }
     cluster.sync();
     return;
   }
   if (dwf_part) {
-    for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
       float u = 0.f;
 #pragma unroll
-      for (int w = 0; w < AP_CWARPS; w++) u += s_wacc[w * CH + c];
-      atomicAdd(dwf_part + (int64_t)b * CH + c, u);
+      for (int w = 0; w < AP_CWARPS; w++) u += s_wacc[w * CHA + c];
+      atomicAdd(dwf_part + (int64_t)b * CHA + c, u);
     }
   }
-  float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
-  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CHA + 2);
+  for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < AP_CWARPS; w++) t += s_acc[w * CH + c];
+    for (int w = 0; w < AP_CWARPS; w++) t += s_acc[w * CHA + c];
     part[2 + c] = t;
   }
   __threadfence();
@@ -547,10 +553,10 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const float* pb = partials + (int64_t)b * nsplit * (CH + 2);
-  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+  const float* pb = partials + (int64_t)b * nsplit * (CHA + 2);
+  for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
     float t = 0.f;
-    for (int sidx = 0; sidx < nsplit; sidx++) t += __ldcg(pb + (int64_t)sidx * (CH + 2) + 2 + c);
+    for (int sidx = 0; sidx < nsplit; sidx++) t += __ldcg(pb + (int64_t)sidx * (CHA + 2) + 2 + c);
     datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
     if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
   }
@@ -610,25 +616,25 @@ static inline bool use_cluster(int ns, int R) {
   return g_opt_att_cluster && ns >= 2 && ns <= 8 && ((R + ns - 1) / ns) * 4 <= 16 * 1024;
 }
 
-template <typename T, int NV, int ACT>
+template <typename T, int NVA, int NVC, int ACT>
 static int fwd_launch_a(const AttFwdArgs& x, cudaStream_t st) {
-  using C = ApCfg<T, NV>;
+  using C = ApCfg<T, NVA, NVC>;
   constexpr int SM_MAX = C::SMEM + 16 * 1024;
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NV, true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
   const int rpi = x.rows_per_img > 1 ? x.rows_per_img : 1;
   if (use_cluster(ns, x.R)) {
     const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, true, ACT>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc, x.att2,
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc, x.att2,
                        x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R, ns,
                        (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
   } else {
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NV, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1, (const T*)x.enc,
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1, (const T*)x.enc,
                        x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R,
                        ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
   }
@@ -636,29 +642,32 @@ static int fwd_launch_a(const AttFwdArgs& x, cudaStream_t st) {
   return LO_OK;
 }
 
-template <typename T, int NV>
+template <typename T, int NVA, int NVC>
 static int fwd_launch(const AttFwdArgs& x, cudaStream_t st) {
-  return x.act == 1 ? fwd_launch_a<T, NV, 1>(x, st) : fwd_launch_a<T, NV, 0>(x, st);
+  return x.act == 1 ? fwd_launch_a<T, NVA, NVC, 1>(x, st) : fwd_launch_a<T, NVA, NVC, 0>(x, st);
 }
 
+// C: enc channels; x.a_ch: att1 channels (0 = C).  Supported: A == C in {256, 512, 1024} and (A, C) = (256, 512)
+template <typename T>
+static int fwd_dispatch(const AttFwdArgs& x, int C, cudaStream_t st) {
+  const int A = x.a_ch > 0 ? x.a_ch : C;
+  if (A == 256 && C == 512) return fwd_launch<T, 1, 2>(x, st);
+  if (A != C) return fail(LO_EINVAL, "%s: attention width pair (%ld, %ld) not instantiated", __func__, A, C);
+  if (C == 256) return fwd_launch<T, 1, 1>(x, st);
+  if (C == 512) return fwd_launch<T, 2, 2>(x, st);
+  return fwd_launch<T, 4, 4>(x, st);
+}
 int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st) {
-  if (dt == LO_F32) {
-    if (C == 256) return fwd_launch<float, 1>(x, st);
-    if (C == 512) return fwd_launch<float, 2>(x, st);
-    return fwd_launch<float, 4>(x, st);
-  }
-  if (C == 256) return fwd_launch<bf16, 1>(x, st);
-  if (C == 512) return fwd_launch<bf16, 2>(x, st);
-  return fwd_launch<bf16, 4>(x, st);
+  return dt == LO_F32 ? fwd_dispatch<float>(x, C, st) : fwd_dispatch<bf16>(x, C, st);
 }
 
-template <typename T, int NV, int ACT>
+template <typename T, int NVA, int NVC, int ACT>
 static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
-  using C = ApCfg<T, NV>;
+  using C = ApCfg<T, NVA, NVC>;
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NV, true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NVA, NVC, false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_bwd_pipe_kernel<T, NVA, NVC, true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
@@ -667,29 +676,31 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
       x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,       \
       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, x.dwf_part
   if (use_cluster(ns, x.R)) {
-    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, true, ACT>, dim3(ns, x.B), (size_t)C::SMEM, ns, st, LO_BWD_ARGS));
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NVA, NVC, true, ACT>, dim3(ns, x.B), (size_t)C::SMEM, ns, st, LO_BWD_ARGS));
   } else {
-    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NV, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, LO_BWD_ARGS));
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NVA, NVC, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, LO_BWD_ARGS));
   }
 #undef LO_BWD_ARGS
   LO_LAUNCH_OK();
   return LO_OK;
 }
 
-template <typename T, int NV>
+template <typename T, int NVA, int NVC>
 static int bwd_launch(const AttBwdArgs& x, cudaStream_t st) {
-  return x.act == 1 ? bwd_launch_a<T, NV, 1>(x, st) : bwd_launch_a<T, NV, 0>(x, st);
+  return x.act == 1 ? bwd_launch_a<T, NVA, NVC, 1>(x, st) : bwd_launch_a<T, NVA, NVC, 0>(x, st);
 }
 
+template <typename T>
+static int bwd_dispatch(const AttBwdArgs& x, int C, cudaStream_t st) {
+  const int A = x.a_ch > 0 ? x.a_ch : C;
+  if (A == 256 && C == 512) return bwd_launch<T, 1, 2>(x, st);
+  if (A != C) return fail(LO_EINVAL, "%s: attention width pair (%ld, %ld) not instantiated", __func__, A, C);
+  if (C == 256) return bwd_launch<T, 1, 1>(x, st);
+  if (C == 512) return bwd_launch<T, 2, 2>(x, st);
+  return bwd_launch<T, 4, 4>(x, st);
+}
 int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st) {
-  if (dt == LO_F32) {
-    if (C == 256) return bwd_launch<float, 1>(x, st);
-    if (C == 512) return bwd_launch<float, 2>(x, st);
-    return bwd_launch<float, 4>(x, st);
-  }
-  if (C == 256) return bwd_launch<bf16, 1>(x, st);
-  if (C == 512) return bwd_launch<bf16, 2>(x, st);
-  return bwd_launch<bf16, 4>(x, st);
+  return dt == LO_F32 ? bwd_dispatch<float>(x, C, st) : bwd_dispatch<bf16>(x, C, st);
 }
 
 }  // namespace lo

@@ -159,6 +159,7 @@ struct AttFwdArgs {
   int rows_per_img;
   int nsplit_hint;
   int act;             // 0 ReLU score (torch flavour), 1 tanh (Genthial cell)
+  int a_ch;            // channels of att1 / att2 / wf (0 = same as enc)
 };
 struct AttBwdArgs {
   const void *att1, *enc;
@@ -172,6 +173,7 @@ struct AttBwdArgs {
   float* dwf_part;     // [B][A] running sum over the time loop of the full_att.weight gradient contributions (optional)
   int nsplit_hint;
   int act;
+  int a_ch;
 };
 extern int g_opt_att_pipe;
 extern int g_opt_conv_mc;

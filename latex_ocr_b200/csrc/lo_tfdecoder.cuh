@@ -13,8 +13,8 @@
 //
 // Schedule (same ideas as the torch flavour): att_img hoisted; the embedding half of the LSTM kernel folded into a
 // [V+1][4D] table (row V = start token); logits and every weight gradient hoisted out of the time loop into stacked GEMMs;
-// d att_img by one post-loop sweep; d enc by a batched alpha^T dctx GEMM.  att_img is stored zero-padded from A to C columns
-// (beta padded with zeros) so that the TMA-ring attention kernels serve both flavours unchanged (ACT = tanh instantiation).
+// d att_img by one post-loop sweep; d enc by a batched alpha^T dctx GEMM.  The TMA-ring attention kernels serve both flavours:
+// the (NVA, NVC) = (1, 2) instantiation streams dim_e = 256 att_img columns next to C = 512 image channels, ACT = tanh.
 
 namespace lo {
 
@@ -215,7 +215,7 @@ struct TfDims {
 static inline TfDims tf_dims(const lo_tfdec_args* a) {
   TfDims d;
   d.B = a->B; d.T = a->T; d.R = a->R; d.C = a->C; d.A = a->A; d.D = a->D; d.O = a->O; d.E = a->E; d.V = a->V;
-  d.XH = a->O + a->D; d.G = 4 * a->D; d.LW = a->E + a->O + a->D; d.N2 = a->A + a->O; d.DW = a->C + a->O;
+  d.XH = a->O + a->D; d.G = 4 * a->D; d.LW = a->E + a->O + a->D; d.N2 = a->A + a->O; d.DW = a->A + a->O;
   d.Vl = a->ldl > 0 ? a->ldl : a->V;
   d.rpi = a->rows_per_img > 1 ? a->rows_per_img : 1;
   d.nimg = a->B / d.rpi;
@@ -223,8 +223,8 @@ static inline TfDims tf_dims(const lo_tfdec_args* a) {
 }
 
 struct TfWs {
-  void *att_img, *datt_img;                       // dt [nimg*R][C]
-  float *beta_pad, *dbeta_acc, *ptab, *dptab;
+  void *att_img, *datt_img;                       // dt [nimg*R][A]
+  float *dbeta_acc, *ptab, *dptab;
   float *xh, *call, *gates, *ztmp, *out2, *ctx, *oc, *dologit, *dout2, *dhc, *dz, *dxh, *dc, *de, *dctx, *mean, *initpre, *sinit,
       *dinit, *dmean, *dlogits, *row_loss, *gtmp;
   bf16 *xh_bf, *ctx_bf, *dout2_bf, *dz_bf, *dlogits_bf;
@@ -248,10 +248,9 @@ static TfWs tf_carve(const lo_tfdec_args* a) {
   };
   const size_t TB = (size_t)d.T * d.B, T1B = (size_t)(d.T + 1) * d.B;
   TfWs w{};
-  w.att_img = take((size_t)d.nimg * d.R * d.C * es);
-  w.datt_img = take((size_t)d.nimg * d.R * d.C * es);
-  w.beta_pad = (float*)take((size_t)d.C * 4);
-  w.dbeta_acc = (float*)take((size_t)d.B * d.C * 4);
+  w.att_img = take((size_t)d.nimg * d.R * d.A * es);
+  w.datt_img = take((size_t)d.nimg * d.R * d.A * es);
+  w.dbeta_acc = (float*)take((size_t)d.B * d.A * 4);
   w.ptab = (float*)take((size_t)(d.V + 1) * d.G * 4);
   w.dptab = (float*)take((size_t)(d.V + 1) * d.G * 4);
   w.xh = (float*)take(T1B * d.XH * 4);
@@ -299,9 +298,8 @@ static int tf_check(const lo_tfdec_args* a) {
   LO_CHECK_ARG(a != nullptr, "null args");
   LO_CHECK_ARG(a->B > 0 && a->B <= 512 && a->T > 0 && a->R > 0 && a->V > 1, "B in 1..512, T, R > 0, V > 1");
   LO_CHECK_ARG(a->C == 256 || a->C == 512 || a->C == 1024, "channels in {256,512,1024}");
-  LO_CHECK_ARG(a->A > 0 && a->A <= a->C && a->A % 8 == 0, "dim_e <= channels, multiple of 8");
+  LO_CHECK_ARG(a->A == a->C || (a->A == 256 && a->C == 512), "(dim_e, channels): equal, or (256, 512) — the instantiated attention widths");
   LO_CHECK_ARG(a->D % 8 == 0 && a->O % 8 == 0 && a->E % 8 == 0, "num_units, dim_o, dim_embeddings multiples of 8");
-  LO_CHECK_ARG(a->A + a->O >= a->C, "dim_e + dim_o >= channels (the attention kernels read C columns of the [att_h | o_h] rows)");
   LO_CHECK_ARG(a->dt == LO_F32 || a->dt == LO_BF16, "dt");
   LO_CHECK_ARG(a->ldl == 0 || (a->ldl >= a->V && a->ldl % 8 == 0), "ldl >= V, multiple of 8");
   LO_CHECK_ARG(a->enc && a->ws && a->logits && a->alphas, "null buffer");
@@ -336,9 +334,8 @@ static int tf_tn(const lo_tfdec_args* a, const float* A32, const bf16* Abf, int6
 
 static int tf_prologue(const lo_tfdec_args* a, const TfDims& d, const TfWs& w, cudaStream_t st) {
   const int dt = a->dt;
-  // att_img = img W_img, no bias, once (attention_mechanism.py:43); columns A..C-1 of the buffer stay zero
-  LO_TRY(gemm_nt(a->enc, dt, d.C, a->w_img, dt, d.C, w.att_img, dt, d.C, d.nimg * d.R, d.A, d.C, nullptr, 0, 0, a->impl, st));
-  LO_CUDA(cudaMemcpyAsync(w.beta_pad, a->beta, (size_t)d.A * 4, cudaMemcpyDeviceToDevice, st));
+  // att_img = img W_img, no bias, once (attention_mechanism.py:43)
+  LO_TRY(gemm_nt(a->enc, dt, d.C, a->w_img, dt, d.C, w.att_img, dt, d.A, d.nimg * d.R, d.A, d.C, nullptr, 0, 0, a->impl, st));
   // token -> gate pre-activation table: [embedding_table ; start_token] K[:E] + b   (replaces the lookup + x[:, :E] K[:E])
   LO_TRY(gemm_nt(a->emb, dt, d.E, a->w_lstm, dt, d.LW, w.ptab, LO_F32, d.G, d.V + 1, d.G, d.E, a->b_lstm, 0, 0, LO_IMPL_SIMT, st));
   {
@@ -373,8 +370,8 @@ static int tf_step(const lo_tfdec_args* a, const TfDims& d, const TfWs& w, int t
   // [h_t W_h | h_t o_W_h]   (attention_mechanism.py:79, attention_cell.py:82)
   LO_TRY(tf_nt(a, xh_n + d.O, xhb_n ? xhb_n + d.O : nullptr, d.XH, a->w_cat2, d.D, out2, d.N2, d.B, d.N2, d.D, nullptr, 0, st));
   {
-    AttFwdArgs x{w.att_img, a->enc, out2, d.N2, w.beta_pad, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R, w.ctx + rowt * d.C, nullptr,
-                 0, nullptr, w.ctx_bf ? w.ctx_bf + rowt * d.C : nullptr, d.B, d.R, w.attwork, d.rpi, 0, 1};
+    AttFwdArgs x{w.att_img, a->enc, out2, d.N2, a->beta, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R, w.ctx + rowt * d.C, nullptr,
+                 0, nullptr, w.ctx_bf ? w.ctx_bf + rowt * d.C : nullptr, d.B, d.R, w.attwork, d.rpi, 0, 1, d.A};
     LO_TRY(attention_fwd_pipe(x, a->dt, d.C, st));
   }
   // o_t = tanh(h_t o_W_h + ctx o_W_c)
@@ -461,7 +458,7 @@ int lo_tfdec_backward(const lo_tfdec_args* a, void* stream) {
   LO_TRY(tf_nt(a, w.dlogits, w.dlogits_bf, d.Vl, w.wbY, d.Vl, w.dologit, d.O, TB, d.O, d.Vl, nullptr, 0, st));
   LO_CUDA(cudaMemsetAsync(w.dxh, 0, (size_t)d.B * d.XH * 4, st));
   LO_CUDA(cudaMemsetAsync(w.dc, 0, (size_t)d.B * d.D * 4, st));
-  LO_CUDA(cudaMemsetAsync(w.dbeta_acc, 0, (size_t)d.B * d.C * 4, st));
+  LO_CUDA(cudaMemsetAsync(w.dbeta_acc, 0, (size_t)d.B * d.A * 4, st));
   LO_CUDA(cudaMemsetAsync(w.dptab, 0, (size_t)(d.V + 1) * d.G * 4, st));
   for (int t = d.T - 1; t >= 0; t--) {
     const int64_t rowt = (int64_t)t * d.B, rown = (int64_t)(t + 1) * d.B;
@@ -469,14 +466,14 @@ int lo_tfdec_backward(const lo_tfdec_args* a, void* stream) {
     bf16* dout2b = w.dout2_bf ? w.dout2_bf + rowt * d.DW : nullptr;
     LO_CUDA(launch_pdl(tf_o_pw_bwd_kernel, dim3(cdiv((long)d.B * d.O, 256)), dim3(256), (size_t)0, st, w.dxh, (int64_t)d.XH,
                        (const float*)(w.dologit + rowt * d.O), a->keep_o ? a->keep_o + rowt * d.O : (const float*)nullptr,
-                       (const float*)(w.xh + rown * d.XH), dout2 + d.C, dout2b ? dout2b + d.C : (bf16*)nullptr, (int64_t)d.DW, d.B, d.O));
+                       (const float*)(w.xh + rown * d.XH), dout2 + d.A, dout2b ? dout2b + d.A : (bf16*)nullptr, (int64_t)d.DW, d.B, d.O));
     LO_LAUNCH_OK();
     // [d h_t (o path) | d ctx] = d pre_o [o_W_h^T | o_W_c^T]
-    LO_TRY(tf_nt(a, dout2 + d.C, dout2b ? dout2b + d.C : nullptr, d.DW, w.wb4, d.O, w.dhc, d.D + d.C, d.B, d.D + d.C, d.O, nullptr, 0, st));
+    LO_TRY(tf_nt(a, dout2 + d.A, dout2b ? dout2b + d.A : nullptr, d.DW, w.wb4, d.O, w.dhc, d.D + d.C, d.B, d.D + d.C, d.O, nullptr, 0, st));
     {
-      AttBwdArgs x{w.att_img, a->enc, w.out2 + rowt * d.N2, nullptr, d.N2, w.beta_pad, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+      AttBwdArgs x{w.att_img, a->enc, w.out2 + rowt * d.N2, nullptr, d.N2, a->beta, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
                    w.ctx + rowt * d.C, w.dhc + d.D, d.D + d.C, nullptr, 0, nullptr, 0, w.de + (int64_t)t * d.R, dout2, nullptr, d.DW,
-                   dout2b, nullptr, w.dctx + rowt * d.C, d.B, d.R, w.attwork, w.dbeta_acc, 0, 1};
+                   dout2b, nullptr, w.dctx + rowt * d.C, d.B, d.R, w.attwork, w.dbeta_acc, 0, 1, d.A};
       LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
     }
     // d h_t += d att_h W_h^T
@@ -504,28 +501,27 @@ int lo_tfdec_backward(const lo_tfdec_args* a, void* stream) {
   LO_TRY(colsum(w.dptab, LO_F32, a->g_b_lstm, d.V + 1, d.G, d.G, 0, st));
   // att_h.kernel and o_W_h (adjacent rows of w_cat2), o_W_c, y_W_o
   LO_TRY(tf_tn(a, w.dout2, w.dout2_bf, d.DW, H32, Hbf, d.XH, a->g_w_cat2, d.D, d.A, d.D, TB, st));
-  LO_TRY(tf_tn(a, w.dout2 + d.C, w.dout2_bf ? w.dout2_bf + d.C : nullptr, d.DW, H32, Hbf, d.XH, a->g_w_cat2 + (int64_t)d.A * d.D, d.D, d.O,
+  LO_TRY(tf_tn(a, w.dout2 + d.A, w.dout2_bf ? w.dout2_bf + d.A : nullptr, d.DW, H32, Hbf, d.XH, a->g_w_cat2 + (int64_t)d.A * d.D, d.D, d.O,
                d.D, TB, st));
-  LO_TRY(tf_tn(a, w.dout2 + d.C, w.dout2_bf ? w.dout2_bf + d.C : nullptr, d.DW, w.ctx, w.ctx_bf, d.C, a->g_w_oc, d.C, d.O, d.C, TB, st));
+  LO_TRY(tf_tn(a, w.dout2 + d.A, w.dout2_bf ? w.dout2_bf + d.A : nullptr, d.DW, w.ctx, w.ctx_bf, d.C, a->g_w_oc, d.C, d.O, d.C, TB, st));
   LO_TRY(tf_tn(a, w.dlogits, w.dlogits_bf, d.Vl, O32, Obf, d.XH, a->g_w_y, d.O, d.V, d.O, TB, st));
   // att_beta: per-row partial sums were accumulated by the attention backward kernels
-  LO_TRY(colsum(w.dbeta_acc, LO_F32, w.dmean, d.B, d.C, d.C, 0, st));
-  LO_CUDA(cudaMemcpyAsync(a->g_beta, w.dmean, (size_t)d.A * 4, cudaMemcpyDeviceToDevice, st));
-  // d att_img[b,r,a] = beta[a] sum_t de[b,t,r] (1 - tanh^2(att_img + att_h_t))   (one sweep over t, padded columns give 0)
+  LO_TRY(colsum(w.dbeta_acc, LO_F32, a->g_beta, d.B, d.A, d.A, 0, st));
+  // d att_img[b,r,a] = beta[a] sum_t de[b,t,r] (1 - tanh^2(att_img + att_h_t))   (one sweep over t)
   {
-    dim3 grid(d.C / 64, cdiv(d.R, 32), d.B);
-    LO_DISPATCH_DT(dt, T, (datt1_kernel<T, false, 1><<<grid, 128, 0, st>>>((const T*)w.att_img, w.out2, d.N2, (int64_t)d.B * d.N2, w.de,
-                                                                            w.beta_pad, (T*)w.datt_img, nullptr, d.T, d.R, d.C)));
+    dim3 grid(d.A / 64, cdiv(d.R, 32), d.B);
+    LO_DISPATCH_DT(dt, T, (datt1_kernel<T, false, 1><<<grid, 128, 0, st>>>((const T*)w.att_img, w.out2, d.N2, (int64_t)d.B * d.N2, w.de, a->beta,
+                                                                            (T*)w.datt_img, nullptr, d.T, d.R, d.A)));
     LO_LAUNCH_OK();
   }
   const int BR = d.B * d.R;
-  // att_img.kernel: d W_img^T [A][C] = d att_img[:, :A]^T enc ; d enc = d att_img[:, :A] W_img^T
+  // att_img.kernel: d W_img^T [A][C] = d att_img^T enc ; d enc = d att_img W_img^T
   if (dt == LO_BF16) {
-    LO_TRY(tf_tn(a, nullptr, (const bf16*)w.datt_img, d.C, nullptr, (const bf16*)a->enc, d.C, a->g_w_img, d.C, d.A, d.C, BR, st));
-    LO_TRY(gemm_nt(w.datt_img, LO_BF16, d.C, w.wimgT, LO_BF16, d.A, a->denc, LO_F32, d.C, BR, d.C, d.A, nullptr, 0, 0, a->impl, st));
+    LO_TRY(tf_tn(a, nullptr, (const bf16*)w.datt_img, d.A, nullptr, (const bf16*)a->enc, d.C, a->g_w_img, d.C, d.A, d.C, BR, st));
+    LO_TRY(gemm_nt(w.datt_img, LO_BF16, d.A, w.wimgT, LO_BF16, d.A, a->denc, LO_F32, d.C, BR, d.C, d.A, nullptr, 0, 0, a->impl, st));
   } else {
-    LO_TRY(gemm_tn(w.datt_img, LO_F32, d.C, a->enc, LO_F32, d.C, a->g_w_img, LO_F32, d.C, d.A, d.C, BR, 0, LO_IMPL_SIMT, st));
-    LO_TRY(gemm_nn(w.datt_img, LO_F32, d.C, a->w_img, LO_F32, d.C, a->denc, LO_F32, d.C, BR, d.C, d.A, 0, LO_IMPL_SIMT, st));
+    LO_TRY(gemm_tn(w.datt_img, LO_F32, d.A, a->enc, LO_F32, d.C, a->g_w_img, LO_F32, d.C, d.A, d.C, BR, 0, LO_IMPL_SIMT, st));
+    LO_TRY(gemm_nn(w.datt_img, LO_F32, d.A, a->w_img, LO_F32, d.C, a->denc, LO_F32, d.C, BR, d.C, d.A, 0, LO_IMPL_SIMT, st));
   }
   // d enc[b] += alphas[b]^T dctx[:, b, :]   (the context read, summed over time)
   {
