@@ -1411,7 +1411,11 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
     LO_TRY(forward_step(a, d, t, Rows{0, d.B, a->work, 0}, next_tok, 1, nullptr, 0, nullptr, st));
     float* h_new = a->hall + (int64_t)(t + 1) * d.B * d.D;
     float* c_new = a->call + (int64_t)(t + 1) * d.B * d.D;
-    LO_TRY(gemm_nt(h_new, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));
+    if (bv.on)       // bf16 mirror of h_t -> mma.sync kernel (row blocks of 64), CUDA cores otherwise
+      LO_TRY(gemm_nt(bv.hall + (int64_t)(t + 1) * d.B * d.D, LO_BF16, d.D, a->w_fc, LO_BF16, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D,
+                     a->b_fc, 0, 0, LO_IMPL_TC, st));
+    else
+      LO_TRY(gemm_nt(h_new, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));
     beam_step_kernel<<<n_img, 256, smem, st>>>(a->logits, d.V, beam, t, end_id, logp, finished, ids, parents, fin_hist, next_tok,
                                                parent_rows, max_steps);
     LO_LAUNCH_OK();

@@ -111,11 +111,14 @@ int gemm(const void* A, int dtA, const void* B, int dtB, void* C, int dtC, const
   LO_CHECK_ARG(d.M > 0 && d.N > 0 && d.K > 0 && d.batch > 0, "empty GEMM");
   if (impl == LO_IMPL_TC && dtA == LO_BF16 && dtB == LO_BF16 && d.sak == 1 && d.sbk == 1 && d.batch == 1 && d.sam % 8 == 0 &&
       d.sbn % 8 == 0 && tc_available()) {
-    // few rows, fp32 result: the latency-optimised mma.sync kernel (lo_skinny.cu) — same path as the decoder's per-step GEMMs
-    if (g_opt_skinny_mma && d.M <= 64 && dtC == LO_F32 && !d.relu && d.K % 16 == 0 && d.N % 2 == 0 && d.ldc % 2 == 0)
+    // few rows, fp32 result: the latency-optimised mma.sync kernel (lo_skinny.cu) — same path as the decoder's per-step GEMMs;
+    // up to 512 rows (row blocks of 64) when the shape does not qualify for tcgen05 (e.g. beam-search logits with V % 8 != 0)
+    const bool tc_ok = d.K % 64 == 0 && d.N % 8 == 0 && d.ldc % 8 == 0;
+    if (g_opt_skinny_mma && (d.M <= 64 || (!tc_ok && d.M <= 512)) && dtC == LO_F32 && !d.relu && d.K % 16 == 0 && d.N % 2 == 0 &&
+        d.ldc % 2 == 0)
       return skinny_gemm_nt((const bf16*)A, d.sam, (const bf16*)B, d.sbn, (float*)C, d.ldc, d.M, d.N, d.K, d.bias, 1, d.accumulate, st);
     // otherwise tcgen05; few rows -> 64-wide N tiles (twice the CTAs)
-    if (d.K % 64 == 0 && d.N % 8 == 0 && d.ldc % 8 == 0)
+    if (tc_ok)
       return tc_gemm_nt_ex((const bf16*)A, d.sam, (const bf16*)B, d.sbn, C, dtC, d.ldc, d.M, d.N, d.K, d.bias, d.accumulate, d.relu, 1, 0,
                            d.M <= 64 ? 1 : 0, st);
   }

@@ -33,10 +33,13 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// grid (N/16, ksplit), 128 threads (warp w owns rows 16w..16w+15)
+// grid (N/16, ksplit, row blocks of 64), 128 threads (warp w owns rows 16w..16w+15 of its row block)
 __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ W, int64_t ldw,
                                                           float* __restrict__ C, int64_t ldc, int M, int N, int K, int kc,
                                                           const float* __restrict__ bias, int atomic) {
+  A += (int64_t)blockIdx.z * 64 * lda;
+  C += (int64_t)blockIdx.z * 64 * ldc;
+  M = min(64, M - (int)blockIdx.z * 64);
   extern __shared__ __align__(16) uint8_t sk_smem[];
   bf16* sA = reinterpret_cast<bf16*>(sk_smem);               // [64][SK_PITCH]
   bf16* sW = sA + 64 * SK_PITCH;                             // [16][SK_PITCH]
@@ -189,7 +192,7 @@ int skinny_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw
 // splits > 1 or atomic_acc: partial sums are added onto C with fp32 atomics (C holds the base values)
 int skinny_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                    int splits, int atomic_acc, cudaStream_t st) {
-  LO_CHECK_ARG(M >= 1 && M <= 64 && K % 16 == 0 && N % 2 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 2 == 0, "M<=64, K%16, ld%8");
+  LO_CHECK_ARG(M >= 1 && M <= 64 * 1024 && K % 16 == 0 && N % 2 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 2 == 0, "K%16, ld%8");
   static bool attr = false;
   if (!attr) {
     LO_CUDA(cudaFuncSetAttribute(skinny_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
@@ -202,8 +205,8 @@ int skinny_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, float
   ks = cdiv(K, kc);
   const int atomic = (ks > 1 || atomic_acc) ? 1 : 0;
   if (ks > 1 && !atomic_acc) LO_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
-  LO_CUDA(launch_pdl(skinny_mma_kernel, dim3(cdiv(N, SK_NT), ks), dim3(128), (size_t)SK_SMEM, st, A, lda, W, ldw, C, ldc, M, N, K, kc, bias,
-                     atomic));
+  LO_CUDA(launch_pdl(skinny_mma_kernel, dim3(cdiv(N, SK_NT), ks, cdiv(M, 64)), dim3(128), (size_t)SK_SMEM, st, A, lda, W, ldw, C, ldc, M, N,
+                     K, kc, bias, atomic));
   LO_LAUNCH_OK();
   return LO_OK;
 }

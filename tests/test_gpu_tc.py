@@ -34,7 +34,7 @@ def test_tc_gemm_nt(M, N, K, out_dtype):
 
 
 @pytest.mark.parametrize("M,N,K,acc", [(64, 3072, 512, 0), (64, 2048, 512, 0), (64, 1024, 2048, 1), (64, 512, 1024, 1), (40, 1024, 576, 0),
-                                         (1, 200, 64, 1), (17, 30, 2112, 0)])
+                                         (1, 200, 64, 1), (17, 30, 2112, 0), (200, 500, 512, 0), (255, 500, 512, 1)])
 def test_skinny_mma_gemm(M, N, K, acc):
     """The decoder's per-step GEMM shapes (M = batch <= 64 rows, fp32 out) through the mma.sync kernel (lo_skinny.cu) and
     through the tcgen05 kernel (option skinny_mma=0): both against float64."""
