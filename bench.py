@@ -247,7 +247,7 @@ def main():
         "roofline_all": probes["all"],
         "peaks": pk,
     }
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only (the scaling runs stay short)
         out["cpu_baseline"] = bs.cpu_baseline(c)
     print(json.dumps(out), flush=True)
     if world > 1:
