@@ -53,40 +53,24 @@ __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict_
     const int r = i / cpr, c = i % cpr;
     cp_async16(sW + r * SK_PITCH + c * 8, W + (int64_t)min(n0 + r, N - 1) * ldw + k0 + c * 8, n0 + r < N);
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");       // group 0: the weight slice
   pdl_wait();
   pdl_trigger();
-  // the activations arrive in K chunks of 128 (one commit group each), so the MMAs of chunk c run while chunks > c are in flight
-  constexpr int KCH = 128;
-  const int nch = (kn + KCH - 1) / KCH;                      // <= 4
-  for (int ch = 0; ch < nch; ch++) {
-    const int c0 = ch * (KCH / 8), c1 = min(cpr, c0 + KCH / 8), w = c1 - c0;
-    for (int i = tid; i < 64 * w; i += 128) {
-      const int r = i / w, c = c0 + i % w;
-      cp_async16(sA + r * SK_PITCH + c * 8, A + (int64_t)min(r, M - 1) * lda + k0 + c * 8, r < M);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < 64 * cpr; i += 128) {
+    const int r = i / cpr, c = i % cpr;
+    cp_async16(sA + r * SK_PITCH + c * 8, A + (int64_t)min(r, M - 1) * lda + k0 + c * 8, r < M);
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const bf16* a_ptr = sA + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SK_PITCH + (lane >> 4) * 8;
   const bf16* b_ptr = sW + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
-  for (int ch = 0; ch < nch; ch++) {
-    switch (nch - 1 - ch) {                                  // groups still allowed in flight
-      case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-      case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-      case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-      default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    }
-    __syncthreads();
-    const int k1 = min(kn, (ch + 1) * KCH);
 #pragma unroll 4
-    for (int k = ch * KCH; k < k1; k += 16) {
-      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
-      ldmatrix_x4(a0, a1, a2, a3, a_ptr + k);
-      ldmatrix_x4(b0, b1, b2, b3, b_ptr + k);
-      mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);        // columns n0 .. n0+7
-      mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);        // columns n0+8 .. n0+15
-    }
+  for (int k = 0; k < kn; k += 16) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    ldmatrix_x4(a0, a1, a2, a3, a_ptr + k);
+    ldmatrix_x4(b0, b1, b2, b3, b_ptr + k);
+    mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);          // columns n0 .. n0+7
+    mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);          // columns n0+8 .. n0+15
   }
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
