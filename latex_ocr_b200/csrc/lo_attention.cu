@@ -100,11 +100,6 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
   __syncthreads();
   // PDL: the producer's bulk copies read only loop-invariant tensors (att1, enc: written long before the preceding kernel), so they
   // are issued BEFORE griddepcontrol.wait and overlap the tail of the preceding launch; consumers wait before touching its results.
-  if (wid != AP_CWARPS) {
-    pdl_wait();
-    pdl_trigger();
-  }
-
   float m = -INFINITY, l = 0.f;
   float acc[NVC * 8];
 #pragma unroll
@@ -135,10 +130,11 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     // ===== consumer warps =====
     float a2[NVA * 8], wv[NVA * 8];
 #pragma unroll
-    for (int j = 0; j < NVA; j++) {
-      ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
-      ld8(wf + (j * 32 + lane) * 8, wv + j * 8);
-    }
+    for (int j = 0; j < NVA; j++) ld8(wf + (j * 32 + lane) * 8, wv + j * 8);        // a parameter: independent of the preceding launch
+    pdl_wait();
+    pdl_trigger();
+#pragma unroll
+    for (int j = 0; j < NVA; j++) ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
     for (int i = 0; i < nst; i++) {
       const int s = i % AP_STAGES;
       const uint32_t ph = (i / AP_STAGES) & 1;
@@ -353,10 +349,6 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
   __syncthreads();
   // PDL: the producer's bulk copies read only loop-invariant tensors (att1, enc: written long before the preceding kernel), so they
   // are issued BEFORE griddepcontrol.wait and overlap the tail of the preceding launch; consumers wait before touching its results.
-  if (wid != AP_CWARPS) {
-    pdl_wait();
-    pdl_trigger();
-  }
   float macc[NVA * 8], wacc[NVA * 8];     // wacc: d w_full partial = sum_r de_r * relu(att1_r + att2)   (full_att.weight gradient)
 #pragma unroll
   for (int i = 0; i < NVA * 8; i++) { macc[i] = 0.f; wacc[i] = 0.f; }
@@ -384,21 +376,33 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
   } else {
     float a2[NVA * 8], dc[NVC * 8];
     float sdot = 0.f;
+    // att2 / gate / ctx / sreg were saved by the forward pass: they are fetched BEFORE griddepcontrol.wait (overlapping the tail of
+    // the preceding launch); only d gctx comes from the preceding kernel
+    float gv[NVC * 8], cxv[NVC * 8];
 #pragma unroll
     for (int j = 0; j < NVA; j++) ld8(att2 + (int64_t)b * o1_stride + (j * 32 + lane) * 8, a2 + j * 8);
 #pragma unroll
     for (int j = 0; j < NVC; j++) {
       const int c0 = (j * 32 + lane) * 8;
-      float g[8], cx[8], dg[8], gp[8];
-      if (gate) ld8(gate + (int64_t)b * o1_stride + c0, g);
-      ld8(ctx + (int64_t)b * CHC + c0, cx);
+      if (gate) ld8(gate + (int64_t)b * o1_stride + c0, gv + j * 8);
+      ld8(ctx + (int64_t)b * CHC + c0, cxv + j * 8);
+    }
+    const float sreg_b = sreg ? sreg[(int64_t)b * sreg_stride] : 0.f;
+    pdl_wait();
+    pdl_trigger();
+#pragma unroll
+    for (int j = 0; j < NVC; j++) {
+      const int c0 = (j * 32 + lane) * 8;
+      float dg[8], gp[8];
+      const float* g = gv + j * 8;
+      const float* cx = cxv + j * 8;
       ld8(dgctx + (int64_t)b * dg_stride + c0, dg);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        if (!gate) g[i] = 1.f;                             // Genthial cell: the context is used ungated
-        dc[j * 8 + i] = dg[i] * g[i];
+        const float gi = gate ? g[i] : 1.f;                // Genthial cell: the context is used ungated
+        dc[j * 8 + i] = dg[i] * gi;
         sdot = fmaf(dc[j * 8 + i], cx[i], sdot);
-        gp[i] = dg[i] * cx[i] * g[i] * (1.f - g[i]);
+        gp[i] = dg[i] * cx[i] * gi * (1.f - gi);
       }
       if (sp == 0 && wid == 0) {
         if (dgp) st8(dgp + (int64_t)b * dcat_stride + c0, gp);
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
         if (dctx_out) st8(dctx_out + (int64_t)b * CHC + c0, dc + j * 8);
       }
     }
-    const float sall = warp_sum(sdot) + (sreg ? sreg[(int64_t)b * sreg_stride] : 0.f);
+    const float sall = warp_sum(sdot) + sreg_b;
     const float* alb = alpha + (int64_t)b * alpha_stride;
     float* deb = de + (int64_t)b * alpha_stride;
     const float* drb = dreg + (int64_t)b * dreg_stride;
