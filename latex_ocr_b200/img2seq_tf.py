@@ -85,10 +85,10 @@ class Img2SeqModel:
             img = img.permute(0, 3, 1, 2)
         return img.contiguous().to(self.device, non_blocking=True)
 
-    def train_step(self, images, formulas, dropout=1.0):
-        """One update (img2seq.py:163-170): images as above, formulas = list of id lists (padded here like _get_feed_dict
-        :132-135) or an (int array [N,T], lengths [N]) pair.  Returns the device loss vector [mean CE, mean CE, 0, n_words]."""
-        L = _lib.lib()
+    def compute_gradients(self, images, formulas, dropout=1.0):
+        """Forward + loss + backward (+ the data-parallel all-reduce): images as above, formulas = list of id lists (padded here like
+        _get_feed_dict img2seq.py:132-135) or an (int array [N,T], lengths [N]) pair.  Gradients land in the two flat stores;
+        returns the device loss vector [mean CE, mean CE, 0, n_words]."""
         if isinstance(formulas, tuple):
             formula, length = formulas
         else:
@@ -118,6 +118,11 @@ class Img2SeqModel:
         if self.dist is not None:
             self.dist.reduce_async(self.encoder.store.grad)
             self.dist.wait()
+        return loss
+
+    def apply_gradients(self):
+        """optimizer.apply_gradients (img2seq.py:113-123): optional clip_by_global_norm, then Adam on both stores."""
+        L = _lib.lib()
         scale = 1.0
         if self.clip > 0:                                                   # tf.clip_by_global_norm (img2seq.py:116-121)
             gn = float(torch.sqrt(self.encoder.store.grad.pow(2).sum() + self.decoder.store.grad.pow(2).sum()))
@@ -127,6 +132,11 @@ class Img2SeqModel:
             check(L.lo_adam_step(ptr(S.master), ptr(S.grad), ptr(S.m), ptr(S.v), ptr(S.shadow), S.numel, ptr(S.adam_state), 0.9, 0.999,
                                  1e-8, float(scale), stream_ptr()))
             m._shadow_fresh = True                                          # the fused Adam refreshed the bf16 shadow
+
+    def train_step(self, images, formulas, dropout=1.0):
+        """One update (img2seq.py:163-170).  Returns the device loss vector [mean CE, mean CE, 0, n_words]."""
+        loss = self.compute_gradients(images, formulas, dropout)
+        self.apply_gradients()
         return loss
 
     def _run_train(self, config, train_set, val_set, epoch, lr_schedule):
