@@ -196,9 +196,50 @@ __global__ void colsum_kernel(const T* __restrict__ X, float* __restrict__ out, 
   }
 }
 
+// vectorised variant: a warp reads 256 consecutive columns of one row (8 per lane, 16 B for bf16), 8 warps stride the rows
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ X, float* __restrict__ out, int M, int N, int64_t ld,
+                                                          int rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 256 + lane * 8;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    for (int m = m0 + warp; m < m1; m += 8) {
+      float v[8];
+      ld8(X + (int64_t)m * ld + n, v);
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) red[warp][lane * 8 + k] = acc[k];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += red[w][c];
+    atomicAdd(out + blockIdx.x * 256 + c, t);
+  }
+}
+
 int colsum(const void* X, int dt, float* out, int M, int N, int64_t ld, int accumulate, cudaStream_t st) {
   LO_CHECK_ARG(M > 0 && N > 0, "empty colsum");
   if (!accumulate) LO_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
+  const size_t es = dt == LO_F32 ? 4 : 2;
+  if (N % 8 == 0 && ld % 8 == 0 && ((uintptr_t)X % (8 * es)) == 0 && M >= 256) {
+    const int cb = cdiv(N, 256);
+    int splits = cdiv(148 * 4, cb);
+    if (splits > cdiv(M, 64)) splits = cdiv(M, 64);
+    if (splits < 1) splits = 1;
+    const int rpb = cdiv(M, splits);
+    dim3 grid(cb, cdiv(M, rpb));
+    LO_DISPATCH_DT(dt, T, (colsum_vec_kernel<T><<<grid, 256, 0, st>>>((const T*)X, out, M, N, ld, rpb)));
+    LO_LAUNCH_OK();
+    return LO_OK;
+  }
   const int cb = cdiv(N, 32);
   int splits = cdiv(148 * 8, cb);
   if (splits > cdiv(M, 64)) splits = cdiv(M, 64);

@@ -89,6 +89,19 @@ def test_colsum():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum_vectorised_path(dtype):
+    """N % 8 == 0, ld % 8 == 0, >= 256 rows: the 16-byte-per-lane kernel (bias gradients of the conv stack take this path)."""
+    _lib, L = _L()
+    torch.manual_seed(2)
+    X = torch.randn(5000, 520, device="cuda").to(dtype)
+    o = torch.full((512,), 7.0, device="cuda")
+    _lib.check(L.lo_colsum(_lib.ptr(X), _lib.dt_of(X), _lib.ptr(o), 5000, 512, 520, 0, _lib.stream_ptr()))
+    assert relerr(o, X[:, :512].double().sum(0).float()) < 1e-5
+    _lib.check(L.lo_colsum(_lib.ptr(X), _lib.dt_of(X), _lib.ptr(o), 5000, 512, 520, 1, _lib.stream_ptr()))     # accumulate
+    assert relerr(o, 2 * X[:, :512].double().sum(0).float()) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv1_pool(dtype):
     _lib, L = _L()
     torch.manual_seed(3)
