@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 21: skinny mma kernel tests + step time with/without it
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest (tc + kernels + decode)"
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15

@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 22: PDL pre-wait prefetch (attention producer, skinny weights) — tests + step time + tc-only conv probe
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest"
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8

@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 23: TF-flavour decoder parity tests, then the whole GPU suite
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== TF decoder tests"
 timeout 600 python -m pytest tests/test_gpu_tf_decoder.py -q -m gpu 2>&1 | tail -40

@@ -1,7 +1,7 @@
 #!/bin/bash
 # run 25: verification pass — GPU suite, smoke, full bench (both arms), launch list of the bench command, one full capture of the
 # mma.sync per-step GEMM
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider --tb=short 2>&1 | tail -8 | cut -c1-300
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3

@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 27: cnn variant + fused-LSTM mma.sync epilogue + attention-bwd scalar prefetch: tests, then step time default vs fuse_lstm=1
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider --tb=short 2>&1 | tail -25 | cut -c1-300
 echo "== bench default"

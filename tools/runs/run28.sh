@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== cnn variant test"; timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k cnn_variant --tb=short 2>&1 | tail -8 | cut -c1-300
 echo "== ncu full: attention_bwd_pipe_kernel"

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== cnn variant + TF tests"; timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tf_decoder.py -q -s -m gpu -k "cnn_variant or tf_" --tb=short 2>&1 | grep -v "^$" | tail -30 | cut -c1-250
 echo "== bench"

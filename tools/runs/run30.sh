@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 30: attention kernels with separate att1/enc widths: whole GPU suite, TF-flavour timings, decode throughput, step time
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider --tb=short 2>&1 | tail -12 | cut -c1-300
 echo "== TF bench"; timeout 300 python tools/tf_bench.py 2>&1 | tail -2 | cut -c1-600

@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 31: verification pass after the last kernel changes (mma.sync row blocks, beam logits): suite, smoke, decode throughput, both bench arms
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider --tb=short 2>&1 | tail -12 | cut -c1-300
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -4

@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 32: chunk-pipelined mma.sync GEMM: whole suite, step time, TF-flavour timings again
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider --tb=short 2>&1 | tail -8 | cut -c1-300
 echo "== bench"

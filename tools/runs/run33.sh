@@ -1,6 +1,6 @@
 #!/bin/bash
 # run 33: attention kernels fetch forward-saved operands before griddepcontrol.wait: suite, step time, fresh full captures
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider --tb=short 2>&1 | tail -8 | cut -c1-300
 echo "== bench"
