@@ -163,24 +163,56 @@ def cpu_threads():
     return max(1, min(n, int(os.environ.get("LO_CPU_THREADS", "64"))))
 
 
-def cpu_baseline(c):
-    """The reference's CPU algorithm (oracle port, executed un-hoisted like the reference) on this box's
-    host cores, on a bounded sample of the workload."""
+def cpu_arm(c, sample_b, steps, warmup):
+    """Times the reference's CPU train step (getLoss: forward, loss, backward, two Adam steps — img2seq_torch.py:136-172) on
+    `sample_b` images of the cfg2 workload, all host threads.  When the reference tree is importable (/root/reference in the
+    build container, baseline/_ref on a box where the driver installed it) the UNMODIFIED reference modules are driven through
+    oracle/ref_shim.py (kind "reference"); otherwise the oracle port executes the same un-hoisted algorithm (kind "port").
+    Returns (seconds per step, kind, cores)."""
     from oracle import ref_model as rm
+    from oracle import ref_shim
     cores = cpu_threads()
     torch.set_num_threads(cores)
-    sb = int(os.environ.get("LO_REF_SAMPLE_B", "4"))
-    pe, pd = rm.init_params(c["V"], seed=0)
-    img, formula = rm.synthetic_batch(sb, c["H"], c["W"], c["V"], c["T"], c["T"], seed=1234)
-    state = {}
+    img, formula = rm.synthetic_batch(sample_b, c["H"], c["W"], c["V"], c["T"], c["T"], seed=1234)
+    T = formula.shape[1] - 1
+    if ref_shim.reference_available():
+        kind = "reference"
+        enc, dec = ref_shim.build_reference_models(c["V"])
+        enc.train(True)
+        dec.train(True)                                            # nn.Dropout(0.5) active, as in the reference's training loop
+        oe = torch.optim.Adam(enc.parameters(), lr=1e-3)          # img2seq_torch.py:86-87
+        od = torch.optim.Adam(dec.parameters(), lr=1e-3)
+
+        def step():
+            loss, _, _ = ref_shim.ref_get_loss(enc, dec, img, formula)
+            od.zero_grad()
+            oe.zero_grad()
+            loss.backward()
+            od.step()
+            oe.step()
+            return loss.item()
+    else:
+        kind = "port"
+        pe, pd = rm.init_params(c["V"], seed=0)
+        state = {}
+        gen = torch.Generator().manual_seed(7)
+
+        def step():
+            mask = (torch.rand(sample_b, T, 512, generator=gen) >= 0.5).float() * 2.0
+            return rm.train_step(pe, pd, img, formula, state, dropout_mask=mask, hoist=False)[0]
+    for _ in range(warmup):
+        step()
     t0 = time.perf_counter()
-    rm.train_step(pe, pd, img, formula, state, hoist=False)        # warm-up (also bounds the sample)
-    warm = time.perf_counter() - t0
-    n = 2 if warm < 12 else 1
-    t0 = time.perf_counter()
-    for _ in range(n):
-        rm.train_step(pe, pd, img, formula, state, hoist=False)
-    dt = (time.perf_counter() - t0) / n
-    return {"value": sb / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "%d of %d images per step (cfg2 shapes), %d timed step(s) after 1 warm-up, torch %s CPU fp32, %.2f s/step"
-                      % (sb, c["B"], n, torch.__version__, dt)}
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps, kind, cores
+
+
+def cpu_baseline(c):
+    """`cpu_baseline` of the product arm's JSON line: the reference's CPU algorithm on this box's host cores, on a bounded
+    sample of the workload (same sample size as `bench.py --impl reference`)."""
+    sb = int(os.environ.get("LO_REF_SAMPLE_B", "8"))
+    dt, kind, cores = cpu_arm(c, sb, steps=2, warmup=1)
+    return {"value": sb / dt, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": "%d of %d images per step (cfg2 shapes), 2 timed steps after 1 warm-up, torch %s CPU fp32, %.2f s/step"
+                      % (sb, c["B"], torch.__version__, dt)}

@@ -184,7 +184,7 @@ typedef struct lo_decoder_args {
   float* hd;               /* [B][T][D] h after dropout */
   float* logits;           /* [B][T][ldl]  (== predictions in the first V columns) */
   /* loss */
-  float* row_loss;         /* [B*T] */
+  float* row_loss;         /* [B*T + B*R]: per-position CE, then the B*R regulariser partials (1 - sum_t alpha)^2 */
   float* loss;             /* [4]: total, ce, reg, n_valid */
   /* backward state */
   float* dlogits;          /* [B][T][ldl] */
@@ -201,7 +201,7 @@ typedef struct lo_decoder_args {
   void* datt1;             /* big [B][R][A] */
   float* denc;             /* f32 [B][R][C]  (output: gradient w.r.t. encoder_out) */
   float* dinit;            /* [B][2D] = dh0 | dc0 */
-  float* dmean;            /* [B][C] */
+  float* dmean;            /* [B][max(A,C)]: d mean_r(enc); doubles as the [B][A] d full_att.weight scratch of the time loop */
   /* parameter gradients (fp32, reference layouts) */
   float* g_w_enc_att; float* g_b_enc_att;
   float* g_wcat1; float* g_bcat1;

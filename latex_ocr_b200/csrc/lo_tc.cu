@@ -10,6 +10,7 @@
 // tile per CTA, 2 CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 
+#include <mutex>
 #include <unordered_map>
 
 #include "lo_common.cuh"
@@ -625,7 +626,9 @@ struct MapKeyHash {
     return (size_t)h;
   }
 };
+// the ABI allows one host thread per device: the descriptor cache is shared by all of them -> guarded
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static std::mutex g_map_mutex;
 
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                     const cuuint32_t* box) {
@@ -634,13 +637,17 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   key.base = base; key.rank = rank;
   for (int i = 0; i < rank; i++) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
   for (int i = 0; i + 1 < rank; i++) key.str[i] = strides_bytes[i];
-  auto it = g_map_cache.find(key);
-  if (it != g_map_cache.end()) { *m = it->second; return LO_OK; }
+  {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *m = it->second; return LO_OK; }
+  }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LO_ECUDA, "%s: cuTensorMapEncodeTiled failed (%ld)", "tc", (long)r);
+  std::lock_guard<std::mutex> lk(g_map_mutex);
   if (g_map_cache.size() > 20000) g_map_cache.clear();
   g_map_cache.emplace(key, *m);
   return LO_OK;

@@ -3,8 +3,9 @@
 // reuses that file's kernels: attention launchers, datt1 sweep, transposes, beam step, argmax ...).
 //
 // Reference semantics (paths relative to the reference root):
-//   model/components/attention_cell.py:58-89   step:  x = [emb ; o] ; (c,h) = LSTMCell(x,(c,h)) ; ctx = attention(h) ;
-//                                              o = tanh(h o_W_h + ctx o_W_c) ; logits = o y_W_o
+//   model/components/attention_cell.py:58-89   step:  x = [emb ; o] ; (c,h) = LSTMCell(x,(c,h)) ; hd = dropout(h) ; ctx = attention(hd) ;
+//                                              o = dropout(tanh(hd o_W_h + ctx o_W_c)) ; logits = o y_W_o ; next state (c, h, o):
+//                                              the recurrent h is the UNDROPPED one (:71, :87), the recurrent o the dropped one
 //   model/components/attention_mechanism.py:43 att_img = img W_img (once) ; :79-94 e = beta . tanh(att_img + h W_h), softmax
 //   :145-153 / attention_cell.py:51-56         c0, h0, o0 = tanh(mean_r(img) W + b)
 //   model/decoder.py:48-57, 75-96              training inputs [start_token ; E[formula[:, :-1]]], dynamic_rnn over all T columns
@@ -22,7 +23,8 @@ namespace lo {
 __global__ void tf_lstm_pw_fwd_kernel(const float* __restrict__ z, const float* __restrict__ ptab, const int64_t* __restrict__ tok,
                                       int64_t tok_stride, int V, const float* __restrict__ c_prev, float* __restrict__ gates,
                                       float* __restrict__ c_out, float* __restrict__ h_out, bf16* __restrict__ h_bf, int64_t xh_stride,
-                                      const float* __restrict__ keep, int nrows, int D) {
+                                      const float* __restrict__ keep, float* __restrict__ hd_out, bf16* __restrict__ hd_bf, int nrows,
+                                      int D) {
   pdl_wait();
   pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,13 +43,19 @@ __global__ void tf_lstm_pw_fwd_kernel(const float* __restrict__ z, const float* 
   const float f = sigmoidf_(z0[2 * D + j] + pt[2 * D + j] + 1.0f);       // forget_bias = 1.0
   const float o = sigmoidf_(z0[3 * D + j] + pt[3 * D + j]);
   const float c = f * c_prev[(int64_t)b * D + j] + i * g;
-  float h = o * tanhf(c);
-  if (keep) h *= keep[(int64_t)b * D + j];              // tf.nn.dropout(new_h) — the dropped h is also the recurrent state
+  const float h = o * tanhf(c);
   float* gt = gates + (int64_t)b * 4 * D;
   gt[j] = i; gt[D + j] = g; gt[2 * D + j] = f; gt[3 * D + j] = o;
   c_out[(int64_t)b * D + j] = c;
+  // attention_cell.py:71-72,87: new_cell_state keeps the UNDROPPED h as the recurrent state; tf.nn.dropout(new_h) feeds only
+  // the attention and the o projection of this step -> separate buffer hd (only when dropout is on)
   h_out[(int64_t)b * xh_stride + j] = h;
   if (h_bf) h_bf[(int64_t)b * xh_stride + j] = __float2bfloat16_rn(h);
+  if (keep) {
+    const float hdv = h * keep[(int64_t)b * D + j];
+    hd_out[(int64_t)b * D + j] = hdv;
+    if (hd_bf) hd_bf[(int64_t)b * D + j] = __float2bfloat16_rn(hdv);
+  }
 }
 
 __global__ void tf_o_pw_fwd_kernel(const float* __restrict__ oc, const float* __restrict__ oh, int64_t oh_stride,
@@ -96,9 +104,12 @@ __global__ void tf_lstm_pw_bwd_kernel(float* __restrict__ dxh, int64_t xh_stride
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nrows * D) return;
   const int b = idx / D, j = idx % D;
-  float dh = dxh[(int64_t)b * xh_stride + O + j] + dhc[(int64_t)b * dhc_stride + j];
+  // d h_t = (recurrent path: next step's LSTM read the undropped h) + keep * (attention / o-projection paths, which read
+  // the dropped h of this step)
+  float dhd = dhc[(int64_t)b * dhc_stride + j];
+  if (keep) dhd *= keep[(int64_t)b * D + j];
+  const float dh = dxh[(int64_t)b * xh_stride + O + j] + dhd;
   dxh[(int64_t)b * xh_stride + O + j] = 0.f;
-  if (keep) dh *= keep[(int64_t)b * D + j];
   const float* gt = gates + (int64_t)b * 4 * D;
   const float i = gt[j], g = gt[D + j], f = gt[2 * D + j], o = gt[3 * D + j];
   const float tc = tanhf(c_cur[(int64_t)b * D + j]);
@@ -226,8 +237,8 @@ struct TfWs {
   void *att_img, *datt_img;                       // dt [nimg*R][A]
   float *dbeta_acc, *ptab, *dptab;
   float *xh, *call, *gates, *ztmp, *out2, *ctx, *oc, *dologit, *dout2, *dhc, *dz, *dxh, *dc, *de, *dctx, *mean, *initpre, *sinit,
-      *dinit, *dmean, *dlogits, *row_loss, *gtmp;
-  bf16 *xh_bf, *ctx_bf, *dout2_bf, *dz_bf, *dlogits_bf;
+      *dinit, *dmean, *dlogits, *row_loss, *gtmp, *hd;
+  bf16 *xh_bf, *ctx_bf, *dout2_bf, *dz_bf, *dlogits_bf, *hd_bf;
   void *wb4, *wb5, *wb6, *wbY, *wimgT;            // dt: transposed weights for the backward GEMMs
   void* attwork;
   int64_t* next_tok;
@@ -281,6 +292,8 @@ static TfWs tf_carve(const lo_tfdec_args* a) {
   w.dout2_bf = bf ? (bf16*)take(TB * d.DW * 2) : nullptr;
   w.dz_bf = bf ? (bf16*)take(TB * d.G * 2) : nullptr;
   w.dlogits_bf = bf ? (bf16*)take(TB * d.Vl * 2) : nullptr;
+  w.hd = (float*)take(TB * d.D * 4);                                  // dropped h_t (attention_cell.py:72), used when keep_h != NULL
+  w.hd_bf = bf ? (bf16*)take(TB * d.D * 2) : nullptr;
   w.wb4 = take((size_t)(d.D + d.C) * d.O * es);
   w.wb5 = take((size_t)d.D * d.A * es);
   w.wb6 = take((size_t)d.XH * d.G * es);
@@ -365,10 +378,14 @@ static int tf_step(const lo_tfdec_args* a, const TfDims& d, const TfWs& w, int t
   LO_CUDA(launch_pdl(tf_lstm_pw_fwd_kernel, dim3(cdiv((long)d.B * d.D, 256)), dim3(256), (size_t)0, st, (const float*)w.ztmp,
                      (const float*)w.ptab, tok, tok_stride, d.V, (const float*)(w.call + rowt * d.D), w.gates + rowt * d.G,
                      w.call + rown * d.D, xh_n + d.O, xhb_n ? xhb_n + d.O : (bf16*)nullptr, (int64_t)d.XH,
-                     a->keep_h ? a->keep_h + rowt * d.D : (const float*)nullptr, d.B, d.D));
+                     a->keep_h ? a->keep_h + rowt * d.D : (const float*)nullptr, w.hd + rowt * d.D,
+                     w.hd_bf ? w.hd_bf + rowt * d.D : (bf16*)nullptr, d.B, d.D));
   LO_LAUNCH_OK();
-  // [h_t W_h | h_t o_W_h]   (attention_mechanism.py:79, attention_cell.py:82)
-  LO_TRY(tf_nt(a, xh_n + d.O, xhb_n ? xhb_n + d.O : nullptr, d.XH, a->w_cat2, d.D, out2, d.N2, d.B, d.N2, d.D, nullptr, 0, st));
+  // [hd_t W_h | hd_t o_W_h] with hd_t = dropout(h_t)   (attention_cell.py:72, attention_mechanism.py:79, attention_cell.py:82)
+  if (a->keep_h)
+    LO_TRY(tf_nt(a, w.hd + rowt * d.D, w.hd_bf ? w.hd_bf + rowt * d.D : nullptr, d.D, a->w_cat2, d.D, out2, d.N2, d.B, d.N2, d.D, nullptr, 0, st));
+  else
+    LO_TRY(tf_nt(a, xh_n + d.O, xhb_n ? xhb_n + d.O : nullptr, d.XH, a->w_cat2, d.D, out2, d.N2, d.B, d.N2, d.D, nullptr, 0, st));
   {
     AttFwdArgs x{w.att_img, a->enc, out2, d.N2, a->beta, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R, w.ctx + rowt * d.C, nullptr,
                  0, nullptr, w.ctx_bf ? w.ctx_bf + rowt * d.C : nullptr, d.B, d.R, w.attwork, d.rpi, 0, 1, d.A};
@@ -487,8 +504,10 @@ int lo_tfdec_backward(const lo_tfdec_args* a, void* stream) {
     LO_TRY(tf_nt(a, w.dz + rowt * d.G, w.dz_bf ? w.dz_bf + rowt * d.G : nullptr, d.G, w.wb6, d.G, w.dxh, d.XH, d.B, d.XH, d.G, nullptr, 1, st));
   }
   // ---- hoisted parameter gradients (stacked over all T*B rows) ----
-  const float* H32 = w.xh + (int64_t)d.B * d.XH + d.O;                       // h_t, t = 0..T-1 (rows 1..T of xh)
-  const bf16* Hbf = w.xh_bf ? w.xh_bf + (int64_t)d.B * d.XH + d.O : nullptr;
+  // h_t as the attention / o projections saw it: rows 1..T of xh, or the dropped copies when dropout is on
+  const float* H32 = a->keep_h ? w.hd : w.xh + (int64_t)d.B * d.XH + d.O;
+  const bf16* Hbf = a->keep_h ? w.hd_bf : (w.xh_bf ? w.xh_bf + (int64_t)d.B * d.XH + d.O : nullptr);
+  const int64_t ldH = a->keep_h ? d.D : d.XH;
   const float* O32 = w.xh + (int64_t)d.B * d.XH;                             // o_t
   const bf16* Obf = w.xh_bf ? w.xh_bf + (int64_t)d.B * d.XH : nullptr;
   // LSTM kernel, [o ; h] rows: dz^T xh[0..T-1]
@@ -500,8 +519,8 @@ int lo_tfdec_backward(const lo_tfdec_args* a, void* stream) {
   LO_TRY(gemm_tn(w.dptab, LO_F32, d.G, a->emb, dt, d.E, a->g_w_lstm, LO_F32, d.LW, d.G, d.E, d.V + 1, 0, LO_IMPL_SIMT, st));
   LO_TRY(colsum(w.dptab, LO_F32, a->g_b_lstm, d.V + 1, d.G, d.G, 0, st));
   // att_h.kernel and o_W_h (adjacent rows of w_cat2), o_W_c, y_W_o
-  LO_TRY(tf_tn(a, w.dout2, w.dout2_bf, d.DW, H32, Hbf, d.XH, a->g_w_cat2, d.D, d.A, d.D, TB, st));
-  LO_TRY(tf_tn(a, w.dout2 + d.A, w.dout2_bf ? w.dout2_bf + d.A : nullptr, d.DW, H32, Hbf, d.XH, a->g_w_cat2 + (int64_t)d.A * d.D, d.D, d.O,
+  LO_TRY(tf_tn(a, w.dout2, w.dout2_bf, d.DW, H32, Hbf, ldH, a->g_w_cat2, d.D, d.A, d.D, TB, st));
+  LO_TRY(tf_tn(a, w.dout2 + d.A, w.dout2_bf ? w.dout2_bf + d.A : nullptr, d.DW, H32, Hbf, ldH, a->g_w_cat2 + (int64_t)d.A * d.D, d.D, d.O,
                d.D, TB, st));
   LO_TRY(tf_tn(a, w.dout2 + d.A, w.dout2_bf ? w.dout2_bf + d.A : nullptr, d.DW, w.ctx, w.ctx_bf, d.C, a->g_w_oc, d.C, d.O, d.C, TB, st));
   LO_TRY(tf_tn(a, w.dlogits, w.dlogits_bf, d.Vl, O32, Obf, d.XH, a->g_w_y, d.O, d.V, d.O, TB, st));

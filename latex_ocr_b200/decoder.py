@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .params import FlatStore, ParamHolder
+from .params import FlatStore, LRUCache, ParamHolder
 
 
 def _dt(precision):
@@ -118,7 +118,7 @@ class DecoderWithAttention(nn.Module):
             h.bind("bias", S, n + ".bias")
             setattr(self, n, h)
         self.reset_parameters()
-        self._ws = {}
+        self._ws = LRUCache()     # bounded: see params.LRUCache
         self._shadow_fresh = False
 
     def reset_parameters(self):
@@ -226,6 +226,10 @@ class DecoderWithAttention(nn.Module):
             t["dmean"] = z(B, C)
             ws["need_grad"] = True
         return ws
+
+    def _ws_for(self, B, T, R):
+        """The cached workspace of an exact shape (tests / bench probes)."""
+        return self._ws[(B, T, R)]
 
     def fill_args(self, ws, enc, B, T, R, has_dropout, dalpha_ext=None):
         S, t = self.store, ws["t"]

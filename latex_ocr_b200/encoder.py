@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .params import FlatStore, ParamHolder
+from .params import FlatStore, LRUCache, ParamHolder
 
 # (sequential index, Cin, Cout, pad, pool after)    seq2seq_torch.py:35-56
 _LAYERS = (("0", 1, 64, 1, (2, 2)), ("3", 64, 128, 1, (2, 2)), ("6", 128, 256, 1, None),
@@ -80,7 +80,7 @@ class EncoderCNN(nn.Module):
             h.bind("bias", self.store, "cnn.%s.bias" % idx)
             self.cnn[idx] = h
         self.reset_parameters()
-        self._ws = {}
+        self._ws = LRUCache()     # bounded: see params.LRUCache
         self._shadow_fresh = False
 
     # nn.Conv2d default init (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)))

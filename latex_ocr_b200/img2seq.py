@@ -18,6 +18,7 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 from .decoder import DecoderWithAttention
 from .encoder import EncoderCNN
+from .params import LRUCache
 
 
 class Img2SeqModel:
@@ -36,7 +37,7 @@ class Img2SeqModel:
         self.encoder = None
         self.decoder = None
         self.use_graph = bool(getattr(config, "cuda_graph", False))
-        self._graphs = {}
+        self._graphs = LRUCache()  # captured train-step graphs, one per (shapes, mode): bounded like the workspaces
         self.dist = None          # set by latex_ocr_b200.dist.attach(model)
         self.lr = float(getattr(config, "lr_init", 1e-3))
 
@@ -185,6 +186,9 @@ class Img2SeqModel:
                 mask = self.decoder.make_dropout_mask(N, T)
                 st["loss"] = self._step_body(st["img"], st["caps"], decode_lengths, mask)
             st["graph"] = graph          # capture records the launches, it does not execute them
+            # the graph replays on the workspaces that were live during capture: keep them alive even if the bounded
+            # workspace caches evict their entries
+            st["keep"] = (list(self.decoder._ws.values()), list(self.encoder._ws.values()))
             g = self._graphs[key] = st
         g["img"].copy_(img_d, non_blocking=True)
         g["caps"].copy_(caps_d, non_blocking=True)

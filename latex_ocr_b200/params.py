@@ -4,6 +4,33 @@ views.  One buffer -> one fused Adam launch and one NCCL all-reduce bucket per m
 import torch
 import torch.nn as nn
 
+import os
+from collections import OrderedDict
+
+
+class LRUCache(OrderedDict):
+    """Bounded shape-keyed cache for workspaces / captured CUDA graphs.  Real data gives a different (batch, max formula
+    length, image bucket) on nearly every batch; an unbounded per-shape cache would grow by tens to hundreds of MB per
+    distinct key over an epoch.  Least-recently-used entries are dropped (their tensors return to torch's caching
+    allocator, so a re-created workspace of a recurring shape costs no cudaMalloc)."""
+
+    def __init__(self, maxsize=None):
+        super().__init__()
+        self.maxsize = int(maxsize if maxsize is not None else os.environ.get("LO_WS_CACHE", "4"))
+
+    def get(self, key, default=None):
+        if key in self:
+            self.move_to_end(key)
+            return super().__getitem__(key)
+        return default
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        self.move_to_end(key)
+        while len(self) > max(1, self.maxsize):
+            self.popitem(last=False)
+
+
 ALIGN = 8  # elements: 32 B in fp32, 16 B in bf16 (vector-load alignment of the kernels)
 
 

@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check, stream_ptr
-from .params import FlatStore, ParamHolder
+from .params import FlatStore, LRUCache, ParamHolder
 
 DecoderOutput = collections.namedtuple("DecoderOutput", ("logits", "ids"))      # greedy_decoder_cell.py:5-6
 
@@ -117,7 +117,7 @@ class Decoder(nn.Module):
         for n in ("att_beta", "b_c_0", "b_h_0", "b_o_0", "embedding_table", "start_token"):
             bind(self, n, S, n)
         self.reset_parameters()
-        self._ws = {}
+        self._ws = LRUCache()     # bounded: see params.LRUCache
         self._shadow_fresh = False
 
     # tf.get_variable / tf.layers.dense default: glorot_uniform; LSTMCell bias zeros; embeddings decoder.py:98-105

@@ -23,7 +23,12 @@ CASES = {
     "tiny_train": dict(B=3, H=32, W=80, V=40, tmin=3, tmax=7, train=True, positional=True, pseed=12, dseed=22),
     "tiny_nopos": dict(B=2, H=48, W=64, V=37, tmin=2, tmax=5, train=False, positional=False, pseed=13, dseed=23),
     "cfg1": dict(B=4, H=64, W=256, V=100, tmin=8, tmax=32, train=False, positional=True, pseed=14, dseed=24),
+    # BASELINE.json configs[1] shapes (R = 14*62 = 868, T = 150, V = 500) on a B=8 sample of the batch, dropout active:
+    # the exact tiles / 150-step recurrence the bench runs.  Summaries only (strided samples), ~1.5 MB.
+    "cfg2": dict(B=8, H=128, W=512, V=500, tmin=150, tmax=150, train=True, positional=True, pseed=16, dseed=26, summaries_only=True),
 }
+
+SAMPLE_N = 8192
 
 
 def summarize(g):
@@ -35,7 +40,20 @@ def summarize(g):
         else:
             out[k] = dict(sum=v.double().sum().item(), abssum=v.double().abs().sum().item(),
                           head=v.reshape(-1)[:256].clone(), shape=tuple(v.shape))
+            out[k].update(strided_sample(v))
     return out
+
+
+def strided_sample(v):
+    """SAMPLE_N values at a fixed stride (coprime offsets so that every row/column phase is visited) + the full-tensor
+    L2 norm: lets a test bound the relative NORM error of a big tensor from the sample."""
+    flat = v.detach().reshape(-1)
+    n = flat.numel()
+    stride = max(1, n // SAMPLE_N)
+    if stride > 1 and stride % 2 == 0:
+        stride += 1
+    idx = (torch.arange(min(SAMPLE_N, n), dtype=torch.int64) * stride) % n
+    return dict(sample_stride=stride, sample=flat[idx].clone(), norm=flat.double().norm().item())
 
 
 def dropout_masks(seed, B, T, D, p=0.5):
@@ -67,9 +85,13 @@ def run_case(name, c):
         loss.backward()
         if step == 0:
             rec["loss"] = loss.item()
-            rec["scores"] = scores.detach().clone()
-            rec["alphas"] = alphas.detach().clone()
-            rec["enc_out"] = enc(img).detach().clone()
+            if c.get("summaries_only"):
+                big = summarize({"scores": scores, "alphas": alphas, "enc_out": enc(img)})
+                rec["scores"], rec["alphas"], rec["enc_out"] = big["scores"], big["alphas"], big["enc_out"]
+            else:
+                rec["scores"] = scores.detach().clone()
+                rec["alphas"] = alphas.detach().clone()
+                rec["enc_out"] = enc(img).detach().clone()
             rec["grad_enc"] = summarize({k: v.grad for k, v in enc.named_parameters()})
             rec["grad_dec"] = summarize({k: v.grad for k, v in dec.named_parameters()})
         od.step()
@@ -83,7 +105,10 @@ def run_case(name, c):
     mask = dropout_masks(mask_seed, c["B"], T, 512) if c["train"] else None
     l2, aux = rm.get_loss(pe, pd, img, formula, dropout_mask=mask, positional=c["positional"])
     assert abs(l2.item() - rec["loss"]) == 0.0, (name, l2.item(), rec["loss"])
-    assert (aux["scores"] - rec["scores"]).abs().max().item() == 0.0
+    if c.get("summaries_only"):
+        assert (strided_sample(aux["scores"])["sample"] - rec["scores"]["sample"]).abs().max().item() == 0.0
+    else:
+        assert (aux["scores"] - rec["scores"]).abs().max().item() == 0.0
     torch.save(rec, os.path.join(OUT, name + ".pt"))
     print(name, "loss", rec["loss"], "traj", traj, "T", T,
           "bytes", os.path.getsize(os.path.join(OUT, name + ".pt")))

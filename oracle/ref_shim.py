@@ -21,7 +21,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("LATEX_OCR_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """Search order (SURVEY.md §8-c "GPU-box note"): $LATEX_OCR_REFERENCE, /root/reference (the build container),
+    then <repo>/baseline/_ref (where a driver-side install of the reference lands on the GPU box; git-ignored)."""
+    cands = [os.environ.get("LATEX_OCR_REFERENCE"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "model", "components", "seq2seq_torch.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -84,13 +84,14 @@ def cell_step(p, enc, att_img, emb, c, h, o, keep_h=None, keep_o=None):
     """AttentionCell.step (attention_cell.py:58-89).  keep_h / keep_o: optional dropout multipliers (already scaled by
     1/keep_prob like tf.nn.dropout) for new_h and new_o.  Returns logits, (c, h, o), alpha."""
     x = torch.cat([emb, o], dim=-1)                                   # :70
-    c2, h2 = lstm_cell_tf(p, x, c, h)                                 # :71
-    if keep_h is not None:
-        h2 = h2 * keep_h                                              # :72  (the dropped h is also the next LSTM state h)
-    ctx, a = attention_context(p, enc, att_img, h2)                   # :75
-    o2 = torch.tanh(h2 @ p["o_W_h"] + ctx @ p["o_W_c"])               # :82
+    c2, h2 = lstm_cell_tf(p, x, c, h)                                 # :71  new_h, new_cell_state = cell(x, prev)
+    hd = h2 if keep_h is None else h2 * keep_h                        # :72  dropout on the LOCAL new_h only
+    ctx, a = attention_context(p, enc, att_img, hd)                   # :75
+    o2 = torch.tanh(hd @ p["o_W_h"] + ctx @ p["o_W_c"])               # :82
     if keep_o is not None:
         o2 = o2 * keep_o                                              # :83
+    # :87 new_state = AttentionState(new_cell_state, new_o): the recurrent h is the UNDROPPED LSTM output, the recurrent o
+    # is the dropped new_o
     return o2 @ p["y_W_o"], (c2, h2, o2), a                           # :84-87
 
 
