@@ -82,18 +82,43 @@ def kernel_probes(model, c, pk):
 
     ms_att = _time_ms(att_steps, 3) / T
     att_bytes = B * R * (A + C) * bpe + B * R * 4
-    traffic = None
+    traffic_tab = {}
     try:
         import json
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
-        if B == 64 and R == 868 and bpe == 2:
-            traffic = tj["attention_fwd_pipe_kernel"]["bytes"]
+        traffic_tab = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")))
     except Exception:
         pass
+
+    def traffic_of(kernel):
+        """dram__bytes_read + dram__bytes_write per launch of `kernel` from this round's `ncu --set full` capture (profiles/
+        r2_traffic.json is written by tools/ncu_traffic.py from the committed raw CSVs); null off the profiled shape."""
+        e = traffic_tab.get(kernel)
+        return e["bytes"] if (e and B == 64 and R == 868 and bpe == 2) else None
+
     att = {"kernel": "attention_fwd_pipe_kernel (score + softmax + context + gate, one decode step, TMA ring)", "bound": "hbm",
-           "achieved": att_bytes / (ms_att * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "traffic": traffic,
+           "achieved": att_bytes / (ms_att * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "traffic": traffic_of("attention_fwd_pipe_kernel"),
            "us_per_launch": ms_att * 1e3, "algorithmic_bytes": att_bytes, "peak_source": pk["src"]}
     att["frac"] = att["achieved"] / att["peak"]
+
+    # attention backward step kernel: the same stream (att1 + enc read once) + the d e row written
+    DX = C + 512
+
+    def att_bwd_steps():
+        for s in range(T - 1, -1, -1):
+            o1 = t["out1"][s]
+            _lib.check(L.lo_attention_backward(_lib.ptr(t["att1"]), _lib.ptr(enc_out), dt, _lib.ptr(o1), ctypes.c_void_p(o1.data_ptr() + A * 4), O1,
+                                               a.w_full, ctypes.c_void_p(t["alphas"].data_ptr() + s * R * 4), T * R, _lib.ptr(t["ctx"][s]),
+                                               _lib.ptr(t["dxh"]), DX, _lib.ptr(t["dreg"]), R, ctypes.c_void_p(t["sreg"].data_ptr() + s * 4), T,
+                                               ctypes.c_void_p(t["de"].data_ptr() + s * R * 4), _lib.ptr(t["dcat"][s]),
+                                               ctypes.c_void_p(t["dcat"][s].data_ptr() + A * 4), O1, _lib.ptr(t["dctx"][s]), None,
+                                               B, R, A, C, _lib.ptr(t["work"]), st))
+
+    ms_attb = _time_ms(att_bwd_steps, 3) / T
+    attb = {"kernel": "attention_bwd_pipe_kernel (d alpha, softmax backward, ReLU-mask sums, one decode step, TMA ring)", "bound": "hbm",
+            "achieved": att_bytes / (ms_attb * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+            "traffic": traffic_of("attention_bwd_pipe_kernel"), "us_per_launch": ms_attb * 1e3, "algorithmic_bytes": att_bytes,
+            "peak_source": pk["src"]}
+    attb["frac"] = attb["achieved"] / attb["peak"]
 
     img = enc_ws["img"]
     denc = t["denc"].view(B, enc_ws["out"].shape[1], enc_ws["out"].shape[2], C)
@@ -145,9 +170,14 @@ def kernel_probes(model, c, pk):
         _lib.check(L.lo_decoder_backward(ctypes.byref(a), st))
 
     ms_dec = _time_ms(dec_all, 2)
-    extra = {"decoder_fwd_bwd_ms": ms_dec, "encoder_fwd_bwd_ms": ms_conv, "attention_fwd_us_per_step": ms_att * 1e3}
-    dominant = conv if ms_conv >= T * ms_att * 2 else att
-    return {"dominant": dominant, "all": {"attention": att, "conv": conv, "conv_tensor_kernels": conv_tc_r, "phases": extra}}
+    extra = {"decoder_fwd_bwd_ms": ms_dec, "encoder_fwd_bwd_ms": ms_conv, "attention_fwd_us_per_step": ms_att * 1e3,
+             "attention_bwd_us_per_step": ms_attb * 1e3}
+    # the dominant kernel = the largest MEASURED share of the step among the kernels the north star names
+    share = {"attention_fwd": T * ms_att, "attention_bwd": T * ms_attb, "conv_tensor_kernels": ms_tc}
+    extra["kernel_share_ms"] = share
+    dominant = {"attention_fwd": att, "attention_bwd": attb, "conv_tensor_kernels": conv_tc_r}[max(share, key=share.get)]
+    return {"dominant": dominant, "all": {"attention": att, "attention_bwd": attb, "conv": conv, "conv_tensor_kernels": conv_tc_r,
+                                          "phases": extra}}
 
 
 def cpu_threads():

@@ -136,6 +136,19 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
                          float* gate_pre, int64_t gate_stride, float* gctx,
                          int B, int R, int A, int C, void* work, void* stream);
 
+/* Backward of one attention step (autograd of seq2seq_torch.py:186-190 + the gate of :311-312), reading att1 and enc ONCE:
+ *   dctx = dgctx * gate ; dgp = dgctx * ctx * gate (1 - gate) ; s = <dctx, ctx> + sreg[b]
+ *   dalpha_r = <dctx, enc_r> + dreg[b][r] ; de_r = alpha_r (dalpha_r - s) ; datt2_a = wf_a sum_r de_r [att1_ra + att2_a > 0]
+ * att2 / gate [B][o1_stride] fp32 as the forward left them (gate after the sigmoid; NULL = ungated context) ; alpha / de
+ * [B][alpha_stride] ; ctx / dctx_out [B][C] ; dgctx [B][dg_stride] ; dreg [B][dreg_stride] and sreg [B][sreg_stride] may be NULL ;
+ * datt2 / dgp [B][dcat_stride] ; dwf_part (optional) [B][A] += sum_r de_r relu(att1_r + att2) (full_att.weight gradient).
+ * d att1 and d enc are NOT produced here: they are hoisted out of the time loop (see lo_decoder_backward). */
+int lo_attention_backward(const void* att1, const void* enc, int dt, const float* att2, const float* gate, int64_t o1_stride,
+                          const float* wf, const float* alpha, int64_t alpha_stride, const float* ctx, const float* dgctx,
+                          int64_t dg_stride, const float* dreg, int64_t dreg_stride, const float* sreg, int64_t sreg_stride,
+                          float* de, float* datt2, float* dgp, int64_t dcat_stride, float* dctx_out, float* dwf_part,
+                          int B, int R, int A, int C, void* work, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Whole teacher-forced decoder: DecoderWithAttention.forward seq2seq_torch.py:267-320 (+ the loss of
  * img2seq_torch.py:147-159) and its hand-derived backward.  One struct carries every buffer; the
@@ -147,7 +160,9 @@ typedef struct lo_decoder_args {
   int32_t B, T, R, C, A, D, E, V;
   int32_t dt;              /* storage of enc/att1/weight shadows */
   int32_t impl;            /* LO_IMPL_SIMT | LO_IMPL_TC for the hoisted GEMMs */
-  int32_t has_dropout;     /* 0: eval ; 1: multiply h by dropout_mask before fc */
+  int32_t has_dropout;     /* 0: eval ; 1: multiply h by dropout_mask before fc (injected mask: parity tests) ;
+                              2: draw the inverted-dropout mask inside the LSTM kernels (Philox4x32-10 keyed by dropout_state,
+                                 regenerated in the backward; nothing is stored) */
   int32_t ldl;             /* row stride of logits/dlogits (>= V; a multiple of 64 enables the tcgen05 fc GEMMs); 0 -> V */
   float alpha_c;           /* doubly-stochastic regulariser weight (img2seq_torch.py:157) */
   int32_t rows_per_img;    /* decode only: consecutive rows that share one image (beam size); 0/1 for training */
@@ -181,6 +196,8 @@ typedef struct lo_decoder_args {
   float* gates;            /* [T][B][4D] post-activation i,f,g,o */
   float* gtmp;             /* [B][4D] scratch */
   const float* dropout_mask; /* [B][T][D] multipliers or NULL */
+  const uint64_t* dropout_state; /* has_dropout=2: device {seed, call counter}; lo_decoder_backward increments the counter */
+  float dropout_p;         /* has_dropout=2: drop probability (seq2seq_torch.py:216 nn.Dropout(p)) */
   float* hd;               /* [B][T][D] h after dropout */
   float* logits;           /* [B][T][ldl]  (== predictions in the first V columns) */
   /* loss */
@@ -239,6 +256,14 @@ int lo_decoder_greedy_hist(const lo_decoder_args* a, int64_t start_id, int64_t e
  * fin_hist [n_img][max_steps][beam] int32 (finished flags after each step), logp [n_img][beam] final scores. */
 int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* ids,
                     int64_t* parents, int32_t* fin_hist, float* logp, void* stream);
+/* the same with the diversity penalty of beam_search_decoder_cell.py:258-287 (Li et al. 2016; configs/model.json:15-16
+ * div_gamma / div_prob): every candidate's accumulated log-prob gets log(div_gamma) * (its rank inside its beam row, 0 = best)
+ * where div_prob > u, u ~ U[0,1) per (image, beam, token).  Off when div_gamma == 1 or div_prob == 0 (:270-273).
+ * div_u (optional) injects the uniforms [max_steps][B][V] (parity tests); otherwise they are drawn in the kernel from
+ * Philox4x32-10 keyed by div_state = device {seed, call counter}. */
+int lo_decoder_beam_div(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* ids,
+                        int64_t* parents, int32_t* fin_hist, float* logp, float div_gamma, float div_prob,
+                        const float* div_u, const uint64_t* div_state, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * TensorFlow-flavour decoder: the Genthial attention cell of
@@ -301,6 +326,9 @@ int lo_tfdec_greedy(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64
  * [n_img][max_steps][beam], logp [n_img][beam] */
 int lo_tfdec_beam(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents, int32_t* fin_hist,
                   float* logp, void* stream);
+/* with the diversity penalty (see lo_decoder_beam_div) */
+int lo_tfdec_beam_div(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents, int32_t* fin_hist,
+                      float* logp, float div_gamma, float div_prob, const float* div_u, const uint64_t* div_state, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimiser: torch.optim.Adam defaults (img2seq_torch.py:86-87, :168-170) on one flat buffer.

@@ -118,6 +118,30 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: the same (key, counter) gives the same 4 words in the forward and the
+// backward kernel, so dropout masks are regenerated instead of stored.  Host mirror: latex_ocr_b200/philox.py.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// uniform in [0, 1) with 24 bits
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// inverted-dropout multiplier of element (row b, step t, unit j): state = {seed, call counter} in device memory
+__device__ __forceinline__ float philox_dropout_mult(const unsigned long long* state, int b, int t, int j, float p, float scale) {
+  const unsigned long long seed = state[0], call = state[1];
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 2), (uint32_t)t, (uint32_t)b, (uint32_t)call),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w = (j & 3) == 0 ? r.x : ((j & 3) == 1 ? r.y : ((j & 3) == 2 ? r.z : r.w));
+  return u01(w) >= p ? scale : 0.f;
+}
+
 // host-side dtype dispatch: calls f(T*) with T = float or bf16
 #define LO_DISPATCH_DT(dt, T, ...)                   \
   do {                                               \

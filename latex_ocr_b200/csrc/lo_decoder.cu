@@ -385,7 +385,7 @@ __global__ void lstm_pw_fwd_kernel(const float* __restrict__ gtmp, const float* 
                                    int64_t hh_stride, const float* __restrict__ c_prev, float* __restrict__ gates,
                                    float* __restrict__ c_out, float* __restrict__ h_out, bf16* __restrict__ h_bf,
                                    float* __restrict__ hd, int64_t hd_stride, const float* __restrict__ dmask, int nrows, int D,
-                                   int V) {
+                                   int V, const unsigned long long* __restrict__ dstate, float dp, int row0, int t_idx) {
   pdl_wait();
   pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,7 +409,12 @@ __global__ void lstm_pw_fwd_kernel(const float* __restrict__ gtmp, const float* 
   c_out[(int64_t)b * D + j] = c;
   h_out[(int64_t)b * D + j] = h;
   if (h_bf) h_bf[(int64_t)b * D + j] = __float2bfloat16_rn(h);
-  if (hd) hd[(int64_t)b * hd_stride + j] = dmask ? h * dmask[(int64_t)b * hd_stride + j] : h;
+  if (hd) {
+    float mult = 1.f;
+    if (dmask) mult = dmask[(int64_t)b * hd_stride + j];                                           // injected mask (parity tests)
+    else if (dstate) mult = philox_dropout_mult(dstate, row0 + b, t_idx, j, dp, 1.f / (1.f - dp));  // drawn here, redrawn in the backward
+    hd[(int64_t)b * hd_stride + j] = h * mult;
+  }
 }
 
 // backward of the cell pointwise part: dh = dhd[b,t] + dh_next ; writes d(pre-activations), dc_prev in place
@@ -418,7 +423,8 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_st
                                    int64_t dhn_stride, float* __restrict__ dc, const float* __restrict__ gates,
                                    const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                                    float* __restrict__ dG, int64_t dG_stride, bf16* __restrict__ dG_bf, float* __restrict__ dxh_zero,
-                                   int C, int nrows, int D) {
+                                   int C, int nrows, int D, const unsigned long long* __restrict__ dstate, float dp, int row0,
+                                   int t_idx) {
   pdl_wait();
   pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -429,6 +435,7 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_st
   const float tc = tanhf(c_cur[(int64_t)b * D + j]);
   float dh = dhd[(int64_t)b * dhd_stride + j];
   if (dmask) dh *= dmask[(int64_t)b * dhd_stride + j];
+  else if (dstate) dh *= philox_dropout_mult(dstate, row0 + b, t_idx, j, dp, 1.f / (1.f - dp));
   dh += dh_next[(int64_t)b * dhn_stride + j];
   const float dct = dc[(int64_t)b * D + j] + dh * o * (1.f - tc * tc);
   float* d = dG + (int64_t)b * dG_stride;
@@ -645,8 +652,10 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const float* __restrict_
                                                         float* __restrict__ logp, int32_t* __restrict__ finished,
                                                         int64_t* __restrict__ ids, int64_t* __restrict__ parents,
                                                         int32_t* __restrict__ fin_hist, int64_t* __restrict__ next_tok,
-                                                        int32_t* __restrict__ parent_rows, int max_steps) {
-  extern __shared__ float s_tot[];            // [beam*V]
+                                                        int32_t* __restrict__ parent_rows, int max_steps, float div_log_gamma,
+                                                        float div_prob, const float* __restrict__ div_u,
+                                                        const unsigned long long* __restrict__ div_state) {
+  extern __shared__ float s_tot[];            // [beam*V] (+ [beam*V] penalties when the diversity penalty is on)
   __shared__ float s_red[8];
   __shared__ int s_redi[8];
   __shared__ float s_lse[LO_BEAM_MAX];
@@ -675,6 +684,33 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const float* __restrict_
     s_tot[i] = logp[row0 + k] + lp;
   }
   __syncthreads();
+  if (div_log_gamma != 0.f && div_prob > 0.f) {
+    // add_div_penalty (beam_search_decoder_cell.py:258-287, Li et al. 2016): rank of every candidate inside its beam row
+    // (0 = best; tf.nn.top_k(sorted) puts the lower index first among equals), penalty = log(gamma) * rank, applied where
+    // div_prob > u with u ~ U[0,1) per (image, beam, token) — injected (div_u, parity tests) or drawn from Philox
+    float* s_pen = s_tot + beam * V;
+    for (int i = tid; i < total; i += 256) {
+      const int k = i / V, v = i % V;
+      const float x = s_tot[i];
+      const float* rowp = s_tot + k * V;
+      int rank = 0;
+      for (int q = 0; q < V; q++) {
+        const float y = rowp[q];
+        rank += (y > x || (y == x && q < v)) ? 1 : 0;
+      }
+      float u;
+      if (div_u) u = div_u[(int64_t)(row0 + k) * V + v];
+      else {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(v >> 2), (uint32_t)t, (uint32_t)(row0 + k), (uint32_t)div_state[1]),
+                                      make_uint2((uint32_t)div_state[0], (uint32_t)(div_state[0] >> 32)));
+        u = u01((v & 3) == 0 ? r.x : ((v & 3) == 1 ? r.y : ((v & 3) == 2 ? r.z : r.w)));
+      }
+      s_pen[i] = div_prob > u ? div_log_gamma * (float)rank : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += 256) s_tot[i] += s_pen[i];
+    __syncthreads();
+  }
   for (int j = 0; j < beam; j++) {
     float best = -INFINITY;
     int bi = 0x7fffffff;
@@ -740,6 +776,8 @@ __global__ void fill_i64_kernel(int64_t* p, int64_t v, int n) {
   if (i < n) p[i] = v;
 }
 
+__global__ void bump_counter_kernel(unsigned long long* c) { *c += 1ull; }
+
 __global__ void dlen_kernel(int32_t* dlen, int B, int Tn, int full) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) dlen[i] = full;
@@ -788,6 +826,8 @@ static int check_args(const lo_decoder_args* a) {
   LO_CHECK_ARG(a->ldl == 0 || a->ldl >= a->V, "ldl >= V");
   LO_CHECK_ARG(a->rows_per_img <= 1 || a->B % a->rows_per_img == 0, "B must be a multiple of rows_per_img");
   LO_CHECK_ARG(a->bt_host && a->caps && a->enc && a->work, "null pointer");
+  LO_CHECK_ARG(a->has_dropout != 2 || (a->dropout_state && a->dropout_p >= 0.f && a->dropout_p < 1.f && !g_opt_fuse_lstm),
+               "has_dropout=2 needs dropout_state, 0 <= dropout_p < 1 and fuse_lstm=0");
   for (int t = 0; t < a->T; t++) {
     LO_CHECK_ARG(a->bt_host[t] >= 1 && a->bt_host[t] <= a->B, "bt_host out of range");
     if (t) LO_CHECK_ARG(a->bt_host[t] <= a->bt_host[t - 1], "bt_host must be non-increasing");
@@ -985,7 +1025,8 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
                      a->hall + ((int64_t)(t + 1) * d.B + r0) * d.D,
                      bv.on ? bv.hall + ((int64_t)(t + 1) * d.B + r0) * d.D : (bf16*)nullptr,
                      hd_t ? hd_t + r0 * hd_stride : (float*)nullptr, hd_stride,
-                     dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, nrows, d.D, d.V));
+                     dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, nrows, d.D, d.V,
+                     (const unsigned long long*)((hd_t && a->has_dropout == 2) ? a->dropout_state : nullptr), a->dropout_p, (int)r0, t));
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -1050,6 +1091,20 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
                                   B, R, C, work, (cudaStream_t)stream);
 }
 
+int lo_attention_backward(const void* att1, const void* enc, int dt, const float* att2, const float* gate, int64_t o1_stride,
+                          const float* wf, const float* alpha, int64_t alpha_stride, const float* ctx, const float* dgctx,
+                          int64_t dg_stride, const float* dreg, int64_t dreg_stride, const float* sreg, int64_t sreg_stride, float* de,
+                          float* datt2, float* dgp, int64_t dcat_stride, float* dctx_out, float* dwf_part, int B, int R, int A, int C,
+                          void* work, void* stream) {
+  LO_CHECK_ARG(att1 && enc && att2 && wf && alpha && ctx && dgctx && de && datt2 && work, "null pointer");
+  LO_CHECK_ARG(A == C && (C == 256 || C == 512 || C == 1024), "attention_dim == encoder_dim in {256,512,1024}");
+  LO_CHECK_ARG(B > 0 && B <= 512 && R > 0, "B in 1..512, R > 0");
+  LO_CHECK_ARG(g_opt_att_pipe, "stand-alone attention backward runs on the TMA-ring kernel (option att_pipe=1)");
+  AttBwdArgs x{att1, enc, att2, gate, o1_stride, wf, alpha, alpha_stride, ctx, dgctx, dg_stride, dreg, dreg_stride, sreg, sreg_stride,
+               de, datt2, dgp, dcat_stride, nullptr, nullptr, dctx_out, B, R, work, dwf_part, 0};
+  return attention_bwd_pipe(x, dt, C, (cudaStream_t)stream);
+}
+
 int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
   LO_TRY(check_args(a));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1070,7 +1125,7 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
   for (int chain = 0; chain < nchains; chain++) {
     cudaStream_t cs = chain == 0 ? st : g_side;
     for (int t = 0; t < d.T; t++) {
-      const float* dm = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+      const float* dm = (a->has_dropout == 1 && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
       const Rows rs = chain_rows(a, d, chain, nchains, a->bt_host[t]);
       LO_TRY(forward_step(a, d, t, rs, a->caps + t, a->caps_stride, a->hd + (int64_t)t * d.D, (int64_t)d.T * d.D, dm, cs));
     }
@@ -1189,13 +1244,14 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     bf16* dcat_bf_t = bv.on ? bv.dcat + ((int64_t)t * d.B + r0) * d.O1 : nullptr;
     const float* o1 = a->out1 + ((int64_t)t * d.B + r0) * d.O1;
     float* dxh = a->dxh + r0 * (d.C + d.D);
-    const float* dmul = (a->has_dropout && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D + r0 * d.T * d.D : nullptr;
+    const float* dmul = (a->has_dropout == 1 && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D + r0 * d.T * d.D : nullptr;
     LO_CUDA(launch_pdl(lstm_pw_bwd_kernel, dim3(cdiv((long)nrows * d.D, 256)), dim3(256), (size_t)0, st,
                        (const float*)(a->dhd + (int64_t)t * d.D + r0 * d.T * d.D), (int64_t)d.T * d.D, dmul, (const float*)(dxh + d.C),
                        (int64_t)(d.C + d.D), a->dc + r0 * d.D, (const float*)(a->gates + ((int64_t)t * d.B + r0) * d.G),
                        (const float*)(a->call + ((int64_t)t * d.B + r0) * d.D),
                        (const float*)(a->call + ((int64_t)(t + 1) * d.B + r0) * d.D), dcat_t + d.A + d.C, (int64_t)d.O1,
-                       bv.on ? dcat_bf_t + d.A + d.C : (bf16*)nullptr, bv.on ? dxh : (float*)nullptr, d.C, nrows, d.D));
+                       bv.on ? dcat_bf_t + d.A + d.C : (bf16*)nullptr, bv.on ? dxh : (float*)nullptr, d.C, nrows, d.D,
+                       (const unsigned long long*)(a->has_dropout == 2 ? a->dropout_state : nullptr), a->dropout_p, (int)r0, t));
     LO_LAUNCH_OK();
     // [dgctx | dh_prev] = dG @ [W_ih[:, E:] | W_hh]
     if (bv.on && g_opt_skinny_mma && nrows <= 64) {
@@ -1341,6 +1397,11 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     add_rowbcast_kernel<<<148 * 8, 256, 0, st>>>(a->denc, a->dmean, d.R, d.C, 1.0f / (float)d.R, total);
     LO_LAUNCH_OK();
   }
+  if (a->has_dropout == 2) {
+    // forward and backward of this step drew the same Philox stream; the next step (also a graph replay) gets a new one
+    bump_counter_kernel<<<1, 1, 0, st>>>((unsigned long long*)a->dropout_state + 1);
+    LO_LAUNCH_OK();
+  }
   return LO_OK;
 }
 
@@ -1382,11 +1443,19 @@ int lo_decoder_greedy(const lo_decoder_args* a, int64_t start_id, int64_t end_id
 
 int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents,
                     int32_t* fin_hist, float* logp, void* stream) {
+  return lo_decoder_beam_div(a, start_id, end_id, max_steps, ids, parents, fin_hist, logp, 1.f, 0.f, nullptr, nullptr, stream);
+}
+
+int lo_decoder_beam_div(const lo_decoder_args* a, int64_t start_id, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents,
+                        int32_t* fin_hist, float* logp, float div_gamma, float div_prob, const float* div_u,
+                        const uint64_t* div_state, void* stream) {
   LO_TRY(check_args(a));
+  const bool div_on = !(div_gamma == 1.f || div_prob == 0.f);               // beam_search_decoder_cell.py:270-273
+  LO_CHECK_ARG(!div_on || (div_gamma > 0.f && (div_u || div_state)), "diversity penalty needs gamma > 0 and div_u or div_state");
   const int beam = a->rows_per_img;
   LO_CHECK_ARG(beam >= 1 && beam <= LO_BEAM_MAX && a->B % beam == 0, "1 <= beam (rows_per_img) <= 16, B % beam == 0");
   LO_CHECK_ARG(ids && parents && fin_hist && logp && max_steps > 0 && max_steps <= a->T, "outputs / max_steps (<= T capacity)");
-  LO_CHECK_ARG((size_t)beam * a->V * 4 <= 200 * 1024, "beam*V too large for the shared-memory top-k");
+  LO_CHECK_ARG((size_t)beam * a->V * 4 * (div_on ? 2 : 1) <= 200 * 1024, "beam*V too large for the shared-memory top-k");
   cudaStream_t st = (cudaStream_t)stream;
   const Dims d = dims(a);
   const int n_img = d.B / beam;
@@ -1401,7 +1470,7 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
   LO_CUDA(cudaMemsetAsync(logp, 0, (size_t)d.B * 4, st));          // initial log-probs are zeros (:106-107)
   LO_TRY(forward_prologue(a, d, st));
   const BfViews bv = bf_views(a, d);
-  const size_t smem = (size_t)beam * d.V * 4;
+  const size_t smem = (size_t)beam * d.V * 4 * (div_on ? 2 : 1);
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     LO_CUDA(cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1417,7 +1486,9 @@ int lo_decoder_beam(const lo_decoder_args* a, int64_t start_id, int64_t end_id, 
     else
       LO_TRY(gemm_nt(h_new, LO_F32, d.D, a->w_fc, a->dt, d.D, a->logits, LO_F32, d.V, d.B, d.V, d.D, a->b_fc, 0, 0, LO_IMPL_SIMT, st));
     beam_step_kernel<<<n_img, 256, smem, st>>>(a->logits, d.V, beam, t, end_id, logp, finished, ids, parents, fin_hist, next_tok,
-                                               parent_rows, max_steps);
+                                               parent_rows, max_steps, div_on ? logf(div_gamma) : 0.f, div_on ? div_prob : 0.f,
+                                               div_u ? div_u + (int64_t)t * d.B * d.V : (const float*)nullptr,
+                                               (const unsigned long long*)div_state);
     LO_LAUNCH_OK();
     // reorder the recurrent state by parents (through gtmp as a temporary)
     gather_rows_kernel<<<cdiv((long)d.B * d.D, 256), 256, 0, st>>>(h_new, parent_rows, a->gtmp, d.B, d.D);

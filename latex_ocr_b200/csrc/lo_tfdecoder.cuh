@@ -586,7 +586,14 @@ int lo_tfdec_greedy(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64
 
 int lo_tfdec_beam(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents, int32_t* fin_hist, float* logp,
                   void* stream) {
+  return lo_tfdec_beam_div(a, end_id, max_steps, ids, parents, fin_hist, logp, 1.f, 0.f, nullptr, nullptr, stream);
+}
+
+int lo_tfdec_beam_div(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents, int32_t* fin_hist,
+                      float* logp, float div_gamma, float div_prob, const float* div_u, const uint64_t* div_state, void* stream) {
   LO_TRY(tf_check(a));
+  const bool div_on = !(div_gamma == 1.f || div_prob == 0.f);               // beam_search_decoder_cell.py:270-273
+  LO_CHECK_ARG(!div_on || (div_gamma > 0.f && (div_u || div_state)), "diversity penalty needs gamma > 0 and div_u or div_state");
   LO_CHECK_ARG(ids && parents && fin_hist && logp && max_steps > 0 && max_steps <= a->T, "outputs / max_steps (<= T capacity)");
   cudaStream_t st = (cudaStream_t)stream;
   const TfDims d = tf_dims(a);
@@ -596,14 +603,17 @@ int lo_tfdec_beam(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t
   LO_CUDA(cudaMemsetAsync(w.finished, 0, (size_t)d.B * 4, st));
   LO_CUDA(cudaMemsetAsync(logp, 0, (size_t)d.B * 4, st));                    // initial log-probs are zeros (:106-107)
   LO_TRY(tf_prologue(a, d, w, st));
-  const size_t smem = (size_t)beam * d.V * 4;
+  const size_t smem = (size_t)beam * d.V * 4 * (div_on ? 2 : 1);
+  LO_CHECK_ARG(smem <= 200 * 1024, "beam*V too large for the shared-memory top-k");
   if (smem > 48 * 1024) LO_CUDA(cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   for (int t = 0; t < max_steps; t++) {
     LO_TRY(tf_step(a, d, w, t, t == 0 ? nullptr : w.next_tok, 1, st));
     const int64_t rown = (int64_t)(t + 1) * d.B;
     LO_TRY(tf_logits(a, d, w, rown, d.B, a->logits, d.V, st));
     beam_step_kernel<<<d.nimg, 256, smem, st>>>(a->logits, d.V, beam, t, end_id, logp, w.finished, ids, parents, fin_hist, w.next_tok,
-                                                w.parent_rows, max_steps);
+                                                w.parent_rows, max_steps, div_on ? logf(div_gamma) : 0.f, div_on ? div_prob : 0.f,
+                                                div_u ? div_u + (int64_t)t * d.B * d.V : (const float*)nullptr,
+                                                (const unsigned long long*)div_state);
     LO_LAUNCH_OK();
     // reorder the cell state (c, h, o) by parents (gather_helper, beam_search_decoder_cell.py:370-391)
     tf_gather_rows_kernel<<<cdiv((long)d.B * d.XH, 256), 256, 0, st>>>(w.xh + rown * d.XH, w.parent_rows, w.gtmp,

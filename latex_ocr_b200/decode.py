@@ -42,8 +42,10 @@ def _prepare(model, img, rows_per_img, max_steps):
     return a, ws, N
 
 
-def greedy_decode(model, img, start_id, end_id, max_length_formula=150):
-    """Returns token ids [N, steps] (CPU int64), steps as the reference's loop would have run."""
+def greedy_decode(model, img, start_id, end_id, max_length_formula=150, return_attention=False):
+    """Returns token ids [N, steps] (CPU int64), steps as the reference's loop would have run.  ``return_attention=True`` also
+    returns the attention weights of every step, [N, steps, R] fp32 on the CPU — what the reference collects in
+    ``attention_mechanism.ctx_vector`` for visualize_attention.py (attention_mechanism.py:96-121)."""
     L = _lib.lib()
     max_steps = max_length_formula + 2
     with torch.no_grad():
@@ -55,15 +57,26 @@ def greedy_decode(model, img, start_id, end_id, max_length_formula=150):
         check(L.lo_decoder_greedy_hist(ctypes.byref(a), int(start_id), int(end_id), max_steps, tokens.data_ptr(), finished.data_ptr(),
                                        hist.data_ptr(), stream_ptr()))
         n = _n_steps(hist.cpu())
+        if return_attention:
+            return tokens[:, :n].cpu(), ws["t"]["alphas"][:, :n].float().cpu()
         return tokens[:, :n].cpu()
 
 
+def attention_maps(alphas, att_h, att_w):
+    """visualize_attention.py:49-72 (getOutArray): an attention vector over the R = att_h * att_w regions as a grey image,
+    region r at (r // att_w, r % att_w), value (1 - alpha) * 255 (dark = attended).  alphas [..., R] -> float [..., att_h, att_w]."""
+    a = torch.as_tensor(alphas, dtype=torch.float32)
+    if a.shape[-1] != att_h * att_w:
+        raise ValueError("attention vector of %d regions does not match a %dx%d feature map" % (a.shape[-1], att_h, att_w))
+    return ((1.0 - a) * 255.0).reshape(tuple(a.shape[:-1]) + (att_h, att_w))
+
+
 def beam_decode(model, img, start_id, end_id, beam_size=5, max_length_formula=150, finalize="reference",
-                div_gamma=1, div_prob=0):
+                div_gamma=1, div_prob=0, div_u=None, div_seed=None):
     """Returns (ids [N, beam, steps], log_probs [N, beam]) on the CPU; hypothesis 0 is the one the reference scores
-    (img2seq.py:210)."""
-    if not (div_gamma == 1 or div_prob == 0):
-        raise NotImplementedError("diversity penalty (beam_search_decoder_cell.py:258-287) is off in the shipped config and not implemented")
+    (img2seq.py:210).  ``div_gamma`` / ``div_prob``: the diversity penalty of beam_search_decoder_cell.py:258-287 (off when
+    gamma == 1 or prob == 0, as in configs/model.json:15-16); its Bernoulli draws come from the in-kernel Philox stream seeded
+    by ``div_seed`` (default: torch's initial seed), or from ``div_u`` — uniforms [steps, N*beam, V] — when given (tests)."""
     if finalize not in ("reference", "backtrack"):
         raise NotImplementedError("finalize must be 'reference' or 'backtrack'")
     L = _lib.lib()
@@ -75,8 +88,19 @@ def beam_decode(model, img, start_id, end_id, beam_size=5, max_length_formula=15
         parents = torch.zeros_like(ids)
         hist = torch.zeros(N, max_steps, beam_size, dtype=torch.int32, device=dev)
         logp = torch.zeros(N, beam_size, dtype=torch.float32, device=dev)
-        check(L.lo_decoder_beam(ctypes.byref(a), int(start_id), int(end_id), max_steps, ids.data_ptr(), parents.data_ptr(),
-                                hist.data_ptr(), logp.data_ptr(), stream_ptr()))
+        div_on = not (div_gamma == 1 or div_prob == 0)
+        u_dev = state = None
+        if div_on and div_u is not None:
+            u_dev = torch.as_tensor(div_u, dtype=torch.float32).to(dev).contiguous()
+            if tuple(u_dev.shape) != (max_steps, N * beam_size, a.V):
+                raise ValueError("div_u must be [max_length_formula + 2, N * beam, V]")
+        elif div_on:
+            seed = torch.initial_seed() if div_seed is None else int(div_seed)
+            state = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+        check(L.lo_decoder_beam_div(ctypes.byref(a), int(start_id), int(end_id), max_steps, ids.data_ptr(), parents.data_ptr(),
+                                    hist.data_ptr(), logp.data_ptr(), float(div_gamma), float(div_prob),
+                                    u_dev.data_ptr() if u_dev is not None else None,
+                                    state.data_ptr() if state is not None else None, stream_ptr()))
         n = _n_steps(hist.cpu())
         ids, parents = ids[:, :n].cpu(), parents[:, :n].cpu()
         if finalize == "backtrack":

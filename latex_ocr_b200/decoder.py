@@ -120,6 +120,12 @@ class DecoderWithAttention(nn.Module):
         self.reset_parameters()
         self._ws = LRUCache()     # bounded: see params.LRUCache
         self._shadow_fresh = False
+        # in-kernel dropout (has_dropout=2): device {seed, call counter}; the counter is advanced by lo_decoder_backward, so
+        # CUDA-graph replays draw a fresh mask every step
+        self.dropout_state = torch.tensor([int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+
+    def seed_dropout(self, seed, call=0):
+        self.dropout_state.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(call)], dtype=torch.int64))
 
     def reset_parameters(self):
         A, E, D, V, C = self.attention_dim, self.embed_dim, self.decoder_dim, self.vocab_size, self.encoder_dim
@@ -204,7 +210,7 @@ class DecoderWithAttention(nn.Module):
             t["loss"] = z(4)
             t["sreg"] = z(B, max(T, 2))
             t["work"] = z(int(_lib.lib().lo_decoder_workspace_bytes(B, max(A, C))), dtype=torch.uint8)
-            t["dropout_mask"] = z(B, T, D)
+            t["dropout_mask"] = None             # [B,T,D] allocated on first use of an injected mask
             ws["bt"] = (ctypes.c_int32 * T)(*([B] * T))
             self._ws[key] = ws
         if need_grad and not ws["need_grad"]:
@@ -238,7 +244,9 @@ class DecoderWithAttention(nn.Module):
         a.C, a.A, a.D, a.E, a.V = self.encoder_dim, self.attention_dim, self.decoder_dim, self.embed_dim, self.vocab_size
         a.dt = _dt(self.precision)
         a.impl = _lib.LO_IMPL_TC if (self.impl == "tc" and self.precision == "bf16") else _lib.LO_IMPL_SIMT
-        a.has_dropout = 1 if has_dropout else 0
+        a.has_dropout = int(has_dropout)           # 0 eval, 1 injected mask, 2 in-kernel Philox
+        a.dropout_state = self.dropout_state.data_ptr()
+        a.dropout_p = float(self.dropout_p)
         a.ldl = ws["ldl"]
         a.alpha_c = float(self.alpha_c)
         a.bt_host = ctypes.cast(ws["bt"], ctypes.c_void_p)
@@ -263,8 +271,10 @@ class DecoderWithAttention(nn.Module):
         a.w_init, a.b_init = W("init_h.weight"), F("init_h.bias")
         a.w_fc, a.b_fc = W("fc.weight"), F("fc.bias")
         for k in ("att1", "ptab", "mean", "hall", "call", "out1", "alphas", "ctx", "gctx", "gates", "gtmp", "hd", "logits",
-                  "row_loss", "loss", "sreg", "work", "dropout_mask"):
+                  "row_loss", "loss", "sreg", "work"):
             setattr(a, k, t[k].data_ptr())
+        if t.get("dropout_mask") is not None:
+            a.dropout_mask = t["dropout_mask"].data_ptr()
         if ws["need_grad"]:
             for k in ("wbwd1", "wbwd2", "dlogits", "dhd", "dreg", "dcat", "dxh", "dc", "dctx", "de", "dptab", "datt1", "denc",
                       "dinit", "dmean"):
@@ -305,7 +315,9 @@ class DecoderWithAttention(nn.Module):
             return hc[0], hc[1]
 
     def run_forward(self, enc_flat, caps_sorted, decode_lengths, with_loss, need_grad, dropout_mask=None):
-        """enc_flat: storage-dtype CUDA [B,R,C] (sorted rows); caps_sorted: CUDA int64 [B,T+1]."""
+        """enc_flat: storage-dtype CUDA [B,R,C] (sorted rows); caps_sorted: CUDA int64 [B,T+1].
+        dropout_mask: None (no dropout), a [B,T,D] tensor of multipliers (injected, parity tests) or the string "philox"
+        (mask drawn inside the kernels)."""
         L = _lib.lib()
         B, R, _ = enc_flat.shape
         T = max(decode_lengths)
@@ -313,8 +325,11 @@ class DecoderWithAttention(nn.Module):
         self.sync_shadow()
         ws["t"]["caps"].copy_(caps_sorted[:, :T + 1])
         self.set_lengths(ws, decode_lengths, B, T)
-        has_do = dropout_mask is not None
-        if has_do:
+        has_do = 0 if dropout_mask is None else (2 if isinstance(dropout_mask, str) else 1)
+        if has_do == 1:
+            if ws["t"].get("dropout_mask") is None:
+                ws["t"]["dropout_mask"] = torch.zeros(B, T, self.decoder_dim, dtype=torch.float32, device=self.store.device)
+                ws.pop("args", None)
             ws["t"]["dropout_mask"].copy_(dropout_mask)
         a = self.fill_args(ws, enc_flat, B, T, R, has_do)
         check(L.lo_decoder_forward(ctypes.byref(a), 1 if with_loss else 0, stream_ptr()))
@@ -323,11 +338,16 @@ class DecoderWithAttention(nn.Module):
     def run_backward(self, ws):
         check(_lib.lib().lo_decoder_backward(ctypes.byref(ws["args"]), stream_ptr()))
 
-    def make_dropout_mask(self, B, T):
-        """Inverted-dropout multipliers for h before fc (seq2seq_torch.py:316), in sorted row order."""
+    def make_dropout_mask(self, B, T, materialize=False):
+        """Dropout of h before fc (seq2seq_torch.py:316).  Training mode: "philox" = the inverted-dropout multipliers are drawn
+        inside the LSTM kernels (csrc/lo_common.cuh:philox_dropout_mult) and redrawn in the backward — no mask tensor, no torch
+        RNG launch; ``materialize=True`` returns the [B,T,D] tensor of torch-drawn multipliers instead (the injected-mask path
+        the parity tests use)."""
         p = self.dropout_p
         if not self.training or p <= 0.0:
             return None
+        if not materialize:
+            return "philox"
         keep = torch.rand(B, T, self.decoder_dim, device=self.store.device) >= p
         return keep.float() / (1.0 - p)
 
@@ -349,6 +369,8 @@ class DecoderWithAttention(nn.Module):
             T = max(decode_lengths)
             mask = self.make_dropout_mask(B, T)
             ws = self.run_forward(enc, caps, decode_lengths, with_loss=False, need_grad=False, dropout_mask=mask)
+            if isinstance(mask, str):
+                self.dropout_state[1] += 1       # forward-only call: no lo_decoder_backward to advance the Philox call counter
             preds = ws["t"]["logits"][:, :, :self.vocab_size].clone()
             alphas = ws["t"]["alphas"].clone()
             if min(decode_lengths) < T:      # rows that stopped decoding keep zeros (:301-302, :317-318)

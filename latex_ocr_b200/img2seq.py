@@ -231,20 +231,26 @@ class Img2SeqModel:
         return score
 
     def train(self, config, train_set, val_set, lr_schedule):
-        """base_torch.py:169-206 (epoch loop; best-score bookkeeping)."""
+        """base_torch.py:169-206 / base.py:95-140: epoch loop, weights saved whenever the epoch score is a new best (>=), early
+        stopping through ``lr_schedule.stop_training``.  Resume (base.py:40-47, :107-108): epochs below ``self.startepoch`` —
+        set by ``restore_latest()`` from the newest ``model.cpkt-<epoch>`` — are skipped."""
         best_score = None
         for epoch in range(config.n_epochs):
+            if epoch < getattr(self, "startepoch", 0):
+                continue
             score = self._run_train_epoch(config, train_set, val_set, epoch, lr_schedule)
             if best_score is None or score >= best_score:
                 best_score = score
+                if self._dir_output is not None:
+                    self.save_session(epoch)
             if lr_schedule is not None and getattr(lr_schedule, "stop_training", False):
                 break
         return best_score
 
-    # --- inference: img2seq.py:256-285 (TF surface) ------------------------------------------------------
-    def predict_batch(self, images, start_id=None, decoding=None, beam_size=None):
-        """images: float tensor [N,1,H,W].  Returns list[beam][N] of token-id lists truncated at END
-        (greedy: one hypothesis), like Img2SeqModel.predict_batch of the TF path."""
+    # --- inference / evaluation: img2seq.py:198-285 (TF surface) ----------------------------------------
+    def _decode_ids(self, images, start_id=None, decoding=None, beam_size=None):
+        """Token ids per hypothesis rank: list[n_hyp][N] of id lists (NOT truncated), as ``pred_test.ids`` after the
+        reshapes of img2seq.py:236-241 / :265-268."""
         from . import decode
         decoding = decoding or getattr(self._config, "decoding", "greedy")
         end_id = self._vocab.id_end if self._vocab is not None else self._n_tok - 1
@@ -252,51 +258,91 @@ class Img2SeqModel:
         L = int(getattr(self._config, "max_length_formula", 150))
         self.train_mode(False)
         if decoding == "greedy":
-            ids = decode.greedy_decode(self, images, start_id, end_id, L)
-            return [decode.truncate_end(ids.tolist(), end_id)]
+            return [decode.greedy_decode(self, images, start_id, end_id, L).tolist()], end_id
+        if decoding != "beam_search" and decoding != "beam":
+            raise NotImplementedError("decoding=%r: 'greedy' or 'beam_search' (model.json:13)" % (decoding,))
         beam = int(beam_size or getattr(self._config, "beam_size", 5))
-        ids, _ = decode.beam_decode(self, images, start_id, end_id, beam, L)
-        return [decode.truncate_end(ids[:, k].tolist(), end_id) for k in range(beam)]
+        ids, _ = decode.beam_decode(self, images, start_id, end_id, beam, L,
+                                    div_gamma=float(getattr(self._config, "div_gamma", 1)),
+                                    div_prob=float(getattr(self._config, "div_prob", 0)))
+        return [ids[:, k].tolist() for k in range(beam)], end_id
 
-    def evaluate(self, config, test_set, start_id=None):
-        """Evaluation with the TF path's semantics (img2seq.py:198-254; the torch path's own evaluate is broken, SURVEY
-        quirk Q6): teacher-forced perplexity exp(sum CE / n_tokens) over the real tokens (+END), and BLEU-4 / edit distance /
-        exact match of the decoded formulas.  Returns the score dict with ``perplexity`` negated like img2seq.py:252 so that
-        'higher is better' model selection works."""
-        from . import decode, metrics
+    def predict_batch(self, images, start_id=None, decoding=None, beam_size=None):
+        """img2seq.py:256-277.  images: tensor [N,1,H,W] (float or uint8) or a list of HxWx1 arrays (padded like
+        ``pad_batch_images``).  Returns list[n_hyp][N]: each prediction truncated at END and, when the vocabulary has an
+        ``id_to_tok`` table, joined into the formula string like the reference (token-id lists otherwise)."""
+        from . import decode
+        if not torch.is_tensor(images):
+            from .data import pad_batch_images
+            images = torch.from_numpy(pad_batch_images(list(images))).permute(0, 3, 1, 2).contiguous()
+        hyps, end_id = self._decode_ids(images, start_id, decoding, beam_size)
+        rev = getattr(self._vocab, "id_to_tok", None)
+        out = []
+        for hyp in hyps:
+            trunc = decode.truncate_end(hyp, end_id)
+            out.append([" ".join(rev[i] for i in p) for p in trunc] if rev is not None else trunc)
+        return out
+
+    def predict(self, img):
+        """img2seq.py:278-285: one image, one string (or id list) per hypothesis rank."""
+        return [hyp[0] for hyp in self.predict_batch([img])]
+
+    def _teacher_forced_ce(self, img, formula_t, lens, start_id):
+        """(sum of CE over the real tokens incl. END, number of such tokens) of one padded batch — ``ce_words`` / ``n_words`` of
+        img2seq.py:72-75 on the torch-flavour decoder (inputs prefixed with START, targets = tokens then END)."""
+        inp = torch.cat([torch.full((formula_t.shape[0], 1), start_id, dtype=torch.int64), formula_t], dim=1)
+        enc = self.encoder(img.to(self.device))
+        preds, caps, dl, _, _ = self.decoder(enc, inp.to(self.device), lens + 1)
+        tgt = caps[:, 1:]
+        ce_sum, n_tok = 0.0, 0
+        for b, n in enumerate(dl):
+            lp = torch.log_softmax(preds[b, :n].float(), dim=-1)                 # host-side metric arithmetic (plumbing)
+            ce_sum += float(-lp.gather(1, tgt[b, :n].unsqueeze(1)).sum().item())
+            n_tok += int(n)
+        return ce_sum, n_tok
+
+    def write_prediction(self, config, test_set, start_id=None):
+        """img2seq.py:215-254: decodes the whole set, writes ``ref.txt`` / ``hyp_<i>.txt`` under ``config.dir_answers`` through
+        ``write_answers`` and returns (files, perplexity) with perplexity = -exp(sum CE / n_words) (negated so that 'higher
+        is better' model selection works, :252)."""
+        from . import metrics
         from .data import minibatches, pad_batch_formulas, pad_batch_images
         self.train_mode(False)
         end_id, pad_id = self._vocab.id_end, self._vocab.id_pad
         start_id = pad_id if start_id is None else start_id
-        refs, hyps = [], []
-        ce_sum, n_tok = 0.0, 0
-        decoding = getattr(self._config, "decoding", "greedy")
-        L = int(getattr(self._config, "max_length_formula", 150))
+        refs, hyps = [], None
+        ce_words, n_words = 0.0, 0
         for imgs, formulas in minibatches(test_set, config.batch_size):
             img = torch.from_numpy(pad_batch_images(imgs)).permute(0, 3, 1, 2).contiguous()
             formula, length = pad_batch_formulas(formulas, pad_id, end_id)
-            formula_t = torch.from_numpy(formula.astype(np.int64))
-            lens = torch.from_numpy(length.astype(np.int64)).unsqueeze(1)
-            # teacher-forced scores over the true lengths (START-prefixed inputs, targets = tokens then END)
-            inp = torch.cat([torch.full((formula_t.shape[0], 1), start_id, dtype=torch.int64), formula_t], dim=1)
-            enc = self.encoder(img.to(self.device))
-            preds, caps, dl, _, _ = self.decoder(enc, inp.to(self.device), lens + 1)
-            tgt = caps[:, 1:]
-            for b, n in enumerate(dl):
-                lp = torch.log_softmax(preds[b, :n].float(), dim=-1)                 # host-side metric arithmetic (plumbing)
-                ce_sum += float(-lp.gather(1, tgt[b, :n].unsqueeze(1)).sum().item())
-                n_tok += int(n)
-            if decoding == "greedy":
-                ids = decode.greedy_decode(self, img, start_id, end_id, L)
-                hyp = decode.truncate_end(ids.tolist(), end_id)
-            else:
-                ids, _ = decode.beam_decode(self, img, start_id, end_id, int(getattr(self._config, "beam_size", 5)), L)
-                hyp = decode.truncate_end(ids[:, 0].tolist(), end_id)
+            ce, n = self._teacher_forced_ce(img, torch.from_numpy(formula.astype(np.int64)),
+                                            torch.from_numpy(length.astype(np.int64)).unsqueeze(1), start_id)
+            ce_words += ce
+            n_words += n
+            ids, _ = self._decode_ids(img, start_id)
+            if hyps is None:
+                hyps = [[] for _ in ids]
+            for k, h in enumerate(ids):
+                hyps[k] += h
             refs += [list(map(int, f)) for f in formulas]
-            hyps += hyp
-        scores = metrics.score(refs, hyps)
-        scores["perplexity"] = -float(np.exp(ce_sum / max(n_tok, 1)))
+        rev = getattr(self._vocab, "id_to_tok", None) or {i: str(i) for i in range(self._n_tok)}
+        dir_answers = getattr(config, "dir_answers", None) or os.path.join(self._dir_output or ".", "answers") + os.sep
+        files = metrics.write_answers(refs, hyps or [[]], rev, dir_answers, end_id)
+        perp = -float(np.exp(ce_words / float(max(n_words, 1))))
+        return files, perp
+
+    def _run_evaluate(self, config, test_set):
+        """img2seq.py:198-213: scores of hypothesis 0 against the references through the answer files."""
+        from . import metrics
+        files, perp = self.write_prediction(config, test_set)
+        scores = metrics.score_files(files[0], files[1])
+        scores["perplexity"] = perp
         return scores
+
+    def evaluate(self, config, test_set, start_id=None):
+        """base.py:142-160 with the TF path's evaluation semantics (the torch path's own evaluate is broken, SURVEY quirk
+        Q6): BLEU-4 / edit distance / exact match of hypothesis 0 + negated perplexity."""
+        return self._run_evaluate(config, test_set)
 
     # --- checkpoints: state_dict round-trips with the reference modules ----------------------------
     def state_dict(self):
@@ -305,11 +351,86 @@ class Img2SeqModel:
     def load_state_dict(self, sd):
         self.encoder.load_state_dict(sd["encoder"])
         self.decoder.load_state_dict(sd["decoder"])
+        self._graphs.clear()                         # captured steps hold the old bf16 shadows' VALUES only through memory
+        self.encoder._shadow_fresh = False           # that stays valid, but force the shadows to be rebuilt from the masters
+        self.decoder._shadow_fresh = False
 
     def save(self, path=None):
         path = path or os.path.join(self._dir_output or ".", "model.pt")
         torch.save({k: {n: t.detach().cpu().contiguous() for n, t in v.items()} for k, v in self.state_dict().items()}, path)
         return path
 
-    def restore(self, path):
-        self.load_state_dict(torch.load(path, map_location=self.device))
+    def restore(self, path=None, map_location=None):
+        """base_torch.py:150-160 (``model_path=None`` -> the default path of ``save()``)."""
+        path = path or os.path.join(self._dir_output or ".", "model.pt")
+        self.load_state_dict(torch.load(path, map_location=map_location or self.device))
+
+    def auto_restore(self):
+        """base_torch.py:146-148: restore the default checkpoint if it exists."""
+        path = os.path.join(self._dir_output or ".", "model.pt")
+        if os.path.isfile(path):
+            self.restore(path)
+            return True
+        return False
+
+    # TF-style epoch checkpoints (base.py:33-69): ``<dir_output>/model_weights/model.cpkt-<epoch>``, ``max_to_keep=1``,
+    # and on start-up the newest one is loaded and its epoch becomes ``startepoch``
+    def _dir_model(self):
+        return os.path.join(self._dir_output or ".", "model_weights")
+
+    @staticmethod
+    def _ckpt_epoch(name):
+        idx = name.find("-")                         # base.py:45-46
+        try:
+            return int(name[idx + 1:].split(".")[0]) if idx >= 0 else None
+        except ValueError:
+            return None
+
+    def save_session(self, epoch):
+        """base.py:60-68 (tf.train.Saver(max_to_keep=1).save(..., global_step=epoch)): parameters AND both Adam states, so a
+        resumed run continues the same optimisation."""
+        d = self._dir_model()
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, "model.cpkt-%d" % epoch)
+        blob = {"epoch": int(epoch), "state_dict": {k: {n: t.detach().cpu().contiguous() for n, t in v.items()}
+                                                    for k, v in self.state_dict().items()}}
+        opt = {}
+        for name, mod in (("encoder", self.encoder), ("decoder", self.decoder)):
+            S = mod.store
+            if S.m is not None:
+                opt[name] = {"m": S.m.cpu(), "v": S.v.cpu(), "adam_state": S.adam_state.cpu()}
+        blob["optimizer"] = opt
+        torch.save(blob, path + ".tmp")
+        os.replace(path + ".tmp", path)
+        for f in os.listdir(d):                      # max_to_keep=1
+            if f.startswith("model.cpkt-") and f != os.path.basename(path) and not f.endswith(".tmp"):
+                os.remove(os.path.join(d, f))
+        return path
+
+    def latest_checkpoint(self):
+        d = self._dir_model()
+        if not os.path.isdir(d):
+            return None
+        c = [(self._ckpt_epoch(f), f) for f in os.listdir(d) if f.startswith("model.cpkt-") and not f.endswith(".tmp")]
+        c = [x for x in c if x[0] is not None]
+        return os.path.join(d, max(c)[1]) if c else None
+
+    def restore_latest(self):
+        """base.py:40-47: load the newest epoch checkpoint, set ``startepoch`` to its epoch number (the reference re-runs
+        that epoch: ``epoch < startepoch`` skips only the earlier ones).  Returns the epoch or None."""
+        self.startepoch = 0
+        path = self.latest_checkpoint()
+        if path is None:
+            return None
+        blob = torch.load(path, map_location=self.device)
+        self.load_state_dict(blob["state_dict"])
+        for name, mod in (("encoder", self.encoder), ("decoder", self.decoder)):
+            o = blob.get("optimizer", {}).get(name)
+            if o is not None:
+                S = mod.store
+                S.ensure_adam(self.lr)
+                S.m.copy_(o["m"])
+                S.v.copy_(o["v"])
+                S.adam_state.copy_(o["adam_state"])
+        self.startepoch = int(blob["epoch"])
+        return self.startepoch

@@ -56,7 +56,8 @@ def _bind():
     L.lo_tfdec_workspace_bytes.restype = i64
     L.lo_tfdec_workspace_bytes.argtypes = [P]
     for name, argtypes in (("lo_tfdec_forward", [P, i32, vp]), ("lo_tfdec_backward", [P, vp]),
-                           ("lo_tfdec_greedy", [P, i64, i32, vp, vp, vp]), ("lo_tfdec_beam", [P, i64, i32, vp, vp, vp, vp, vp])):
+                           ("lo_tfdec_greedy", [P, i64, i32, vp, vp, vp]), ("lo_tfdec_beam", [P, i64, i32, vp, vp, vp, vp, vp]),
+                           ("lo_tfdec_beam_div", [P, i64, i32, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp])):
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
@@ -94,9 +95,10 @@ class Decoder(nn.Module):
         if self.decoding not in ("greedy", "beam_search"):
             raise NotImplementedError("decoding=%r" % (self.decoding,))
         self._tiles = 1 if self.decoding == "greedy" else int(getattr(config, "beam_size", 2))        # decoder.py:22
-        if self.decoding == "beam_search" and not (float(getattr(config, "div_gamma", 1)) == 1 or float(getattr(config, "div_prob", 0)) == 0):
-            # beam_search_decoder_cell.py:258-287 (diversity penalty) is off in the shipped config (model.json:15-16)
-            raise NotImplementedError("beam-search diversity penalty (div_gamma != 1 and div_prob != 0)")
+        # diversity penalty of beam_search_decoder_cell.py:258-287 (off in the shipped config: model.json:15-16 -> gamma 1, prob 0)
+        self.div_gamma = float(getattr(config, "div_gamma", 1) or 1)
+        self.div_prob = float(getattr(config, "div_prob", 0) or 0)
+        self._div_state = None
         self.max_length_formula = int(getattr(config, "max_length_formula", 150))
         self.precision = precision or getattr(config, "precision", "bf16")
         self.impl = impl if impl is not None else getattr(config, "conv_impl", "tc" if self.precision == "bf16" else "simt")
@@ -249,9 +251,11 @@ class Decoder(nn.Module):
             denc = self.run_backward(ws)
             return ws["loss"], denc
 
-    def decode(self, enc, max_steps=None):
+    def decode(self, enc, max_steps=None, div_u=None, return_attention=False):
         """dynamic_decode(decoder_cell, max_length_formula + 1) (decoder.py:70): at most max_length_formula + 2 steps, stops when
-        every row / beam has emitted END.  Returns DecoderOutput(logits=None, ids)."""
+        every row / beam has emitted END.  Returns DecoderOutput(logits=None, ids).  ``div_u`` (tests): injected uniforms
+        [steps, N*beam, V] for the diversity penalty; ``return_attention`` (greedy): also the attention weights [N, steps, R]
+        (the tensor attention_mechanism.py:96-121 hands to visualize_attention.py)."""
         enc = self._enc(enc)
         N, R, _ = enc.shape
         beam = self._tiles
@@ -268,13 +272,26 @@ class Decoder(nn.Module):
                 check(L.lo_tfdec_greedy(ctypes.byref(a), self._id_end, steps, tokens.data_ptr(), fin.data_ptr(), stream_ptr()))
                 done = fin.bool().all(dim=0)                            # dynamic_decode.py:38-40: loop ends once all rows finished
                 n = int(torch.nonzero(done)[0]) + 1 if bool(done.any()) else steps
+                if return_attention:
+                    return DecoderOutput(None, tokens[:, :n]), ws["alphas"][:, :n].float().clone()
                 return DecoderOutput(None, tokens[:, :n])
             ids = torch.zeros(N, steps, beam, dtype=torch.int64, device=dev)
             parents = torch.zeros_like(ids)
             fin = torch.zeros(N, steps, beam, dtype=torch.int32, device=dev)
             logp = torch.zeros(N, beam, dtype=torch.float32, device=dev)
-            check(L.lo_tfdec_beam(ctypes.byref(a), self._id_end, steps, ids.data_ptr(), parents.data_ptr(), fin.data_ptr(),
-                                  logp.data_ptr(), stream_ptr()))
+            u_dev = None
+            div_on = not (self.div_gamma == 1 or self.div_prob == 0)
+            if div_on and div_u is not None:
+                u_dev = torch.as_tensor(div_u, dtype=torch.float32).to(dev).contiguous()
+                if tuple(u_dev.shape) != (steps, B, self.V):
+                    raise ValueError("div_u must be [steps, N * beam, V]")
+            elif div_on:
+                if self._div_state is None:
+                    self._div_state = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+                self._div_state[1] += 1                                  # a new Philox stream per decode call
+            check(L.lo_tfdec_beam_div(ctypes.byref(a), self._id_end, steps, ids.data_ptr(), parents.data_ptr(), fin.data_ptr(),
+                                      logp.data_ptr(), self.div_gamma, self.div_prob, u_dev.data_ptr() if u_dev is not None else None,
+                                      self._div_state.data_ptr() if (div_on and u_dev is None) else None, stream_ptr()))
             done = fin.bool().all(dim=2).all(dim=0)
             n = int(torch.nonzero(done)[0]) + 1 if bool(done.any()) else steps
             # finalize (beam_search_decoder_cell.py:189-250) gathers with the unchanged initial parents -> identity

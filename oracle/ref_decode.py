@@ -41,9 +41,22 @@ def greedy_decode(p, enc, start_id, end_id, max_iter):
     return torch.stack(out, dim=1)
 
 
-def beam_decode(p, enc, start_id, end_id, beam, max_iter, finalize="reference"):
+def add_div_penalty(log_probs, div_gamma, div_prob, u):
+    """beam_search_decoder_cell.py:258-287 (Li et al. 2016).  log_probs [N, beam, V]; u: the uniforms [N, beam, V] that
+    sample_bernoulli (:253-255, ``tf.greater(p, tf.random_uniform(s))``) would draw — injected so that a test can replay them.
+    rank = position in the descending sort of each beam row (tf.nn.top_k(sorted=True): lower index first among equals),
+    penalty = log(gamma) * rank where div_prob > u."""
+    if div_gamma is None or div_prob is None or div_gamma == 1.0 or div_prob == 0.0:          # :268-273
+        return log_probs
+    order = torch.argsort(log_probs, dim=-1, descending=True, stable=True)                    # :276  (stable = top_k's tie rule)
+    rank = torch.argsort(order, dim=-1)                                                       # :278-280 invert_permutation
+    pen = torch.log(torch.tensor(float(div_gamma), dtype=log_probs.dtype)) * rank.to(log_probs.dtype)   # :282
+    return log_probs + pen * (div_prob > u).to(log_probs.dtype)                               # :284-287
+
+
+def beam_decode(p, enc, start_id, end_id, beam, max_iter, finalize="reference", div_gamma=1.0, div_prob=0.0, div_u=None):
     """beam_search_decoder_cell.py:98-250.  Returns ids [N, steps, beam] (time-major inside the cell, batch-major here)
-    and the final log-probs [N, beam]."""
+    and the final log-probs [N, beam].  div_u [steps, N*beam, V]: injected uniforms of the diversity penalty."""
     N, R, C = enc.shape
     V = p["fc.weight"].shape[0]
     att1 = F.linear(enc, p["attention.encoder_att.weight"], p["attention.encoder_att.bias"])
@@ -67,7 +80,9 @@ def beam_decode(p, enc, start_id, end_id, beam, max_iter, finalize="reference"):
         f = finished.unsqueeze(-1).float()
         step_lp = (1.0 - f) * step_lp + f * one_hot                                       # mask_probs :353-367
         lp = log_probs.unsqueeze(-1) + step_lp                                            # :150
-        flat = lp.view(N, beam * V) if time > 0 else lp[:, 0]                             # :156-160
+        if div_u is not None:
+            lp = add_div_penalty(lp, div_gamma, div_prob, div_u[time].view(N, beam, V))   # :151-152
+        flat = lp.reshape(N, beam * V) if time > 0 else lp[:, 0]                          # :156-160
         new_probs, idx = _topk_low_index_first(flat, beam)                                # :161
         new_ids = idx % V                                                                 # :164
         new_parents = idx // V                                                            # :165

@@ -139,7 +139,7 @@ def greedy_decode(p, enc, end_id, max_iter):
     return torch.stack(out, dim=1)
 
 
-def beam_decode(p, enc, end_id, beam, max_iter):
+def beam_decode(p, enc, end_id, beam, max_iter, div_gamma=1.0, div_prob=0.0, div_u=None):
     """beam_search_decoder_cell.py:98-187 on the Genthial cell (diversity penalty off, model.json:15-16); finalize is the
     reference's identity gather (:189-250).  Returns ids [N, steps, beam], log-probs [N, beam]."""
     N, R, C = enc.shape
@@ -161,6 +161,8 @@ def beam_decode(p, enc, end_id, beam, max_iter):
         f = finished[:, :, None].float()
         lp = (1.0 - f) * lp + f * fin_row                                            # mask_probs :353-367
         total = log_probs[:, :, None] + lp                                           # :150
+        if div_u is not None:
+            total = rd.add_div_penalty(total, div_gamma, div_prob, div_u[time].view(N, beam, V))    # :151-152
         flat = total[:, 0] if time == 0 else total.reshape(N, beam * V)              # :156-160
         vals, idx = rd._topk_low_index_first(flat, beam)                             # :161
         ids, parents = idx % V, idx // V                                             # :164-165

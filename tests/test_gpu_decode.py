@@ -47,6 +47,49 @@ def test_beam_tokens_match_oracle(beam):
         assert (glp - wlp).abs().max().item() < 1e-3 * max(1.0, wlp.abs().max().item())
 
 
+@pytest.mark.parametrize("gamma,prob", [(0.5, 1.0), (0.8, 0.6), (1.7, 0.5)])
+def test_beam_diversity_penalty_matches_oracle(gamma, prob):
+    """add_div_penalty (beam_search_decoder_cell.py:258-287) with the Bernoulli draws injected on both sides."""
+    from latex_ocr_b200 import decode
+    from oracle import ref_decode as rd
+    V, beam, L = 30, 3, 8
+    rm, pd, m, img, enc = _setup(V, seed=6)
+    N = img.shape[0]
+    u = torch.rand(L + 2, N * beam, V, generator=torch.Generator().manual_seed(77))
+    want, wlp = rd.beam_decode(pd, enc, start_id=V - 2, end_id=5, beam=beam, max_iter=L + 1, div_gamma=gamma, div_prob=prob, div_u=u)
+    base, _ = rd.beam_decode(pd, enc, start_id=V - 2, end_id=5, beam=beam, max_iter=L + 1)
+    assert want.shape != base.shape or not torch.equal(want, base)          # the penalty changes the search at these settings
+    got, glp = decode.beam_decode(m, img, start_id=V - 2, end_id=5, beam_size=beam, max_length_formula=L, div_gamma=gamma,
+                                  div_prob=prob, div_u=u)
+    assert got.shape == want.permute(0, 2, 1).shape
+    assert torch.equal(got, want.permute(0, 2, 1))
+    assert (glp - wlp).abs().max().item() < 1e-3 * max(1.0, wlp.abs().max().item())
+    # in-kernel Philox draws: runs, is reproducible for a seed, and differs from the penalty-free search
+    a1, _ = decode.beam_decode(m, img, V - 2, 5, beam, L, div_gamma=0.5, div_prob=0.5, div_seed=9)
+    a2, _ = decode.beam_decode(m, img, V - 2, 5, beam, L, div_gamma=0.5, div_prob=0.5, div_seed=9)
+    assert torch.equal(a1, a2)
+
+
+def test_greedy_attention_export():
+    """attention_mechanism.py:96-121: the per-step attention weights of a greedy decode, and their visualize_attention.py map."""
+    from latex_ocr_b200 import decode
+    from oracle import ref_decode as rd
+    V = 30
+    rm, pd, m, img, enc = _setup(V)
+    ids, att = decode.greedy_decode(m, img, start_id=V - 2, end_id=V - 1, max_length_formula=6, return_attention=True)
+    assert att.shape == (img.shape[0], ids.shape[1], enc.shape[1])
+    assert (att.sum(dim=2) - 1).abs().max().item() < 1e-4
+    # step 0 of the oracle: attention over enc with the initial hidden state
+    h0, c0 = rm.init_hidden_state(pd, enc)
+    _, a0 = rm.attention_forward(pd, enc, h0)
+    assert (att[:, 0] - a0).abs().max().item() < 1e-5
+    hh, ww = m.encoder.out_hw(img.shape[2], img.shape[3])
+    maps = decode.attention_maps(att, hh, ww)
+    assert maps.shape == (img.shape[0], ids.shape[1], hh, ww)
+    r = 5
+    assert abs(maps[0, 0, r // ww, r % ww].item() - (1 - att[0, 0, r].item()) * 255.0) < 1e-3
+
+
 def test_predict_batch_surface():
     rm, pd, m, img, enc = _setup(30, seed=8)
     out = m.predict_batch(img, decoding="greedy")

@@ -356,3 +356,37 @@ def test_cnn_variant_encoder_vs_golden():
             assert err < 1e-2, (k, err)
         b = grads["bf16"][k]
         assert ((b - g).norm() / g.norm()).item() < 0.15, k      # bf16 storage through 7 layers + mask flips: norm-wise 15 %
+
+
+def test_in_kernel_philox_dropout_equals_injected_host_mirror_mask():
+    """has_dropout=2 draws the inverted-dropout multipliers inside lstm_pw_fwd/bwd (Philox4x32-10, regenerated in the backward);
+    the numpy mirror (latex_ocr_b200/philox.py, pinned to the Random123 known-answer vectors in tests/test_host_and_abi.py)
+    reproduces them, and feeding that mask through the injected path gives the same loss and gradients."""
+    from latex_ocr_b200 import philox
+    rm = _oracle()
+    V = 60
+    pe, pd = rm.init_params(V, seed=5)
+    img, formula = rm.synthetic_batch(3, 40, 72, V, 4, 9, seed=6)
+    B, T = formula.shape[0], formula.shape[1] - 1
+    m1 = build_model(V, pe, pd, "fp32", train=True)
+    hw = m1.encoder.out_hw(40, 72)
+    R = hw[0] * hw[1]
+    m1.decoder.seed_dropout(0x1234567887654321 & 0x7FFFFFFFFFFFFFFF, call=3)
+    seed = int(m1.decoder.dropout_state[0].item())
+    l1 = m1._step_body(img.cuda(), formula.cuda(), [T] * B, "philox")
+    torch.cuda.synchronize()
+    assert int(m1.decoder.dropout_state[1].item()) == 4                      # advanced once by lo_decoder_backward
+    mask = torch.from_numpy(philox.dropout_multipliers(seed, 3, B, T, 512, 0.5)).cuda()
+    assert 0.4 < (mask == 0).float().mean().item() < 0.6
+    m2 = build_model(V, pe, pd, "fp32", train=True)
+    l2 = m2._step_body(img.cuda(), formula.cuda(), [T] * B, mask)
+    torch.cuda.synchronize()
+    assert l1[0].item() == l2[0].item()
+    assert torch.equal(m1.decoder._ws_for(B, T, R)["t"]["hd"], m2.decoder._ws_for(B, T, R)["t"]["hd"])
+    for a, b in ((m1.decoder.store.grad, m2.decoder.store.grad), (m1.encoder.store.grad, m2.encoder.store.grad)):
+        assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item()    # split-K atomics: equal up to summation order
+    # a second step draws a different mask
+    hd1 = m1.decoder._ws_for(B, T, R)["t"]["hd"].clone()
+    m1._step_body(img.cuda(), formula.cuda(), [T] * B, "philox")
+    torch.cuda.synchronize()
+    assert ((hd1 == 0) != (m1.decoder._ws_for(B, T, R)["t"]["hd"] == 0)).any()

@@ -95,6 +95,28 @@ def test_tf_beam_ids_match_oracle(beam):
     assert torch.equal(out.ids.cpu(), want)
 
 
+def test_tf_beam_diversity_penalty_and_attention_export():
+    """div_gamma / div_prob of configs/model.json:15-16 switched on (beam_search_decoder_cell.py:258-287) with injected Bernoulli
+    draws; greedy attention export (attention_mechanism.py:96-121)."""
+    beam = 3
+    tfm, p, dec, enc, formula = _setup(seed=7, decoding="beam_search", beam_size=beam, div_gamma=0.6, div_prob=0.7)
+    steps = dec.max_length_formula + 2
+    u = torch.rand(steps, enc.shape[0] * beam, 40, generator=torch.Generator().manual_seed(5))
+    want, _ = tfm.beam_decode(p, enc, end_id=dec._id_end, beam=beam, max_iter=dec.max_length_formula + 1, div_gamma=0.6, div_prob=0.7,
+                              div_u=u)
+    out = dec.decode(enc.cuda(), div_u=u)
+    assert out.ids.shape == want.shape and torch.equal(out.ids.cpu(), want)
+    out2 = dec.decode(enc.cuda())                                   # in-kernel Philox draws
+    assert out2.ids.shape[0] == enc.shape[0]
+    tfm, p, dec, enc, formula = _setup(seed=5, decoding="greedy")
+    out, att = dec.decode(enc.cuda(), return_attention=True)
+    assert att.shape == (enc.shape[0], out.ids.shape[1], enc.shape[1])
+    att_img = enc @ p["att_img.kernel"]
+    c, h, o = tfm.initial_state(p, enc)
+    _, _, a0 = tfm.cell_step(p, enc, att_img, p["start_token"].expand(enc.shape[0], -1), c, h, o)
+    assert (att[:, 0].cpu() - a0).abs().max().item() < 1e-5
+
+
 def test_tf_encoder_input_normalisation():
     """input_norm='tf': conv1 consumes (img - 128) / 128 (model/encoder.py:26-27) — against the oracle encoder on the normalised
     image; uint8 and float inputs agree bit for bit."""

@@ -136,3 +136,15 @@ def test_encoder_variants_state_dict_surface():
     assert EncoderCNN(Cfg(encoder_cnn="cnn"), device="cpu", precision="fp32").out_hw(128, 512) == (15, 62)
     with pytest.raises(NotImplementedError):
         EncoderCNN(Cfg(encoder_cnn="resnet"), device="cpu")
+
+
+def test_philox_host_mirror_known_answers():
+    """Random123 kat_vectors for philox4x32-10 (the device generator in csrc/lo_common.cuh is the same ten rounds)."""
+    from latex_ocr_b200 import philox
+    kat = [((0, 0, 0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 6, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for args, want in kat:
+        assert tuple(int(x) for x in philox.philox4x32_10(*args)) == want
+    m = philox.dropout_multipliers(99, 0, 4, 5, 512, 0.5)
+    assert m.shape == (4, 5, 512) and set(m.reshape(-1).tolist()) == {0.0, 2.0} and abs(m.mean() - 1.0) < 0.05
