@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG2["B"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-decode", action="store_true", help="omit the cfg #5 decode probe (N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,7 +158,9 @@ def main():
         positional_embeddings = True
         lr_init = 1e-3
         lr_method = "adam"
-        cuda_graph = (not args.no_graph) and (world == 1 or os.environ.get("LO_DP_GRAPH", "0") == "1")
+        # the whole step — for N > 1 including the NCCL all-reduces of the gradient buckets — is captured in ONE CUDA graph
+        # (LO_DP_GRAPH=0 falls back to eager launches on the data-parallel path)
+        cuda_graph = (not args.no_graph) and (world == 1 or os.environ.get("LO_DP_GRAPH", "1") == "1")
     kernels = args.kernels
     if kernels == "tc" and not bs.tc_ready():
         kernels = "simt"
@@ -241,6 +244,12 @@ def main():
         "roofline_all": probes["all"],
         "peaks": pk,
     }
+    if not args.skip_decode and world == 1:
+        try:
+            out["decode"] = bs.decode_probe(model, V=c["V"])       # BASELINE.json configs[4]: greedy + beam-5 tokens/s, exact match
+        except Exception as e:                                     # the headline line must survive a probe failure
+            out["decode"] = {"error": repr(e)[:300]}
+        log("decode probe done")
     if not args.skip_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only (the scaling runs stay short)
         out["cpu_baseline"] = bs.cpu_baseline(c)
     print(json.dumps(out), flush=True)

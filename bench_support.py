@@ -246,3 +246,71 @@ def cpu_baseline(c):
     return {"value": sb / dt, "unit": "images/s", "cores": cores, "kind": kind,
             "sample": "%d of %d images per step (cfg2 shapes), 2 timed steps after 1 warm-up, torch %s CPU fp32, %.2f s/step"
                       % (sb, c["B"], torch.__version__, dt)}
+
+
+def decode_probe(model, V=500, n_images=256, height=64, widths=(64, 128, 256, 512, 1024), max_len=150, beam=5, oracle_sample=True):
+    """BASELINE.json configs[4] (cfg #5): greedy and beam-5 decoding of `n_images` variable-width images through the public
+    ``Img2SeqModel.predict_batch`` with HOST uint8 images (list of HxWx1 arrays -> shape bucketing like
+    utils/data_generator.py:84-122 -> pad -> H2D -> encoder -> decode loop -> ids D2H -> truncate), bf16 storage.
+    Random-init weights never emit END, so every batch runs the full max_length_formula + 2 = 152 steps; tokens/s counts the
+    tokens of the scored hypothesis (hypothesis 0, img2seq.py:210).  `exact_match_vs_oracle`: the fp32 CPU oracle's greedy
+    decode (oracle/ref_decode.py) of a bounded sample (2 images per bucket, 24 steps) against the GPU bf16 ids."""
+    import numpy as np
+    from latex_ocr_b200 import data as lod
+    rng = np.random.RandomState(5)
+    per = n_images // len(widths)
+    imgs = []
+    for i, W in enumerate(widths):
+        n = per + (n_images - per * len(widths) if i == len(widths) - 1 else 0)
+        for _ in range(n):
+            a = np.full((height, W, 1), 255, np.uint8)
+            ink = rng.rand(height, W, 1) < 0.10
+            a[ink] = rng.randint(0, 255, size=int(ink.sum())).astype(np.uint8)
+            imgs.append(a)
+    order = rng.permutation(len(imgs))
+    items = lod.bucket_by_shape([(imgs[i], int(i)) for i in order], per)          # same-shape runs of `per` images
+    batches = [[it[0] for it in items[k:k + per]] for k in range(0, len(items), per)]
+    batches = [b for b in batches if b]
+    cfgd = model._config
+    model.decoder._ws.maxsize = model.encoder._ws.maxsize = 2 * len(widths) + 2      # one workspace per (bucket, mode) stays cached
+    out = {"workload": "cfg5: %d images %d x {%s} px, bucketed by width (batches of %d), %d decode steps, bf16, host uint8 images in, "
+                       "token ids out" % (n_images, height, ",".join(map(str, widths)), per, max_len + 2)}
+    for mode, bs in (("greedy", 1), ("beam5", beam)):
+        cfgd.decoding = "greedy" if bs == 1 else "beam_search"
+        cfgd.beam_size = bs
+        cfgd.max_length_formula = max_len
+        for rep in range(2):                                                         # first pass warms the per-bucket workspaces
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            toks = 0
+            for b in batches:
+                ids, _ = model._decode_ids(torch.from_numpy(lod.pad_batch_images(b)).permute(0, 3, 1, 2).contiguous())
+                toks += sum(len(s) for s in ids[0])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out[mode + "_tok_s"] = toks / dt
+        out[mode + "_img_s"] = n_images / dt
+        out[mode + "_seconds"] = dt
+    if oracle_sample:
+        from oracle import ref_decode as rd
+        from oracle import ref_model as rm
+        pe = {k: v.detach().float().cpu() for k, v in model.encoder.state_dict().items()}
+        pd = {k: v.detach().float().cpu() for k, v in model.decoder.state_dict().items()}
+        steps, match, total, exact, nseq = 24, 0, 0, 0, 0
+        cfgd.decoding, cfgd.max_length_formula = "greedy", steps - 2
+        for W in widths:
+            b = [im for im in imgs if im.shape[1] == W][:2]
+            x = torch.from_numpy(lod.pad_batch_images(b)).permute(0, 3, 1, 2).contiguous()
+            enc = rm.encoder_forward(pe, x.float()).reshape(len(b), -1, 512)
+            want = rd.greedy_decode(pd, enc, start_id=V - 2, end_id=V - 1, max_iter=steps - 1)
+            got, _ = model._decode_ids(x)
+            got = torch.tensor(got[0])[:, :want.shape[1]]
+            match += int((got == want[:, :got.shape[1]]).sum())
+            total += got.numel()
+            exact += int((got == want[:, :got.shape[1]]).all(dim=1).sum())
+            nseq += len(b)
+        out["exact_match_vs_oracle"] = exact / max(nseq, 1)
+        out["token_match_vs_oracle"] = match / max(total, 1)
+        out["oracle_sample"] = "%d images (2 per width bucket), %d free-running greedy steps, fp32 CPU oracle vs bf16 GPU" % (nseq, steps)
+    cfgd.max_length_formula = max_len
+    return out

@@ -218,7 +218,21 @@ struct TcLstmEpi {
   const float* c_prev; float* gates; float* c_out; float* h_out; bf16* h_bf;
   float* hd; int64_t hd_stride; const float* dmask;
   int D, V;
+  // in-kernel dropout (has_dropout = 2): Philox state, drop probability, first batch row of this launch, step index
+  const unsigned long long* dstate; float dp; int row0, t_idx;
 };
+// fused decoder forward step (lo_skinny.cu): [gates GEMM + LSTM cell] -> grid barrier -> [projection of h_{t+1} for step t+1]
+struct DecStepFwd {
+  const bf16* gctx; int64_t ld_gctx;       // A of phase 1: gate * context of step t, [M][K]
+  const bf16* wil; int64_t ld_wil;         // gate-interleaved context half of weight_ih [4D][K]
+  TcLstmEpi e;                             // LSTM epilogue (writes h_{t+1} fp32 + bf16 mirror, c, gates, hd)
+  const bf16* wcat; int64_t ld_wcat;       // [N2][D] = [decoder_att; f_beta; weight_hh]
+  const float* bcat; float* o1_next; int64_t ld_o1; int N2;   // phase 2 output (NULL: last step, phase 2 skipped)
+  unsigned int* bar; unsigned int bar_target;                 // monotonic arrival counter of the grid barrier
+  int M, K;
+};
+int dec_step_fwd(const DecStepFwd& p, cudaStream_t st);
+extern int g_opt_dec_fuse;
 int tc_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st);
 extern int g_opt_fuse_lstm;
 extern int g_opt_skinny_mma;

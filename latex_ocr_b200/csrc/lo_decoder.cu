@@ -950,7 +950,7 @@ static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_
   const BfViews bv = bf_views(a, d);
   if (bv.on) {
     LO_TRY(lo_cast(a->hall, LO_F32, bv.hall, LO_BF16, (int64_t)d.B * d.D, (void*)st));
-    if (g_opt_fuse_lstm && d.E % 8 == 0 && d.C % 8 == 0) {
+    if ((g_opt_fuse_lstm || g_opt_dec_fuse) && d.E % 8 == 0 && d.C % 8 == 0) {
       interleave_wih_kernel<<<148 * 2, 256, 0, st>>>((const bf16*)a->w_ih, bv.wil, d.D, d.E, d.C);
       LO_LAUNCH_OK();
     }
@@ -1122,6 +1122,39 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
     LO_CUDA(cudaEventRecord(g_ev_fork, st));
     LO_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
   }
+  const BfViews bvs = bf_views(a, d);
+  const bool fused = bvs.on && g_opt_dec_fuse && g_opt_skinny_mma && !g_opt_fuse_lstm && g_opt_att_pipe && nchains == 1 && d.B <= 64 &&
+                     d.C == d.D && d.D <= 512 && d.D % 16 == 0 && d.O1 % 16 == 0 && d.E % 8 == 0 && a->rows_per_img <= 1;
+  if (fused) {
+    // two launches per step: attention(t) -> dec_step_fwd(t) = [gates GEMM + LSTM cell | grid barrier | projection of h_{t+1}]
+    unsigned int* bar = (unsigned int*)((char*)a->work + lo_attention_workspace_bytes(d.B, d.C));      // chain-1 region is unused here
+    LO_CUDA(cudaMemsetAsync(bar, 0, 4, st));
+    const int grid = cdiv(d.O1, 16) > cdiv(d.G, 16) ? cdiv(d.O1, 16) : cdiv(d.G, 16);
+    LO_TRY(skinny_gemm_nt(bvs.hall, d.D, (const bf16*)a->wcat1, d.D, a->out1, d.O1, a->bt_host[0], d.O1, d.D, a->bcat1, 1, 0, st));
+    unsigned int epoch = 0;
+    for (int t = 0; t < d.T; t++) {
+      const int nrows = a->bt_host[t];
+      float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+      LO_TRY(attention_forward_launch(a->att1, a->enc, a->dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+                                      a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C,
+                                      bvs.gctx + (int64_t)t * d.B * d.C, nrows, d.R, d.C, a->work, st, 1, 0));
+      DecStepFwd p{};
+      p.gctx = bvs.gctx + (int64_t)t * d.B * d.C; p.ld_gctx = d.C;
+      p.wil = bvs.wil; p.ld_wil = d.C;
+      const float* dm = (a->has_dropout == 1 && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+      p.e = TcLstmEpi{a->ptab, a->caps + t, a->caps_stride, o1 + d.A + d.C, d.O1, a->call + (int64_t)t * d.B * d.D,
+                      a->gates + (int64_t)t * d.B * d.G, a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D,
+                      bvs.hall + (int64_t)(t + 1) * d.B * d.D, a->hd + (int64_t)t * d.D, (int64_t)d.T * d.D, dm, d.D, d.V,
+                      (const unsigned long long*)(a->has_dropout == 2 ? a->dropout_state : nullptr), a->dropout_p, 0, t};
+      p.wcat = (const bf16*)a->wcat1; p.ld_wcat = d.D; p.bcat = a->bcat1;
+      const bool more = t + 1 < d.T;
+      p.o1_next = more ? a->out1 + (int64_t)(t + 1) * d.B * d.O1 : nullptr;
+      p.ld_o1 = d.O1; p.N2 = d.O1;
+      p.bar = bar; p.bar_target = more ? (++epoch) * (unsigned int)grid : 0u;
+      p.M = nrows; p.K = d.C;
+      LO_TRY(dec_step_fwd(p, st));
+    }
+  } else
   for (int chain = 0; chain < nchains; chain++) {
     cudaStream_t cs = chain == 0 ? st : g_side;
     for (int t = 0; t < d.T; t++) {

@@ -177,6 +177,191 @@ __global__ void __launch_bounds__(128) skinny_lstm_kernel(const bf16* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Fused decoder forward step: one launch per time step instead of three.
+//   phase 1 (CTAs 0 .. 4D/16-1): gates = (gate*ctx)_t W_ih[:, E:]^T with the LSTM cell in the epilogue -> h_{t+1}, c_{t+1}
+//   grid barrier (all CTAs are co-resident: <= 2 per SM by shared memory, grid <= 296)
+//   phase 2 (CTAs 0 .. N2/16-1): [att2 | gate_pre | hh_pre]_{t+1} = h_{t+1} [W_d; W_beta; W_hh]^T + b
+// The time loop is a chain of dependent 64-row GEMMs: each separate launch costs ~6-7 us of pure latency (launch, cold loads,
+// drain) for ~1 us of math.  Here both weight slices are fetched before griddepcontrol.wait, the barrier costs one L2 atomic
+// round trip, and h_{t+1} is re-read from L2 where the other CTAs just put it.  griddepcontrol.launch_dependents is issued only
+// AFTER the barrier: by then every CTA of this grid is resident, so the early-starting attention kernel of the next step
+// cannot take a slot a not-yet-resident CTA of this grid needs (no deadlock).
+// ------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                       // this CTA's global writes are visible before its arrival is
+    atomicAdd(ctr, 1u);
+    if (ld_acquire_u32(ctr) < target) {
+      const long long t0 = clock64();
+      while (ld_acquire_u32(ctr) < target) {
+        if (clock64() - t0 > 4000000000LL) __trap();          // a protocol bug must fail loudly, not hang the GPU
+      }
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int SKF_SMEM = (64 + 2 * SK_NT) * SK_PITCH * 2;
+
+__global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  bf16* sA = reinterpret_cast<bf16*>(sk_smem);               // [64][SK_PITCH]   A of phase 1, then of phase 2
+  bf16* sW1 = sA + 64 * SK_PITCH;                            // [16][SK_PITCH]   Wil slice
+  bf16* sW2 = sW1 + SK_NT * SK_PITCH;                        // [16][SK_PITCH]   Wcat slice
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * SK_NT;
+  const int K = p.K, cpr = K / 8, M = p.M;
+  const TcLstmEpi& e = p.e;
+  const bool ph1 = n0 < 4 * e.D;
+  const bool ph2 = p.o1_next != nullptr && n0 < p.N2;
+  // ---- weights of both phases: parameters, independent of the preceding launches
+  if (ph1)
+    for (int i = tid; i < SK_NT * cpr; i += 128) {
+      const int r = i / cpr, c = i % cpr;
+      cp_async16(sW1 + r * SK_PITCH + c * 8, p.wil + (int64_t)(n0 + r) * p.ld_wil + c * 8, true);
+    }
+  if (ph2)
+    for (int i = tid; i < SK_NT * cpr; i += 128) {
+      const int r = i / cpr, c = i % cpr;
+      cp_async16(sW2 + r * SK_PITCH + c * 8, p.wcat + (int64_t)min(n0 + r, p.N2 - 1) * p.ld_wcat + c * 8, n0 + r < p.N2);
+    }
+  pdl_wait();
+  const int g = lane >> 2, t = lane & 3;
+  const bf16* a_ptr = sA + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SK_PITCH + (lane >> 4) * 8;
+  if (ph1) {
+    for (int i = tid; i < 64 * cpr; i += 128) {
+      const int r = i / cpr, c = i % cpr;
+      cp_async16(sA + r * SK_PITCH + c * 8, p.gctx + (int64_t)min(r, M - 1) * p.ld_gctx + c * 8, r < M);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int D = e.D;
+    const bool even = (t & 1) == 0;
+    const int row = warp * 16 + g + (even ? 0 : 8);
+    const bool live = row < M;
+    float add[2][4], cprev[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      cprev[j] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; q++) add[j][q] = 0.f;
+    }
+    if (live) {
+      int64_t tk = e.tok[(int64_t)row * e.tok_stride];
+      if (tk < 0) tk = 0;
+      if (tk >= e.V) tk = e.V - 1;
+      const float* pt = e.ptab + tk * 4 * D;
+      const float* hh = e.hh + (int64_t)row * e.hh_stride;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int u = n0 / 4 + 2 * j + (t >> 1);
+        cprev[j] = e.c_prev[(int64_t)row * D + u];
+#pragma unroll
+        for (int q = 0; q < 4; q++) add[j][q] = pt[q * D + u] + hh[q * D + u];
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const bf16* b_ptr = sW1 + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
+#pragma unroll 4
+    for (int k = 0; k < K; k += 16) {
+      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+      ldmatrix_x4(a0, a1, a2, a3, a_ptr + k);
+      ldmatrix_x4(b0, b1, b2, b3, b_ptr + k);
+      mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);
+      mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      // even lanes hold (i,f), odd lanes (g,o) of unit u for rows g (acc[.][0..1]) and g+8 (acc[.][2..3])
+      const float sx = even ? acc[j][2] : acc[j][0], sy = even ? acc[j][3] : acc[j][1];
+      const float rx = __shfl_xor_sync(0xffffffffu, sx, 1), ry = __shfl_xor_sync(0xffffffffu, sy, 1);
+      if (!live) continue;
+      const float pi = (even ? acc[j][0] : rx) + add[j][0];
+      const float pf = (even ? acc[j][1] : ry) + add[j][1];
+      const float pg = (even ? rx : acc[j][2]) + add[j][2];
+      const float po = (even ? ry : acc[j][3]) + add[j][3];
+      const int u = n0 / 4 + 2 * j + (t >> 1);
+      const float ig = sigmoidf_(pi), fg = sigmoidf_(pf), gg = tanhf(pg), og = sigmoidf_(po);
+      const float c = fg * cprev[j] + ig * gg;
+      const float h = og * tanhf(c);
+      float* gt = e.gates + (int64_t)row * 4 * D;
+      gt[u] = ig; gt[D + u] = fg; gt[2 * D + u] = gg; gt[3 * D + u] = og;
+      e.c_out[(int64_t)row * D + u] = c;
+      e.h_out[(int64_t)row * D + u] = h;
+      e.h_bf[(int64_t)row * D + u] = __float2bfloat16_rn(h);
+      if (e.hd) {
+        float mult = 1.f;
+        if (e.dmask) mult = e.dmask[(int64_t)row * e.hd_stride + u];
+        else if (e.dstate) mult = philox_dropout_mult(e.dstate, e.row0 + row, e.t_idx, u, e.dp, 1.f / (1.f - e.dp));
+        e.hd[(int64_t)row * e.hd_stride + u] = h * mult;
+      }
+    }
+  } else {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (p.o1_next == nullptr) {             // last step: nothing follows the cell
+    pdl_trigger();
+    return;
+  }
+  grid_barrier(p.bar, p.bar_target);       // h_{t+1} of every CTA is in L2 (also orders this CTA's reads of sA before reuse)
+  pdl_trigger();
+  if (!ph2) return;
+  for (int i = tid; i < 64 * cpr; i += 128) {
+    const int r = i / cpr, c = i % cpr;
+    cp_async16(sA + r * SK_PITCH + c * 8, e.h_bf + (int64_t)min(r, M - 1) * e.D + c * 8, r < M);     // cp.async.cg: from L2
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const bf16* b_ptr = sW2 + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
+#pragma unroll 4
+  for (int k = 0; k < K; k += 16) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    ldmatrix_x4(a0, a1, a2, a3, a_ptr + k);
+    ldmatrix_x4(b0, b1, b2, b3, b_ptr + k);
+    mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);
+    mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int n = n0 + j * 8 + 2 * t;
+    if (n >= p.N2) continue;
+    const float bx = p.bcat ? p.bcat[n] : 0.f, by = p.bcat ? p.bcat[n + 1] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int r = warp * 16 + g + h * 8;
+      if (r >= M) continue;
+      *reinterpret_cast<float2*>(p.o1_next + (int64_t)r * p.ld_o1 + n) = make_float2(acc[j][2 * h] + bx, acc[j][2 * h + 1] + by);
+    }
+  }
+}
+
+int g_opt_dec_fuse = 1;
+
+int dec_step_fwd(const DecStepFwd& p, cudaStream_t st) {
+  LO_CHECK_ARG(p.M >= 1 && p.M <= 64 && p.K % 16 == 0 && p.K <= SK_KC && p.e.D == p.K && p.e.D % 4 == 0 && p.N2 % 2 == 0, "M<=64, K=D<=512");
+  LO_CHECK_ARG(p.e.h_bf && p.bar, "bf16 mirror of h and the barrier counter are required");
+  static bool attr = false;
+  if (!attr) {
+    LO_CUDA(cudaFuncSetAttribute(dec_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKF_SMEM));
+    attr = true;
+  }
+  const int n1 = 4 * p.e.D / SK_NT, n2 = p.o1_next ? cdiv(p.N2, SK_NT) : 0;
+  const int grid = n1 > n2 ? n1 : n2;
+  LO_CHECK_ARG(grid <= 296, "fused step: grid must be co-resident (<= 2 CTAs per SM)");
+  LO_CUDA(launch_pdl(dec_step_fwd_kernel, dim3(grid), dim3(128), (size_t)SKF_SMEM, st, p));
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
 int skinny_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st) {
   LO_CHECK_ARG(M >= 1 && M <= 64 && K % 16 == 0 && K <= SK_KC && lda % 8 == 0 && ldw % 8 == 0 && D % 4 == 0, "M<=64, K%16, K<=512");
   static bool attr = false;

@@ -31,6 +31,28 @@ class GradSync:
         else:
             self._handles.append(dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def layer_hook(self, encoder, min_bucket=262144):
+        """Returns ``on_layer_grad(idx)`` for EncoderCNN.backward_raw: layers complete from the last conv to the first; their
+        flat-store ranges are adjacent (descending), so consecutive small layers are merged until a bucket reaches
+        ``min_bucket`` elements, and whatever is left goes out with the first layer."""
+        first = encoder.layers[0][0]
+        pending = []          # [lo, hi) of the not-yet-reduced tail, grows downwards
+
+        def hook(idx):
+            off, n = encoder.grad_range(idx)
+            if pending and pending[0] != off + n:          # not adjacent (padding between entries is included by range math)
+                lo, hi = pending[0], pending[1]
+                self.reduce_async(encoder.store.grad[lo:hi])
+                del pending[:]
+            if not pending:
+                pending.extend([off, off + n])
+            else:
+                pending[0] = off
+            if pending[1] - pending[0] >= min_bucket or idx == first:
+                self.reduce_async(encoder.store.grad[pending[0]:pending[1]])
+                del pending[:]
+        return hook
+
     def wait(self):
         for h in self._handles:
             if h == "side":

@@ -212,8 +212,16 @@ class EncoderCNN(nn.Module):
             return ws["out"]
         return x
 
-    def backward_raw(self, img_shape, denc):
-        """denc: fp32 [N,H',W',512] gradient w.r.t. the encoder output.  Fills self.store.grad."""
+    def grad_range(self, idx):
+        """(offset, count) of layer ``idx``'s [weight, bias] gradient inside the flat store (contiguous by construction)."""
+        ow, nw, _ = self.store.offsets["cnn.%s.weight" % idx]
+        ob, nb, _ = self.store.offsets["cnn.%s.bias" % idx]
+        return ow, ob + nb - ow
+
+    def backward_raw(self, img_shape, denc, on_layer_grad=None):
+        """denc: fp32 [N,H',W',512] gradient w.r.t. the encoder output.  Fills self.store.grad.  ``on_layer_grad(idx)`` is
+        called right after the kernels that complete layer idx's weight/bias gradient have been enqueued (last conv first):
+        the data-parallel path fires that layer's gradient all-reduce there, overlapping the rest of the backward."""
         L = _lib.lib()
         N, _, H, W = img_shape
         ws = self._workspace(N, H, W, True)
@@ -256,6 +264,8 @@ class EncoderCNN(nn.Module):
                 check(L.lo_gemm(ptr(dy), dt, ptr(ws["wflip"][idx]), dt, ptr(col), dt, M, K, cout, cout, 1, 1, cout, K, 1, 0, 0, 0, None,
                                 0, 0, impl, st))                                                   # dcol = dy W  (col reused)
                 check(L.lo_col2im(ptr(col), ptr(mask), ptr(G[xin]), dt, N, x.shape[1], x.shape[2], cin, R, S_, stride, pad, st))
+            if on_layer_grad is not None:
+                on_layer_grad(idx)
             if xin.startswith("P") and xin != "P0":
                 src = "Y" + xin[1:]
                 pool_k = cfg[xin[1:]][4]
@@ -266,10 +276,12 @@ class EncoderCNN(nn.Module):
             check(L.lo_conv1_pool_wgrad_norm(ptr(ws["img"]), int(ws["img"].dtype == torch.uint8), 1.0 / 128.0, -1.0,
                                              ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
                                              ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))
-            return
-        wg1 = L.lo_conv1_pool_wgrad_u8 if ws["img"].dtype == torch.uint8 else L.lo_conv1_pool_wgrad
-        check(wg1(ptr(ws["img"]), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
-                                    ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))
+        else:
+            wg1 = L.lo_conv1_pool_wgrad_u8 if ws["img"].dtype == torch.uint8 else L.lo_conv1_pool_wgrad
+            check(wg1(ptr(ws["img"]), ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
+                      ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))
+        if on_layer_grad is not None:
+            on_layer_grad("0")
 
     def forward(self, img):
         """Reference signature (seq2seq_torch.py:88-100): returns a new fp32 tensor [N,H',W',512]."""

@@ -125,9 +125,13 @@ class Img2SeqModel:
         if self.dist is not None:
             self.dist.reduce_async(self.decoder.store.grad)        # decoder bucket flies while the encoder backward runs
             scale = 1.0 / self.dist.world_size
-        self.encoder.backward_raw(tuple(img.shape), ws["t"]["denc"].view(N, enc_out.shape[1], enc_out.shape[2], enc_out.shape[3]))
-        if self.dist is not None:
-            self.dist.reduce_async(self.encoder.store.grad)
+        denc = ws["t"]["denc"].view(N, enc_out.shape[1], enc_out.shape[2], enc_out.shape[3])
+        if self.dist is None:
+            self.encoder.backward_raw(tuple(img.shape), denc)
+        else:
+            # encoder buckets: each layer's gradient is all-reduced as soon as its weight-gradient kernels are enqueued (last
+            # conv first), small layers coalesced; only the first convs' few kB are left exposed before Adam
+            self.encoder.backward_raw(tuple(img.shape), denc, on_layer_grad=self.dist.layer_hook(self.encoder))
             self.dist.wait()
         self._adam(self.decoder.store, scale, self.decoder)
         self._adam(self.encoder.store, scale, self.encoder)

@@ -42,6 +42,28 @@ def _worker(rank, world, port, out):
     sync.wait()
     flat_d /= sync.world_size
     flat_e /= sync.world_size
+    # per-layer encoder buckets (GradSync.layer_hook): every element of the flat gradient is all-reduced exactly once, in
+    # the order the encoder backward completes its layers (last conv first), small layers coalesced
+    class FakeEnc:
+        layers = (("0",), ("3",), ("6",), ("8",))
+        ranges = {"0": (0, 8), "3": (8, 40), "6": (48, 400), "8": (448, 1000)}
+
+        class store:
+            grad = torch.full((1448,), float(rank + 1))
+
+        def grad_range(self, idx):
+            return self.ranges[idx]
+    fe = FakeEnc()
+    calls = []
+    orig = sync.reduce_async
+    sync.reduce_async = lambda t: (calls.append(t.numel()), orig(t))[1]
+    hook = sync.layer_hook(fe, min_bucket=300)
+    for idx in ("8", "6", "3", "0"):
+        hook(idx)
+    sync.wait()
+    sync.reduce_async = orig
+    assert calls == [1000, 400, 48], calls
+    assert torch.equal(fe.store.grad, torch.full((1448,), 3.0))          # 1 + 2 over the two ranks, each element once
     if rank == 0:
         _, ge_full, gd_full, _ = rm.train_step({k: v.clone() for k, v in pe.items()}, {k: v.clone() for k, v in pd.items()},
                                                img, formula, {})

@@ -124,3 +124,47 @@ def test_train_epoch_and_evaluate_surface():
     m.encoder.fine_tune(False)
     m._run_train_epoch(cfg, data, None, 0, None)
     assert torch.equal(before, m.encoder.store.master)
+
+
+def test_bf16_greedy_token_match_rate_at_cfg5_widths():
+    """BASELINE.json configs[4] shapes (height 64, widths 64..1024): greedy tokens of the bf16 / tcgen05 path against the fp32 CPU
+    oracle.  bf16 rounding can legitimately flip an argmax whose top-2 margin is at rounding level, so the comparison is made
+    where it is well defined: teacher-forced on the oracle's own tokens, on the steps whose fp32 top-2 logit margin exceeds
+    5e-2 (logits are O(1)).  Stated bar: >= 0.99 of those steps agree; the free-running exact-match rate is reported."""
+    from latex_ocr_b200 import decode
+    from oracle import ref_decode as rd
+    from oracle import ref_model as rm
+    V, S = 500, 20
+    pe, pd = rm.init_params(V, seed=21)
+    g = torch.Generator().manual_seed(21)
+    pd["fc.weight"] = (torch.rand(V, 512, generator=g) * 2 - 1) * 0.5         # non-degenerate argmax (as in _setup)
+    pd["embedding.weight"] = (torch.rand(V, 512, generator=g) * 2 - 1) * 1.0
+    m = build_model(V, pe, pd, "bf16", impl="tc")
+    m.train_mode(False)
+    agree = considered = exact = nseq = free_match = free_total = 0
+    for W in (64, 128, 256, 512, 1024):
+        img, _ = rm.synthetic_batch(2, 64, W, V, 3, 5, seed=100 + W)
+        enc = rm.encoder_forward(pe, img).reshape(2, -1, 512)
+        want = rd.greedy_decode(pd, enc, start_id=V - 2, end_id=V - 1, max_iter=S - 1)          # [2, S] fp32 oracle tokens
+        n = want.shape[1]
+        caps = torch.cat([torch.full((2, 1), V - 2, dtype=torch.long), want], dim=1)            # START + tokens
+        lens = torch.full((2, 1), n + 1, dtype=torch.long)
+        ref_logits, _, _, _, _ = rm.decoder_forward(pd, enc, caps, lens)                          # teacher-forced fp32 logits
+        top2 = ref_logits.topk(2, dim=-1).values
+        clear = (top2[..., 0] - top2[..., 1]) > 5e-2
+        assert torch.equal(ref_logits.argmax(-1)[clear], want[clear])                             # the oracle agrees with itself
+        enc_gpu = m.encoder(img.cuda())
+        got_logits, _, _, _, _ = m.decoder(enc_gpu, caps.cuda(), lens)
+        hit = got_logits.argmax(-1).cpu() == want
+        agree += int((hit & clear).sum())
+        considered += int(clear.sum())
+        free = decode.greedy_decode(m, img, V - 2, V - 1, S - 2)[:, :n]
+        eq = free == want[:, :free.shape[1]]
+        free_match += int(eq.sum())
+        free_total += eq.numel()
+        exact += int(eq.all(dim=1).sum())
+        nseq += 2
+    rate = agree / max(considered, 1)
+    print("cfg5 bf16 greedy: teacher-forced match on clear-margin steps %d/%d = %.4f ; free-running token match %.4f, exact sequences %d/%d"
+          % (agree, considered, rate, free_match / free_total, exact, nseq))
+    assert considered >= 0.5 * 10 * S and rate >= 0.99
