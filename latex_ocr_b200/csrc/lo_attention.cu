@@ -749,10 +749,12 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "pdl")) lo::g_opt_pdl = value;
   else if (!strcmp(name, "att_cluster")) lo::g_opt_att_cluster = value;
   else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
+  else if (!strcmp(name, "conv_persist")) lo::g_opt_conv_persist = value;
   else if (!strcmp(name, "dec_streams")) { lo::g_opt_dec_streams = value; lo::g_opt_skinny8 = value >= 2 ? 0 : 1; }
   else if (!strcmp(name, "skinny8")) lo::g_opt_skinny8 = value;
   else if (!strcmp(name, "fuse_lstm")) lo::g_opt_fuse_lstm = value;
   else if (!strcmp(name, "dec_fuse")) lo::g_opt_dec_fuse = value;
+  else if (!strcmp(name, "dec_fuse_bwd")) lo::g_opt_dec_fuse_bwd = value;
   else if (!strcmp(name, "skinny_mma")) lo::g_opt_skinny_mma = value;
   else if (!strcmp(name, "l2_persist_mb")) {
     // size of the L2 set-aside that evict_last / persisting accesses may occupy (0 = driver default)

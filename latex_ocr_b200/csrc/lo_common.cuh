@@ -201,6 +201,7 @@ struct AttBwdArgs {
 };
 extern int g_opt_att_pipe;
 extern int g_opt_conv_mc;
+extern int g_opt_conv_persist;
 extern int g_opt_dec_streams;
 extern int g_opt_skinny8;
 int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st);
@@ -232,6 +233,26 @@ struct DecStepFwd {
   int M, K;
 };
 int dec_step_fwd(const DecStepFwd& p, cudaStream_t st);
+// fused decoder backward step (lo_skinny.cu), launched after the attention backward of step t:
+//   phase A: dh_{t-1} += [datt2 | dgate_pre]_t [W_d ; W_beta]          (K = A+C, two K slices, fp32 atomics)
+//   grid barrier ; phase B: LSTM-cell backward of step t-1 (pointwise, spread over the whole grid) ; grid barrier
+//   phase C: [dgctx | dh]_{t-1} = dG_{t-1} [W_ih[:, E:] | W_hh]          (K = 4D, four K slices, fp32 atomics)
+struct DecStepBwd {
+  // phase A (skipped when dcat_a == NULL: first launch of the loop)
+  const bf16* dcat_a; int64_t ld_dcat;      // [Ma][A+C] bf16 mirror of datt2 | dgate_pre of step t
+  const bf16* wbwd2; int64_t ld_w2; int K2; // [D][A+C]
+  int Ma;
+  // phase B/C (skipped when gates == NULL: last launch of the loop)
+  const float* dhd; int64_t dhd_stride; const float* dmask; const unsigned long long* dstate; float dp; int t_idx;
+  float* dc; const float* gates; const float* c_prev; const float* c_cur;
+  float* dG; bf16* dG_bf; int64_t dG_stride;      // d pre-activations of step t-1 (fp32 + bf16 mirror), row stride O1
+  const bf16* wbwd1; int64_t ld_w1; int K1;       // [C+D][4D]
+  int Mb;
+  float* dxh; int C, D;                            // [B][C+D]: dgctx | dh (accumulated with atomics, cleared in phase B)
+  unsigned int* bar; unsigned int bar_target;      // target of the FIRST barrier of this launch (the second is + gridDim.x)
+};
+int dec_step_bwd(const DecStepBwd& p, cudaStream_t st);
+extern int g_opt_dec_fuse_bwd;
 extern int g_opt_dec_fuse;
 int tc_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st);
 extern int g_opt_fuse_lstm;

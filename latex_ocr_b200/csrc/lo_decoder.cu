@@ -1265,6 +1265,54 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     LO_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
   }
   const cudaStream_t st_main = st;
+  const bool fusedb = bv.on && g_opt_dec_fuse_bwd && g_opt_skinny_mma && g_opt_att_pipe && nchains == 1 && d.B <= 64 && d.C == d.D &&
+                      (d.A + d.C) % 512 == 0 && d.G % 512 == 0 && ((d.C + d.D) / 16) * (d.G / 512) <= 296 && a->rows_per_img <= 1;
+  if (fusedb) {
+    // two launches per step: attention_bwd(t) -> dec_step_bwd = [dh += (datt2|dgate) W | barrier | LSTM bwd (t-1) | barrier | dG W]
+    unsigned int* bar = (unsigned int*)((char*)a->work + lo_attention_workspace_bytes(d.B, d.C)) + 16;   // chain-1 region, unused here
+    LO_CUDA(cudaMemsetAsync(bar, 0, 4, st));
+    const unsigned int grid = (unsigned int)(((d.C + d.D) / 16) * (d.G / 512));
+    unsigned int nb = 0;
+    auto fill_bc = [&](DecStepBwd& p, int t) {       // phases B/C for step t
+      p.dhd = a->dhd + (int64_t)t * d.D; p.dhd_stride = (int64_t)d.T * d.D;
+      p.dmask = (a->has_dropout == 1 && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+      p.dstate = (const unsigned long long*)(a->has_dropout == 2 ? a->dropout_state : nullptr);
+      p.dp = a->dropout_p; p.t_idx = t;
+      p.dc = a->dc; p.gates = a->gates + (int64_t)t * d.B * d.G;
+      p.c_prev = a->call + (int64_t)t * d.B * d.D; p.c_cur = a->call + (int64_t)(t + 1) * d.B * d.D;
+      p.dG = a->dcat + (int64_t)t * d.B * d.O1 + d.A + d.C; p.dG_bf = bv.dcat + (int64_t)t * d.B * d.O1 + d.A + d.C; p.dG_stride = d.O1;
+      p.wbwd1 = (const bf16*)a->wbwd1; p.ld_w1 = d.G; p.K1 = d.G; p.Mb = a->bt_host[t];
+    };
+    {
+      DecStepBwd p{};
+      fill_bc(p, d.T - 1);
+      p.wbwd2 = (const bf16*)a->wbwd2; p.ld_w2 = d.A + d.C; p.K2 = d.A + d.C;
+      p.dxh = a->dxh; p.C = d.C; p.D = d.D; p.bar = bar; p.bar_target = (nb + 1) * grid;
+      nb += 1;
+      LO_TRY(dec_step_bwd(p, st));
+    }
+    for (int t = d.T - 1; t >= 0; t--) {
+      const int nrows = a->bt_host[t];
+      float* dcat_t = a->dcat + (int64_t)t * d.B * d.O1;
+      bf16* dcat_bf_t = bv.dcat + (int64_t)t * d.B * d.O1;
+      const float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+      AttBwdArgs x{a->att1, a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+                   a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T,
+                   a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t + d.A, a->dctx + (int64_t)t * d.B * d.C,
+                   nrows, d.R, a->work, a->dmean, 0};
+      LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
+      DecStepBwd p{};
+      p.dcat_a = dcat_bf_t; p.ld_dcat = d.O1; p.wbwd2 = (const bf16*)a->wbwd2; p.ld_w2 = d.A + d.C; p.K2 = d.A + d.C; p.Ma = nrows;
+      p.dxh = a->dxh; p.C = d.C; p.D = d.D; p.bar = bar;
+      p.K1 = d.G;                                  // grid size (phase C tiling) even when phases B/C are skipped
+      if (t > 0) {
+        fill_bc(p, t - 1);
+        p.bar_target = (nb + 1) * grid;
+        nb += 2;
+      }
+      LO_TRY(dec_step_bwd(p, st));
+    }
+  } else
   for (int chain = 0; chain < nchains; chain++) {
    st = chain == 0 ? st_main : g_side;
    for (int t = d.T - 1; t >= 0; t--) {

@@ -362,6 +362,149 @@ int dec_step_fwd(const DecStepFwd& p, cudaStream_t st) {
   return LO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Fused decoder backward step (see DecStepBwd): one launch instead of three between two attention-backward kernels.
+// grid = (C+D)/16 column tiles x 4 K slices of phase C = 256 CTAs (co-resident: 2 per SM); phase A uses the first D/16 x 2.
+// ------------------------------------------------------------------------------------------------------------------------------
+// one 64 x 16 x kn tile: C[r][n0 + ..] += sum_k A[r][k0 + k] W[n0 + ..][k0 + k]   (fp32 atomics)
+__device__ __forceinline__ void skinny_tile_atomic(const bf16* sA, const bf16* sW, int kn, float* C, int64_t ldc, int n0, int N, int M) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const bf16* a_ptr = sA + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SK_PITCH + (lane >> 4) * 8;
+  const bf16* b_ptr = sW + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
+#pragma unroll 4
+  for (int k = 0; k < kn; k += 16) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    ldmatrix_x4(a0, a1, a2, a3, a_ptr + k);
+    ldmatrix_x4(b0, b1, b2, b3, b_ptr + k);
+    mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);
+    mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int n = n0 + j * 8 + 2 * t;
+    if (n >= N) continue;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int r = warp * 16 + g + h * 8;
+      if (r >= M) continue;
+      float* o = C + (int64_t)r * ldc + n;
+      atomicAdd(o, acc[j][2 * h]);
+      atomicAdd(o + 1, acc[j][2 * h + 1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) dec_step_bwd_kernel(DecStepBwd p) {
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  bf16* sA = reinterpret_cast<bf16*>(sk_smem);               // [64][SK_PITCH]
+  bf16* sWa = sA + 64 * SK_PITCH;                            // [16][SK_PITCH]  wbwd2 slice (phase A)
+  bf16* sWc = sWa + SK_NT * SK_PITCH;                        // [16][SK_PITCH]  wbwd1 slice (phase C)
+  const int tid = threadIdx.x;
+  const int cta = blockIdx.x;
+  const int D = p.D, CD = p.C + p.D;
+  // roles
+  const int na_tiles = D / SK_NT, ka_slices = p.K2 / SK_KC;            // phase A: na_tiles x ka_slices CTAs
+  const bool has_a = p.dcat_a != nullptr && cta < na_tiles * ka_slices;
+  const int a_n0 = (cta % na_tiles) * SK_NT, a_k0 = (cta / na_tiles) * SK_KC;
+  const int nc_tiles = CD / SK_NT;                                     // phase C: nc_tiles x (K1 / 512) CTAs = the whole grid
+  const bool has_bc = p.gates != nullptr;
+  const int c_n0 = (cta % nc_tiles) * SK_NT, c_k0 = (cta / nc_tiles) * SK_KC;
+  const bool has_c = has_bc && c_k0 < p.K1;
+  constexpr int cpr = SK_KC / 8;
+  // ---- weight slices: parameters, fetched before griddepcontrol.wait
+  if (has_a)
+    for (int i = tid; i < SK_NT * cpr; i += 128) {
+      const int r = i / cpr, c = i % cpr;
+      cp_async16(sWa + r * SK_PITCH + c * 8, p.wbwd2 + (int64_t)(a_n0 + r) * p.ld_w2 + a_k0 + c * 8, true);
+    }
+  if (has_c)
+    for (int i = tid; i < SK_NT * cpr; i += 128) {
+      const int r = i / cpr, c = i % cpr;
+      cp_async16(sWc + r * SK_PITCH + c * 8, p.wbwd1 + (int64_t)(c_n0 + r) * p.ld_w1 + c_k0 + c * 8, true);
+    }
+  pdl_wait();
+  unsigned int target = p.bar_target;
+  if (p.dcat_a != nullptr) {
+    if (has_a) {
+      for (int i = tid; i < 64 * cpr; i += 128) {
+        const int r = i / cpr, c = i % cpr;
+        cp_async16(sA + r * SK_PITCH + c * 8, p.dcat_a + (int64_t)min(r, p.Ma - 1) * p.ld_dcat + a_k0 + c * 8, r < p.Ma);
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      skinny_tile_atomic(sA, sWa, SK_KC, p.dxh + p.C, CD, a_n0, D, p.Ma);
+    }
+    if (!has_bc) {                           // last launch of the loop: only the projection back to dh_0
+      pdl_trigger();
+      return;
+    }
+    grid_barrier(p.bar, target);             // dh_{t-1} complete
+    target += gridDim.x;
+  }
+  // ---- phase B: LSTM cell backward of step t-1, one (row, unit) per thread over the whole grid
+  {
+    const int total = p.Mb * D;
+    for (int idx = cta * 128 + tid; idx < total; idx += gridDim.x * 128) {
+      const int b = idx / D, j = idx % D;
+      const float* gt = p.gates + (int64_t)b * 4 * D;
+      const float i = gt[j], f = gt[D + j], g = gt[2 * D + j], o = gt[3 * D + j];
+      const float tc = tanhf(p.c_cur[(int64_t)b * D + j]);
+      float dh = p.dhd[(int64_t)b * p.dhd_stride + j];
+      if (p.dmask) dh *= p.dmask[(int64_t)b * p.dhd_stride + j];
+      else if (p.dstate) dh *= philox_dropout_mult(p.dstate, b, p.t_idx, j, p.dp, 1.f / (1.f - p.dp));
+      float* z = p.dxh + (int64_t)b * CD;
+      dh += __ldcg(z + p.C + j);                               // written by other CTAs' atomics (L2)
+      const float dct = p.dc[(int64_t)b * D + j] + dh * o * (1.f - tc * tc);
+      float v[4];
+      v[0] = dct * g * i * (1.f - i);
+      v[1] = dct * p.c_prev[(int64_t)b * D + j] * f * (1.f - f);
+      v[2] = dct * i * (1.f - g * g);
+      v[3] = dh * tc * o * (1.f - o);
+      p.dc[(int64_t)b * D + j] = dct * f;
+      float* d = p.dG + (int64_t)b * p.dG_stride;
+      bf16* q = p.dG_bf + (int64_t)b * p.dG_stride;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        d[k * D + j] = v[k];
+        q[k * D + j] = __float2bfloat16_rn(v[k]);
+      }
+      // clear [dgctx | dh] for the atomics of phase C (dh_next was consumed above; C == D so column j covers the dgctx half)
+      z[p.C + j] = 0.f;
+      for (int c = j; c < p.C; c += D) z[c] = 0.f;
+    }
+  }
+  grid_barrier(p.bar, target);               // dG_{t-1} (bf16 mirror) of every row is in L2, dxh is cleared
+  pdl_trigger();
+  if (!has_c) return;
+  for (int i = tid; i < 64 * cpr; i += 128) {
+    const int r = i / cpr, c = i % cpr;
+    cp_async16(sA + r * SK_PITCH + c * 8, p.dG_bf + (int64_t)min(r, p.Mb - 1) * p.dG_stride + c_k0 + c * 8, r < p.Mb);
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  skinny_tile_atomic(sA, sWc, SK_KC, p.dxh, CD, c_n0, CD, p.Mb);
+}
+
+int g_opt_dec_fuse_bwd = 1;
+
+int dec_step_bwd(const DecStepBwd& p, cudaStream_t st) {
+  LO_CHECK_ARG(p.K2 % SK_KC == 0 && p.K1 % SK_KC == 0 && p.D % SK_NT == 0 && (p.C + p.D) % SK_NT == 0 && p.C == p.D, "K1, K2 multiples of 512, C == D");
+  LO_CHECK_ARG((p.dcat_a == nullptr || (p.Ma >= 1 && p.Ma <= 64)) && (p.gates == nullptr || (p.Mb >= 1 && p.Mb <= 64)), "row counts <= 64");
+  LO_CHECK_ARG(p.bar && p.dxh, "null pointer");
+  static bool attr = false;
+  if (!attr) {
+    LO_CUDA(cudaFuncSetAttribute(dec_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKF_SMEM));
+    attr = true;
+  }
+  const int grid = ((p.C + p.D) / SK_NT) * (p.K1 / SK_KC);
+  LO_CHECK_ARG(grid <= 296 && grid >= (p.D / SK_NT) * (p.K2 / SK_KC), "fused step: grid must be co-resident and cover phase A");
+  LO_CUDA(launch_pdl(dec_step_bwd_kernel, dim3(grid), dim3(128), (size_t)SKF_SMEM, st, p));
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
 int skinny_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st) {
   LO_CHECK_ARG(M >= 1 && M <= 64 && K % 16 == 0 && K <= SK_KC && lda % 8 == 0 && ldw % 8 == 0 && D % 4 == 0, "M<=64, K%16, K<=512");
   static bool attr = false;

@@ -435,6 +435,191 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent 3x3 convolution (forward and data gradient): one CTA per SM walks over output tiles of 128 positions x NT
+// channels; TWO TMEM accumulators (2 x NT columns) so that the 128-thread epilogue of tile i drains while the MMA thread
+// already accumulates tile i+1; the TMA ring runs ahead across tile boundaries.  NT = 256 for the 256/512-channel layers:
+// per 64-wide K block a CTA pulls 16 KB of A + 32 KB of B from L2 for 4.2 MFLOP = 85 FLOP per L2 byte (128 x 128 tiles: 64).
+// The one-tile-per-CTA kernel above is L2-bandwidth bound at 45-56 % tensor-pipe activity (profiles/r1_tc_conv_r1_raw.csv).
+// ------------------------------------------------------------------------------------------------
+template <int NT, int STAGES>
+struct TcPSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = NT * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * NT * 4 /*bias, double buffered*/;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_p_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB, TcParams p, int ntiles_n,
+                                                                 int total_tiles) {
+  using SM = TcPSmem<NT, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;        // [2] accumulator complete
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * SM::STAGE_BYTES + 256);      // [2][NT]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.K / TC_BK;
+  const int cpb = p.Cin / TC_BK;
+  const int per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full_bar + s, 2);                // A producer + B producer
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(tfull_bar + b, 1);
+      mbar_init(tempty_bar + b, 4);              // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * NT);
+  pdl_wait();
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer, A tiles (implicit im2col: tap = coordinate shift, halo = out-of-bounds zero fill) =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / ntiles_n;
+        const int img = mt / per_img, rem = mt % per_img;
+        const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+        for (int kb = 0; kb < KB; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, SM::A_BYTES);
+          const int tap = kb / cpb, cb = kb % cpb;
+          const int r = tap / 3, q = tap % 3;
+          tma_load_4d(smem + s * SM::STAGE_BYTES, &mapA, full_bar + s, cb * TC_BK, w0 + q - p.pad, h0 + r - p.pad, img);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ===== TMA producer, B tiles (weights: re-read by every CTA -> keep them in L2) =====
+      const uint64_t polB = l2_policy_evict_last();
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % ntiles_n) * NT;
+        for (int kb = 0; kb < KB; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, SM::B_BYTES);
+          tma_load_2d_hint(smem + s * SM::STAGE_BYTES + SM::A_BYTES, &mapB, full_bar + s, kb * TC_BK, n0, polB);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, NT);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
+        const uint32_t buf = lt & 1;
+        mbar_wait(tempty_bar + buf, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (2 tiles ago)
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * NT;
+        for (int kb = 0; kb < KB; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint64_t da = make_kmajor_sw128_desc(sa);
+          const uint64_t db = make_kmajor_sw128_desc(sa + SM::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; k++) umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar + s);
+        }
+        umma_commit(tfull_bar + buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warps 2..5 ; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int te = threadIdx.x - 64;                               // 0..127
+    const bool use_mask = p.mask != nullptr;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
+      const uint32_t buf = lt & 1;
+      const int n0 = (tile % ntiles_n) * NT;
+      const int mt = tile / ntiles_n;
+      const int img = mt / per_img, rem = mt % per_img;
+      const int h = (rem / p.tiles_w) * p.BH + row / p.BW, w = (rem % p.tiles_w) * p.BW + row % p.BW;
+      const bool row_ok = (h < p.Ho) && (w < p.Wo);
+      const int64_t row_off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
+      float* sb = s_bias + buf * NT;
+      for (int c = te; c < NT; c += 128) sb[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");               // bias of this tile staged (buffer last read 2 tiles ago)
+      mbar_wait(tfull_bar + buf, (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * NT + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < NT; c += 32) {
+        uint4 mk4[4];
+        if (use_mask && row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; g++)
+            if (n0 + c + g * 8 < p.N) mk4[g] = *reinterpret_cast<const uint4*>(p.mask + row_off + n0 + c + g * 8);
+        }
+        uint32_t v[32];
+        tmem_ld32(tacc + (uint32_t)c, v);
+        if (!row_ok) continue;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const int n = n0 + c + g * 8;
+          if (n >= p.N) continue;
+          float f[8];
+          const float4 b0 = *reinterpret_cast<const float4*>(&sb[c + g * 8]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&sb[c + g * 8 + 4]);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]) + bb[i];
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (use_mask) {
+            const uint32_t wv[4] = {mk4[g].x, mk4[g].y, mk4[g].z, mk4[g].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              if (!(__uint_as_float(wv[i] << 16) > 0.f)) f[2 * i] = 0.f;
+              if (!(__uint_as_float(wv[i] & 0xffff0000u) > 0.f)) f[2 * i + 1] = 0.f;
+            }
+          }
+          st8(reinterpret_cast<bf16*>(p.out) + row_off + n, f);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + buf);                  // this warp's quarter of the accumulator is free again
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * NT);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weight gradient on tcgen05:  dW[co][tap][ci] += sum_p dY[p][co] * X[p + tap][ci]
 // GEMM view: M = co (128), N = ci (NT), K = output positions.  Both operands are "MN-major" (the channel index is
 // contiguous in NHWC), which UMMA takes directly: smem tile = [128 positions][64 channels] (one TMA box, SWIZZLE_128B),
@@ -761,6 +946,28 @@ int tc_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* C, 
   return tc_gemm_nt_ex(A, lda, W, ldw, C, dtC, ldc, M, N, K, bias, accumulate, relu, 1, 0, 0, st);
 }
 
+int g_opt_conv_persist = 1;   // persistent double-accumulator kernel (tc_conv_p_kernel); 0 = one tile per CTA (tc_gemm_conv_kernel)
+
+template <int NT, int STAGES>
+static int launch_conv_p(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, cudaStream_t st) {
+  using SM = TcPSmem<NT, STAGES>;
+  static bool attr_set = false;
+  static int n_sm = 0;
+  if (!attr_set) {
+    LO_CUDA(cudaFuncSetAttribute(tc_conv_p_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    int dev = 0;
+    LO_CUDA(cudaGetDevice(&dev));
+    LO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int ntn = cdiv(p.N, NT);
+  const int total = mtiles * ntn;
+  const int grid = total < n_sm ? total : n_sm;
+  LO_CUDA(launch_pdl(tc_conv_p_kernel<NT, STAGES>, dim3(grid), dim3(TC_THREADS), (size_t)SM::TOTAL, st, mA, mB, p, ntn, total));
+  LO_LAUNCH_OK();
+  return LO_OK;
+}
+
 int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask, bf16* y, int N, int H, int W, int Cin, int Cout,
                int pad, int relu, cudaStream_t st) {
   if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
@@ -769,6 +976,31 @@ int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask
   int BW = 128;
   while (BW > 8 && BW / 2 >= Wo) BW /= 2;     // smallest power of two >= Wo (capped at 128)
   const int BH = 128 / BW;
+  if (g_opt_conv_persist) {
+    const int NTp = Cout % 256 == 0 ? 256 : (Cout > 64 ? 128 : 64);
+    CUtensorMap mA, mB;
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+      LO_TRY(make_map(&mA, x, 4, dims, str, box));
+    }
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
+      cuuint64_t str[1] = {(cuuint64_t)9 * Cin * 2};
+      cuuint32_t box[2] = {64, (cuuint32_t)NTp};
+      LO_TRY(make_map(&mB, w, 2, dims, str, box));
+    }
+    TcParams p{};
+    p.M = N * Ho * Wo; p.N = Cout; p.K = 9 * Cin; p.conv = 1;
+    p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.pad = pad;
+    p.BW = BW; p.BH = BH; p.tiles_w = cdiv(Wo, BW); p.tiles_h = cdiv(Ho, BH);
+    p.bias = bias; p.mask = mask; p.out = y; p.ldc = Cout; p.relu = relu;
+    const int mtiles = N * p.tiles_w * p.tiles_h;
+    if (NTp == 256) return launch_conv_p<256, 4>(mA, mB, p, mtiles, st);
+    if (NTp == 128) return launch_conv_p<128, 6>(mA, mB, p, mtiles, st);
+    return launch_conv_p<64, 8>(mA, mB, p, mtiles, st);
+  }
   CUtensorMap mA, mB;
   const int NT = Cout <= 64 ? 64 : 128;
   const int mc = (g_opt_conv_mc && NT == 128 && cdiv(Cout, 128) % 2 == 0) ? 1 : 0;
