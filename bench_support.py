@@ -80,8 +80,18 @@ def kernel_probes(model, c, pk):
                                               ctypes.c_void_p(t["alphas"].data_ptr() + s * R * 4), T * R, _lib.ptr(t["ctx"][s]),
                                               None, 0, None, B, R, A, C, _lib.ptr(t["work"]), st))
 
-    ms_att = _time_ms(att_steps, 3) / T
-    att_bytes = B * R * (A + C) * bpe + B * R * 4
+    mask_step = t["att_mask"][0]          # [B][R][A/8] bits of one step (any step's bits give the same traffic)
+
+    def att_steps_mask():
+        for s in range(T):
+            o1 = t["out1"][s]
+            _lib.check(L.lo_attention_forward_mask(_lib.ptr(t["att1"]), _lib.ptr(enc_out), dt, _lib.ptr(o1), O1, a.w_full,
+                                                   ctypes.c_void_p(t["alphas"].data_ptr() + s * R * 4), T * R, _lib.ptr(t["ctx"][s]),
+                                                   None, 0, None, _lib.ptr(t["att_mask"][s]), B, R, A, C, _lib.ptr(t["work"]), st))
+
+    maskbits = bool(_lib.lib().lo_get_option(b"att_maskbits"))
+    ms_att = _time_ms(att_steps_mask if maskbits else att_steps, 3) / T
+    att_bytes = B * R * (A + C) * bpe + B * R * 4 + (B * R * A // 8 if maskbits else 0)
     traffic_tab = {}
     try:
         import json
@@ -111,12 +121,17 @@ def kernel_probes(model, c, pk):
                                                _lib.ptr(t["dxh"]), DX, _lib.ptr(t["dreg"]), R, ctypes.c_void_p(t["sreg"].data_ptr() + s * 4), T,
                                                ctypes.c_void_p(t["de"].data_ptr() + s * R * 4), _lib.ptr(t["dcat"][s]),
                                                ctypes.c_void_p(t["dcat"][s].data_ptr() + A * 4), O1, _lib.ptr(t["dctx"][s]), None,
-                                               B, R, A, C, _lib.ptr(t["work"]), st))
+                                               _lib.ptr(t["att_mask"][s]) if maskbits else None, B, R, A, C, _lib.ptr(t["work"]), st))
 
     ms_attb = _time_ms(att_bwd_steps, 3) / T
-    attb = {"kernel": "attention_bwd_pipe_kernel (d alpha, softmax backward, ReLU-mask sums, one decode step, TMA ring)", "bound": "hbm",
-            "achieved": att_bytes / (ms_attb * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-            "traffic": traffic_of("attention_bwd_pipe_kernel"), "us_per_launch": ms_attb * 1e3, "algorithmic_bytes": att_bytes,
+    # algorithmic bytes of the backward: enc read once + 1 mask bit per att1 element (or att1 itself without the mask scheme)
+    # + alpha read and d e written
+    attb_bytes = (B * R * C * bpe + B * R * A // 8 + 2 * B * R * 4) if maskbits else att_bytes
+    kname = "attention_bwd_mask_kernel" if maskbits else "attention_bwd_pipe_kernel"
+    attb = {"kernel": kname + " (d alpha, softmax backward, ReLU-mask sums, one decode step, TMA ring"
+                      + ("; streams enc + the forward's mask bits instead of enc + att1)" if maskbits else ")"), "bound": "hbm",
+            "achieved": attb_bytes / (ms_attb * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+            "traffic": traffic_of(kname), "us_per_launch": ms_attb * 1e3, "algorithmic_bytes": attb_bytes,
             "peak_source": pk["src"]}
     attb["frac"] = attb["achieved"] / attb["peak"]
 

@@ -40,6 +40,8 @@ int64_t lo_launch_count(void);
 /* tuning knobs: "att_pipe" (1: TMA-pipelined attention kernels, 0: register-streaming), "att_policy_enc" /
  * "att_policy_att1" (L2 policy 0 normal, 1 evict_last, 2 evict_first), "att_nsplit" (0 = automatic) */
 int lo_set_option(const char* name, int value);
+/* current value of a tuning knob (-1: unknown name) */
+int lo_get_option(const char* name);
 /* L2 persistence: access-policy window of `stream` over [base, base+bytes) (hits persist, misses stream) with the
  * persisting carve-out sized to fit; bytes = 0 resets.  The attention kernels honour it with att_policy_enc/att1 = 3
  * (bulk copies without an explicit cache hint). */
@@ -135,6 +137,12 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
                          const float* wf, float* alpha, int64_t alpha_stride, float* ctx,
                          float* gate_pre, int64_t gate_stride, float* gctx,
                          int B, int R, int A, int C, void* work, void* stream);
+/* the same, additionally storing the ReLU mask bits [B][R][A/8] (bit a % 8 of byte a / 8 = att1 + att2 > 0) for
+ * lo_attention_backward(relu_mask = ...) */
+int lo_attention_forward_mask(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
+                              const float* wf, float* alpha, int64_t alpha_stride, float* ctx,
+                              float* gate_pre, int64_t gate_stride, float* gctx, uint8_t* relu_mask_out,
+                              int B, int R, int A, int C, void* work, void* stream);
 
 /* Backward of one attention step (autograd of seq2seq_torch.py:186-190 + the gate of :311-312), reading att1 and enc ONCE:
  *   dctx = dgctx * gate ; dgp = dgctx * ctx * gate (1 - gate) ; s = <dctx, ctx> + sreg[b]
@@ -142,12 +150,14 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
  * att2 / gate [B][o1_stride] fp32 as the forward left them (gate after the sigmoid; NULL = ungated context) ; alpha / de
  * [B][alpha_stride] ; ctx / dctx_out [B][C] ; dgctx [B][dg_stride] ; dreg [B][dreg_stride] and sreg [B][sreg_stride] may be NULL ;
  * datt2 / dgp [B][dcat_stride] ; dwf_part (optional) [B][A] += sum_r de_r relu(att1_r + att2) (full_att.weight gradient).
- * d att1 and d enc are NOT produced here: they are hoisted out of the time loop (see lo_decoder_backward). */
+ * d att1 and d enc are NOT produced here: they are hoisted out of the time loop (see lo_decoder_backward).
+ * relu_mask (optional): the bits lo_attention_forward_mask stored; att1 is then NOT read (att2 is unused) and dwf_part is not
+ * accumulated. */
 int lo_attention_backward(const void* att1, const void* enc, int dt, const float* att2, const float* gate, int64_t o1_stride,
                           const float* wf, const float* alpha, int64_t alpha_stride, const float* ctx, const float* dgctx,
                           int64_t dg_stride, const float* dreg, int64_t dreg_stride, const float* sreg, int64_t sreg_stride,
                           float* de, float* datt2, float* dgp, int64_t dcat_stride, float* dctx_out, float* dwf_part,
-                          int B, int R, int A, int C, void* work, void* stream);
+                          const uint8_t* relu_mask, int B, int R, int A, int C, void* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole teacher-forced decoder: DecoderWithAttention.forward seq2seq_torch.py:267-320 (+ the loss of
@@ -191,6 +201,9 @@ typedef struct lo_decoder_args {
   float* call;             /* [T+1][B][D] */
   float* out1;             /* [T][B][A+C+4D]: att2 | gate (sigmoid applied) | h@w_hh^T+b_hh */
   float* alphas;           /* [B][T][R] */
+  uint8_t* att_mask;       /* optional, training only: [T][B][R][A/8] — bit (a % 8) of byte a/8 = (att1[b][r][a] + att2_t[b][a] > 0),
+                              written by the forward attention kernel; the backward then streams enc + these 64 bytes per region
+                              instead of enc + att1 (60.5 MB instead of 114 MB per step at cfg #2).  NULL: att1 is re-read. */
   float* ctx;              /* [T][B][C] */
   float* gctx;             /* [T][B][C] */
   float* gates;            /* [T][B][4D] post-activation i,f,g,o */
@@ -308,6 +321,9 @@ typedef struct lo_tfdec_args {
   /* results */
   float* logits;           /* [T][B][ldl] time-major */
   float* alphas;           /* [B][T][R] */
+  uint8_t* att_mask;       /* optional, training only: [T][B][R][A/8] — bit (a % 8) of byte a/8 = (att1[b][r][a] + att2_t[b][a] > 0),
+                              written by the forward attention kernel; the backward then streams enc + these 64 bytes per region
+                              instead of enc + att1 (60.5 MB instead of 114 MB per step at cfg #2).  NULL: att1 is re-read. */
   float* loss;             /* [4]: mean CE over valid tokens (x2), 0, n_words — ce_words (img2seq.py:74) = loss[0] * loss[3] */
   float* denc;             /* f32 [B][R][C] gradient w.r.t. the encoder output */
   void* ws;                /* lo_tfdec_workspace_bytes(args) bytes, zero-initialised once by the caller */

@@ -20,7 +20,8 @@ int g_opt_pdl = 1;               // programmatic dependent launch for the per-st
 int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
 int g_opt_att_policy_att1 = 2;
 int g_opt_att_nsplit = 0;        // 0 = automatic
-int g_opt_att_cluster = 1;       // 1: the splits of one batch row form a thread-block cluster and combine through DSMEM
+int g_opt_att_cluster = 1;
+int g_opt_att_maskbits = 1;      // 1: the forward attention kernel stores the ReLU mask bits, the backward streams them instead of att1       // 1: the splits of one batch row form a thread-block cluster and combine through DSMEM
 
 #define AP_THREADS 288
 #define AP_CWARPS 8
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
     float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
-    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, int pol_att1, int rpi) {
+    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, int pol_att1, int rpi, uint8_t* __restrict__ mask_out) {
   using C = ApCfg<T, NVA, NVC>;
   constexpr int CHA = C::CHA, CHC = C::CHC;
   extern __shared__ __align__(128) uint8_t ap_smem[];
@@ -148,16 +149,31 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
       const bool two = (C::RPW == 2) && (rb < rows);
       if (one) {
         float e0 = 0.f, e1 = 0.f;
+        // training (ReLU score): bit q of byte c/8 of row r = (att1[r][c] + att2[c] > 0); the backward reads these 64 bytes
+        // per row instead of the 1 KB att1 row
+        uint8_t* mrow = (ACT == 0 && mask_out) ? mask_out + ((int64_t)b * R + row) * (CHA / 8) : nullptr;
 #pragma unroll
         for (int j = 0; j < NVA; j++) {
           float v[8];
           ld8(sa + (size_t)ra * CHA + (j * 32 + lane) * 8, v);
+          uint32_t bits = 0;
 #pragma unroll
-          for (int q = 0; q < 8; q++) e0 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(v[q] + a2[j * 8 + q]), e0);
+          for (int q = 0; q < 8; q++) {
+            const float pre = v[q] + a2[j * 8 + q];
+            if (ACT == 0) bits |= (pre > 0.f ? 1u : 0u) << q;
+            e0 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(pre), e0);
+          }
+          if (mrow) mrow[(int64_t)ra * (CHA / 8) + j * 32 + lane] = (uint8_t)bits;
           if (two) {
             ld8(sa + (size_t)rb * CHA + (j * 32 + lane) * 8, v);
+            bits = 0;
 #pragma unroll
-            for (int q = 0; q < 8; q++) e1 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(v[q] + a2[j * 8 + q]), e1);
+            for (int q = 0; q < 8; q++) {
+              const float pre = v[q] + a2[j * 8 + q];
+              if (ACT == 0) bits |= (pre > 0.f ? 1u : 0u) << q;
+              e1 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(pre), e1);
+            }
+            if (mrow) mrow[(int64_t)rb * (CHA / 8) + j * 32 + lane] = (uint8_t)bits;
           }
         }
         e0 = warp_sum(e0);
@@ -566,6 +582,233 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Attention backward, mask-bit version (ReLU score): the forward kernel left 1 bit per att1 element (att1 + att2 > 0), so the
+// backward streams enc rows (CHC elements) + CHA/8 mask bytes per region instead of enc + att1 rows: 60.5 MB instead of
+// 114 MB per step at cfg #2.  Same math, same masks (the bits ARE the forward's comparisons), same combine order.
+// d w_full is not accumulated here (it needs relu(att1 + att2) itself): the post-loop sweep (datt1_kernel<.., WACC=true>) adds it.
+// ------------------------------------------------------------------------------------------------------------------------------
+#define APM_STAGES 5
+template <typename T, int NVA, int NVC>
+struct ApmCfg {
+  static constexpr int CHA = NVA * 256, CHC = NVC * 256;
+  static constexpr int RPW = (sizeof(T) == 2 && NVC <= 2) ? 2 : 1;
+  static constexpr int ROWS = AP_CWARPS * RPW;
+  static constexpr int ENC_BYTES = ROWS * CHC * (int)sizeof(T);
+  static constexpr int MSK_BYTES = ROWS * (CHA / 8);
+  static constexpr int STAGE_BYTES = ENC_BYTES + MSK_BYTES;
+  static constexpr int SMEM = APM_STAGES * STAGE_BYTES + 128;
+  static_assert(APM_STAGES * STAGE_BYTES >= (AP_CWARPS + 2) * CHA * 4, "combine scratch must fit in the ring");
+};
+
+template <typename T, int NVA, int NVC, bool CL>
+__global__ void __launch_bounds__(AP_THREADS) attention_bwd_mask_kernel(
+    const uint8_t* __restrict__ mask, const T* __restrict__ enc, const float* __restrict__ gate, int64_t o1_stride,
+    const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride, const float* __restrict__ ctx,
+    const float* __restrict__ dgctx, int64_t dg_stride, const float* __restrict__ dreg, int64_t dreg_stride,
+    const float* __restrict__ sreg, int64_t sreg_stride, float* __restrict__ de, float* __restrict__ datt2, float* __restrict__ dgp,
+    int64_t dcat_stride, bf16* __restrict__ datt2_bf, bf16* __restrict__ dgp_bf, float* __restrict__ dctx_out, int R, int nsplit,
+    int* __restrict__ counters, float* __restrict__ partials, int pol_enc) {
+  using C = ApmCfg<T, NVA, NVC>;
+  constexpr int CHA = C::CHA, CHC = C::CHC, MB = CHA / 8;
+  extern __shared__ __align__(128) uint8_t ap_smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + APM_STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + APM_STAGES;
+  __shared__ int s_last;
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rps = (R + nsplit - 1) / nsplit;
+  const int r0 = sp * rps, r1 = min(R, r0 + rps);
+  const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
+  const T* eb = enc + (int64_t)b * R * CHC;
+  const uint8_t* mb = mask + (int64_t)b * R * MB;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < APM_STAGES; s++) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, AP_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  float macc[NVA * 8];
+#pragma unroll
+  for (int i = 0; i < NVA * 8; i++) macc[i] = 0.f;
+
+  if (wid == AP_CWARPS) {
+    // producer: enc is loop-invariant (prefetchable before griddepcontrol.wait); the mask bits of this step were written by the
+    // forward pass long ago as well
+    if (lane == 0) {
+      const uint64_t pe = make_policy(pol_enc), pm = l2_policy_evict_first();
+      for (int i = 0; i < nst; i++) {
+        const int s = i % APM_STAGES;
+        const uint32_t ph = (i / APM_STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        const int row = r0 + i * C::ROWS;
+        const int rows = min(C::ROWS, r1 - row);
+        const uint32_t bytes_c = (uint32_t)rows * CHC * (uint32_t)sizeof(T), bytes_m = (uint32_t)rows * MB;
+        uint8_t* st = ap_smem + (size_t)s * C::STAGE_BYTES;
+        mbar_expect_tx(full_bar + s, bytes_c + bytes_m);
+        bulk_g2s(st, eb + (int64_t)row * CHC, bytes_c, full_bar + s, pe);
+        bulk_g2s(st + C::ENC_BYTES, mb + (int64_t)row * MB, bytes_m, full_bar + s, pm);
+      }
+    }
+    __syncwarp();
+    pdl_wait();
+  } else {
+    float dc[NVC * 8];
+    float sdot = 0.f;
+    float gv[NVC * 8], cxv[NVC * 8];
+#pragma unroll
+    for (int j = 0; j < NVC; j++) {
+      const int c0 = (j * 32 + lane) * 8;
+      if (gate) ld8(gate + (int64_t)b * o1_stride + c0, gv + j * 8);
+      ld8(ctx + (int64_t)b * CHC + c0, cxv + j * 8);
+    }
+    const float sreg_b = sreg ? sreg[(int64_t)b * sreg_stride] : 0.f;
+    pdl_wait();
+    pdl_trigger();
+#pragma unroll
+    for (int j = 0; j < NVC; j++) {
+      const int c0 = (j * 32 + lane) * 8;
+      float dg[8], gp[8];
+      ld8(dgctx + (int64_t)b * dg_stride + c0, dg);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float gi = gate ? gv[j * 8 + i] : 1.f;
+        dc[j * 8 + i] = dg[i] * gi;
+        sdot = fmaf(dc[j * 8 + i], cxv[j * 8 + i], sdot);
+        gp[i] = dg[i] * cxv[j * 8 + i] * gi * (1.f - gi);
+      }
+      if (sp == 0 && wid == 0) {
+        if (dgp) st8(dgp + (int64_t)b * dcat_stride + c0, gp);
+        if (dgp_bf) st8(dgp_bf + (int64_t)b * dcat_stride + c0, gp);
+        if (dctx_out) st8(dctx_out + (int64_t)b * CHC + c0, dc + j * 8);
+      }
+    }
+    const float sall = warp_sum(sdot) + sreg_b;
+    const float* alb = alpha + (int64_t)b * alpha_stride;
+    float* deb = de + (int64_t)b * alpha_stride;
+    const float* drb = dreg + (int64_t)b * dreg_stride;
+    float pa0 = 0.f, pa1 = 0.f, pd0 = 0.f, pd1 = 0.f;
+    auto prefetch = [&](int i) {
+      const int row = r0 + i * C::ROWS;
+      const int rows = min(C::ROWS, r1 - row);
+      const int ra = wid, rb = wid + AP_CWARPS;
+      if (i < nst && ra < rows) {
+        pa0 = alb[row + ra];
+        pd0 = dreg ? drb[row + ra] : 0.f;
+        if (C::RPW == 2 && rb < rows) {
+          pa1 = alb[row + rb];
+          pd1 = dreg ? drb[row + rb] : 0.f;
+        }
+      }
+    };
+    prefetch(0);
+    for (int i = 0; i < nst; i++) {
+      const int s = i % APM_STAGES;
+      const uint32_t ph = (i / APM_STAGES) & 1;
+      const int row = r0 + i * C::ROWS;
+      const int rows = min(C::ROWS, r1 - row);
+      const float al0 = pa0, al1 = pa1, dr0 = pd0, dr1 = pd1;
+      prefetch(i + 1);
+      mbar_wait(full_bar + s, ph);
+      const T* se = reinterpret_cast<const T*>(ap_smem + (size_t)s * C::STAGE_BYTES);
+      const uint8_t* sm = ap_smem + (size_t)s * C::STAGE_BYTES + C::ENC_BYTES;
+      const int ra = wid, rb = wid + AP_CWARPS;
+      const bool one = ra < rows;
+      const bool two = (C::RPW == 2) && (rb < rows);
+      if (one) {
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NVC; j++) {
+          float u[8];
+          ld8(se + (size_t)ra * CHC + (j * 32 + lane) * 8, u);
+#pragma unroll
+          for (int q = 0; q < 8; q++) d0 = fmaf(dc[j * 8 + q], u[q], d0);
+          if (two) {
+            ld8(se + (size_t)rb * CHC + (j * 32 + lane) * 8, u);
+#pragma unroll
+            for (int q = 0; q < 8; q++) d1 = fmaf(dc[j * 8 + q], u[q], d1);
+          }
+        }
+        d0 = warp_sum(d0);
+        d1 = warp_sum(d1);
+        const float de0 = al0 * (d0 + dr0 - sall);
+        const float de1 = two ? al1 * (d1 + dr1 - sall) : 0.f;
+        if (lane == 0) {
+          deb[row + ra] = de0;
+          if (two) deb[row + rb] = de1;
+        }
+#pragma unroll
+        for (int j = 0; j < NVA; j++) {
+          const uint32_t m0 = sm[ra * MB + j * 32 + lane];
+          const uint32_t m1 = two ? sm[rb * MB + j * 32 + lane] : 0u;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            macc[j * 8 + q] += ((m0 >> q) & 1u) ? de0 : 0.f;
+            macc[j * 8 + q] += ((m1 >> q) & 1u) ? de1 : 0.f;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + s);
+    }
+  }
+  __syncthreads();
+  float* s_acc = reinterpret_cast<float*>(ap_smem);            // [8][CHA] mask sums | [CHA] CTA totals
+  float* s_part = s_acc + AP_CWARPS * CHA;
+  if (wid < AP_CWARPS) {
+#pragma unroll
+    for (int j = 0; j < NVA; j++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) s_acc[wid * CHA + (j * 32 + lane) * 8 + i] = macc[j * 8 + i];
+  }
+  __syncthreads();
+  if constexpr (CL) {
+    cg::cluster_group cluster = cg::this_cluster();
+    for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < AP_CWARPS; w++) t += s_acc[w * CHA + c];
+      s_part[c] = t;
+    }
+    cluster.sync();
+    const int cps = (CHA + nsplit - 1) / nsplit;
+    for (int c = sp * cps + threadIdx.x; c < min(CHA, (sp + 1) * cps); c += AP_THREADS) {
+      float t = 0.f;
+      for (int q = 0; q < nsplit; q++) t += cluster.map_shared_rank(s_part, q)[c];      // fixed order -> deterministic
+      datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+      if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
+    }
+    cluster.sync();
+    return;
+  }
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CHA + 2);
+  for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < AP_CWARPS; w++) t += s_acc[w * CHA + c];
+    part[2 + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + b, 1);
+    s_last = (ticket == nsplit - 1);
+    if (s_last) counters[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = partials + (int64_t)b * nsplit * (CHA + 2);
+  for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
+    float t = 0.f;
+    for (int sidx = 0; sidx < nsplit; sidx++) t += __ldcg(pb + (int64_t)sidx * (CHA + 2) + 2 + c);
+    datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+    if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
+  }
+}
+
 int att_pipe_splits(int B, int hint = 0) {
   if (hint > 0) return hint > 8 ? 8 : hint;
   if (g_opt_att_nsplit > 0) return g_opt_att_nsplit > AP_MAXSPLIT ? AP_MAXSPLIT : g_opt_att_nsplit;
@@ -636,11 +879,11 @@ static int fwd_launch_a(const AttFwdArgs& x, cudaStream_t st) {
     const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
     LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc, x.att2,
                        x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R, ns,
-                       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
+                       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi, x.mask_out));
   } else {
     LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1, (const T*)x.enc,
                        x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R,
-                       ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi));
+                       ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi, x.mask_out));
   }
   LO_LAUNCH_OK();
   return LO_OK;
@@ -675,6 +918,27 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
+  if constexpr (ACT == 0) if (x.mask_in) {
+    using CM = ApmCfg<T, NVA, NVC>;
+    static bool attr_m = false;
+    if (!attr_m) {
+      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mask_kernel<T, NVA, NVC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM::SMEM));
+      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mask_kernel<T, NVA, NVC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM::SMEM));
+      attr_m = true;
+    }
+#define LO_BWDM_ARGS                                                                                                                  \
+  x.mask_in, (const T*)x.enc, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride, x.dreg, x.dreg_stride, \
+      x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns, (int*)x.work,           \
+      (float*)((char*)x.work + 4096), g_opt_att_policy_enc
+    if (use_cluster(ns, x.R)) {
+      LO_CUDA(launch_att(attention_bwd_mask_kernel<T, NVA, NVC, true>, dim3(ns, x.B), (size_t)CM::SMEM, ns, st, LO_BWDM_ARGS));
+    } else {
+      LO_CUDA(launch_att(attention_bwd_mask_kernel<T, NVA, NVC, false>, dim3(ns, x.B), (size_t)CM::SMEM, 1, st, LO_BWDM_ARGS));
+    }
+#undef LO_BWDM_ARGS
+    LO_LAUNCH_OK();
+    return LO_OK;
+  }
 #define LO_BWD_ARGS                                                                                                              \
   (const T*)x.att1, (const T*)x.enc, x.att2, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride, x.dreg, \
       x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,       \
@@ -740,6 +1004,21 @@ extern "C" int lo_set_l2_window(const void* base, int64_t bytes, float hit_ratio
   return LO_OK;
 }
 
+extern "C" int lo_get_option(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "att_pipe")) return lo::g_opt_att_pipe;
+  if (!strcmp(name, "att_maskbits")) return lo::g_opt_att_maskbits;
+  if (!strcmp(name, "att_cluster")) return lo::g_opt_att_cluster;
+  if (!strcmp(name, "pdl")) return lo::g_opt_pdl;
+  if (!strcmp(name, "conv_persist")) return lo::g_opt_conv_persist;
+  if (!strcmp(name, "dec_fuse")) return lo::g_opt_dec_fuse;
+  if (!strcmp(name, "dec_fuse_bwd")) return lo::g_opt_dec_fuse_bwd;
+  if (!strcmp(name, "fuse_lstm")) return lo::g_opt_fuse_lstm;
+  if (!strcmp(name, "skinny_mma")) return lo::g_opt_skinny_mma;
+  if (!strcmp(name, "dec_streams")) return lo::g_opt_dec_streams;
+  return -1;
+}
+
 extern "C" int lo_set_option(const char* name, int value) {
   if (!name) return LO_EINVAL;
   if (!strcmp(name, "att_pipe")) lo::g_opt_att_pipe = value;
@@ -748,6 +1027,7 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "att_nsplit")) lo::g_opt_att_nsplit = value;
   else if (!strcmp(name, "pdl")) lo::g_opt_pdl = value;
   else if (!strcmp(name, "att_cluster")) lo::g_opt_att_cluster = value;
+  else if (!strcmp(name, "att_maskbits")) lo::g_opt_att_maskbits = value;
   else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
   else if (!strcmp(name, "conv_persist")) lo::g_opt_conv_persist = value;
   else if (!strcmp(name, "dec_streams")) { lo::g_opt_dec_streams = value; lo::g_opt_skinny8 = value >= 2 ? 0 : 1; }

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
   __shared__ float s_w[8][64];
   const int b = blockIdx.z, r0 = blockIdx.y * 32, a0 = blockIdx.x * 64;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;   // a = a0 + tx*4.., r = r0 + ty*4..
-  float x[4][4], acc[4][4], wacc[4];
+  float x[4][4], nx[4][4], acc[4][4], wacc[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     wacc[i] = 0.f;
@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
     for (int j = 0; j < 4; j++) {
       acc[i][j] = 0.f;
       x[i][j] = (r < R) ? ldf(att1 + ((int64_t)b * R + r) * A + a0 + tx * 4 + j) : -INFINITY;
+      nx[i][j] = -x[i][j];
     }
   }
   for (int t0 = 0; t0 < Tn; t0 += TT) {
@@ -330,12 +331,13 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const float pre = x[i][j] + a2v[j];
           if constexpr (ACT == 0) {
-            const bool on = pre > 0.f;
+            // x + a2 > 0  <=>  a2 > -x exactly (an fp32 sum has the sign of the exact sum): one compare + one predicated add
+            const bool on = a2v[j] > nx[i][j];
             acc[i][j] += on ? dv[i] : 0.f;
-            if (WACC) wacc[j] = fmaf(dv[i], on ? pre : 0.f, wacc[j]);   // (never 0 * -inf: padded rows carry pre = -inf)
+            if (WACC) wacc[j] = fmaf(dv[i], on ? a2v[j] - nx[i][j] : 0.f, wacc[j]);   // (padded rows: nx = +inf -> never on)
           } else {
+            const float pre = x[i][j] + a2v[j];
             // tanh score (Genthial cell); padded rows: tanh(-inf) = -1 -> derivative 0, dv = 0
             const float post = tanhf(pre);
             acc[i][j] = fmaf(dv[i], 1.f - post * post, acc[i][j]);
@@ -836,17 +838,22 @@ static int check_args(const lo_decoder_args* a) {
 }
 
 static int* work_counters(const lo_decoder_args* a) { return (int*)a->work; }
+// ReLU mask bits of step t, first row r0 (NULL when the scheme is off)
+static inline uint8_t* att_mask_at(const lo_decoder_args* a, int t, int64_t r0) {
+  if (!a->att_mask || !g_opt_att_maskbits || !g_opt_att_pipe || a->rows_per_img > 1) return nullptr;
+  return a->att_mask + ((int64_t)t * a->B + r0) * a->R * (a->A / 8);
+}
 static float* work_partials(const lo_decoder_args* a) { return (float*)((char*)a->work + 4096); }
 static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a->work + 2048); }
 
 static int attention_forward_launch(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                                     const float* wf, float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre,
                                     int64_t gate_stride, float* gctx, bf16* gctx_bf, int B, int R, int C, void* work, cudaStream_t st,
-                                    int rpi = 1, int nsplit_hint = 0) {
+                                    int rpi = 1, int nsplit_hint = 0, uint8_t* mask_out = nullptr) {
   if (rpi < 1) rpi = 1;
   if (g_opt_att_pipe) {
     AttFwdArgs x{att1, enc, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, B, R, work, rpi,
-                 nsplit_hint};
+                 nsplit_hint, 0, 0, mask_out};
     return attention_fwd_pipe(x, dt, C, st);
   }
   const int ns = att_splits(B);
@@ -997,7 +1004,7 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
   LO_TRY(attention_forward_launch(att1, enc, dt, o1, d.O1, a->w_full, a->alphas + (r0 * d.T + t) * d.R, (int64_t)d.T * d.R,
                                   a->ctx + ((int64_t)t * d.B + r0) * d.C, o1 + d.A, d.O1, a->gctx + ((int64_t)t * d.B + r0) * d.C,
                                   bv.on ? bv.gctx + ((int64_t)t * d.B + r0) * d.C : nullptr, nrows, d.R, d.C, rs.work, st,
-                                  a->rows_per_img, rs.nsplit));
+                                  a->rows_per_img, rs.nsplit, hd_t ? att_mask_at(a, t, r0) : nullptr));
   // gates_x = (gate*ctx) @ W_ih[:, E:]^T
   if (bv.on && g_opt_fuse_lstm) {
     // ... with the LSTM cell fused into the GEMM epilogue (no gates_x round trip, one launch less per step)
@@ -1091,17 +1098,29 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
                                   B, R, C, work, (cudaStream_t)stream);
 }
 
+int lo_attention_forward_mask(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride, const float* wf,
+                              float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre, int64_t gate_stride, float* gctx,
+                              uint8_t* relu_mask_out, int B, int R, int A, int C, void* work, void* stream) {
+  LO_CHECK_ARG(att1 && enc && att2 && wf && alpha && ctx && work, "null pointer");
+  LO_CHECK_ARG(A == C && (C == 256 || C == 512 || C == 1024), "attention_dim == encoder_dim in {256,512,1024}");
+  LO_CHECK_ARG(B > 0 && B <= 512 && R > 0, "B in 1..512, R > 0");
+  LO_CHECK_ARG(att2_stride % 4 == 0, "att2 rows must be 16-byte aligned");
+  LO_CHECK_ARG(!relu_mask_out || g_opt_att_pipe, "mask bits are written by the TMA-ring kernel (option att_pipe=1)");
+  return attention_forward_launch(att1, enc, dt, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, nullptr,
+                                  B, R, C, work, (cudaStream_t)stream, 1, 0, relu_mask_out);
+}
+
 int lo_attention_backward(const void* att1, const void* enc, int dt, const float* att2, const float* gate, int64_t o1_stride,
                           const float* wf, const float* alpha, int64_t alpha_stride, const float* ctx, const float* dgctx,
                           int64_t dg_stride, const float* dreg, int64_t dreg_stride, const float* sreg, int64_t sreg_stride, float* de,
-                          float* datt2, float* dgp, int64_t dcat_stride, float* dctx_out, float* dwf_part, int B, int R, int A, int C,
-                          void* work, void* stream) {
+                          float* datt2, float* dgp, int64_t dcat_stride, float* dctx_out, float* dwf_part, const uint8_t* relu_mask,
+                          int B, int R, int A, int C, void* work, void* stream) {
   LO_CHECK_ARG(att1 && enc && att2 && wf && alpha && ctx && dgctx && de && datt2 && work, "null pointer");
   LO_CHECK_ARG(A == C && (C == 256 || C == 512 || C == 1024), "attention_dim == encoder_dim in {256,512,1024}");
   LO_CHECK_ARG(B > 0 && B <= 512 && R > 0, "B in 1..512, R > 0");
   LO_CHECK_ARG(g_opt_att_pipe, "stand-alone attention backward runs on the TMA-ring kernel (option att_pipe=1)");
   AttBwdArgs x{att1, enc, att2, gate, o1_stride, wf, alpha, alpha_stride, ctx, dgctx, dg_stride, dreg, dreg_stride, sreg, sreg_stride,
-               de, datt2, dgp, dcat_stride, nullptr, nullptr, dctx_out, B, R, work, dwf_part, 0};
+               de, datt2, dgp, dcat_stride, nullptr, nullptr, dctx_out, B, R, work, dwf_part, 0, 0, 0, relu_mask};
   return attention_bwd_pipe(x, dt, C, (cudaStream_t)stream);
 }
 
@@ -1137,7 +1156,7 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
       float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
       LO_TRY(attention_forward_launch(a->att1, a->enc, a->dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
                                       a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C,
-                                      bvs.gctx + (int64_t)t * d.B * d.C, nrows, d.R, d.C, a->work, st, 1, 0));
+                                      bvs.gctx + (int64_t)t * d.B * d.C, nrows, d.R, d.C, a->work, st, 1, 0, att_mask_at(a, t, 0)));
       DecStepFwd p{};
       p.gctx = bvs.gctx + (int64_t)t * d.B * d.C; p.ld_gctx = d.C;
       p.wil = bvs.wil; p.ld_wil = d.C;
@@ -1299,7 +1318,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
       AttBwdArgs x{a->att1, a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
                    a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T,
                    a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t + d.A, a->dctx + (int64_t)t * d.B * d.C,
-                   nrows, d.R, a->work, a->dmean, 0};
+                   nrows, d.R, a->work, a->dmean, 0, 0, 0, att_mask_at(a, t, 0)};
       LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
       DecStepBwd p{};
       p.dcat_a = dcat_bf_t; p.ld_dcat = d.O1; p.wbwd2 = (const bf16*)a->wbwd2; p.ld_w2 = d.A + d.C; p.K2 = d.A + d.C; p.Ma = nrows;
@@ -1356,7 +1375,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     if (g_opt_att_pipe) {
       AttBwdArgs x{att1, enc, o1, o1 + d.A, d.O1, a->w_full, alpha_t, (int64_t)d.T * d.R, ctx_t, dxh, d.C + d.D, dal_t_ptr, dal_b, sreg_t,
                    d.T, de_t, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr, dctx_t, nrows, d.R, rs.work,
-                   a->dmean + r0 * d.A, rs.nsplit};
+                   a->dmean + r0 * d.A, rs.nsplit, 0, 0, att_mask_at(a, t, r0)};
       LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
     } else {
     int* cnt_c = (int*)rs.work;
@@ -1441,7 +1460,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   LO_CUDA(cudaMemsetAsync(a->g_b_full, 0, 4, st));   // sum_r de = 0 exactly (softmax); reference value is rounding noise
   {
     dim3 grid(d.A / 64, cdiv(d.R, 32), d.B);
-    if (g_opt_att_pipe) {
+    if (g_opt_att_pipe && !att_mask_at(a, 0, 0)) {
       // d w_full was accumulated per batch row by the attention backward kernels (dmean doubles as the [B][A] scratch)
       LO_TRY(colsum(a->dmean, LO_F32, a->g_w_full, d.B, d.A, d.A, 0, st));
       LO_DISPATCH_DT(dt, T, (datt1_kernel<T, false><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,

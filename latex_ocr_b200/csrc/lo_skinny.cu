@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
   }
 }
 
-int g_opt_dec_fuse = 1;
+int g_opt_dec_fuse = 0;       // measured: 13.46 vs 13.35 ms decoder fwd+bwd (run 42) - PDL already hides what the fusion removes
 
 int dec_step_fwd(const DecStepFwd& p, cudaStream_t st) {
   LO_CHECK_ARG(p.M >= 1 && p.M <= 64 && p.K % 16 == 0 && p.K <= SK_KC && p.e.D == p.K && p.e.D % 4 == 0 && p.N2 % 2 == 0, "M<=64, K=D<=512");
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(128) dec_step_bwd_kernel(DecStepBwd p) {
   skinny_tile_atomic(sA, sWc, SK_KC, p.dxh, CD, c_n0, CD, p.Mb);
 }
 
-int g_opt_dec_fuse_bwd = 1;
+int g_opt_dec_fuse_bwd = 0;   // measured: 13.78 vs 13.46 ms (run 42): two grid barriers cost more than two PDL boundaries
 
 int dec_step_bwd(const DecStepBwd& p, cudaStream_t st) {
   LO_CHECK_ARG(p.K2 % SK_KC == 0 && p.K1 % SK_KC == 0 && p.D % SK_NT == 0 && (p.C + p.D) % SK_NT == 0 && p.C == p.D, "K1, K2 multiples of 512, C == D");

@@ -229,7 +229,9 @@ class DecoderWithAttention(nn.Module):
             t["datt1"] = z(B, R, A, dtype=self.tdtype)
             t["denc"] = z(B, R, C)
             t["dinit"] = z(B, 2 * D)
-            t["dmean"] = z(B, C)
+            t["dmean"] = z(B, max(A, C))
+            # ReLU mask bits of every step (forward attention kernel -> backward attention kernel), 1 bit per att1 element
+            t["att_mask"] = torch.empty(T, B, R, A // 8, dtype=torch.uint8, device=dev)
             ws["need_grad"] = True
         return ws
 
@@ -277,7 +279,7 @@ class DecoderWithAttention(nn.Module):
             a.dropout_mask = t["dropout_mask"].data_ptr()
         if ws["need_grad"]:
             for k in ("wbwd1", "wbwd2", "dlogits", "dhd", "dreg", "dcat", "dxh", "dc", "dctx", "de", "dptab", "datt1", "denc",
-                      "dinit", "dmean"):
+                      "dinit", "dmean", "att_mask"):
                 setattr(a, k, t[k].data_ptr())
             a.g_w_enc_att, a.g_b_enc_att = Gd("attention.encoder_att.weight"), Gd("attention.encoder_att.bias")
             a.g_wcat1, a.g_bcat1 = Gd("attention.decoder_att.weight"), Gd("attention.decoder_att.bias")
