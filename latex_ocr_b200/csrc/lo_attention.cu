@@ -64,7 +64,7 @@ struct ApCfg {
   static constexpr int SMEM = AP_STAGES * STAGE_BYTES + 128;
 };
 
-template <typename T, int NVA, int NVC, bool CL, int ACT>
+template <typename T, int NVA, int NVC, bool CL, int ACT, bool MK>
 __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
@@ -149,9 +149,9 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
       const bool two = (C::RPW == 2) && (rb < rows);
       if (one) {
         float e0 = 0.f, e1 = 0.f;
-        // training (ReLU score): bit q of byte c/8 of row r = (att1[r][c] + att2[c] > 0); the backward reads these 64 bytes
-        // per row instead of the 1 KB att1 row
-        uint8_t* mrow = (ACT == 0 && mask_out) ? mask_out + ((int64_t)b * R + row) * (CHA / 8) : nullptr;
+        // training (ReLU score): bit 7 - (c % 8) of byte c/8 of row r = (att1[r][c] + att2[c] > 0); the backward reads these
+        // 64 bytes per row instead of the 1 KB att1 row
+        uint8_t* mrow = MK ? mask_out + ((int64_t)b * R + row) * (CHA / 8) : nullptr;
 #pragma unroll
         for (int j = 0; j < NVA; j++) {
           float v[8];
@@ -160,20 +160,22 @@ __global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const float pre = v[q] + a2[j * 8 + q];
-            if (ACT == 0) bits |= (pre > 0.f ? 1u : 0u) << q;
+            // one funnel shift per element collects the SIGN bits (element q -> bit 7-q); pre > 0 <=> sign clear, except for
+            // pre == +0 exactly, where the ReLU subgradient is a convention and which a sum of a bf16 and an fp32 never hits
+            if (MK) bits = __funnelshift_l(__float_as_uint(pre), bits, 1);
             e0 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(pre), e0);
           }
-          if (mrow) mrow[(int64_t)ra * (CHA / 8) + j * 32 + lane] = (uint8_t)bits;
+          if (MK) mrow[(int64_t)ra * (CHA / 8) + j * 32 + lane] = (uint8_t)(~bits);
           if (two) {
             ld8(sa + (size_t)rb * CHA + (j * 32 + lane) * 8, v);
             bits = 0;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const float pre = v[q] + a2[j * 8 + q];
-              if (ACT == 0) bits |= (pre > 0.f ? 1u : 0u) << q;
+              if (MK) bits = __funnelshift_l(__float_as_uint(pre), bits, 1);
               e1 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(pre), e1);
             }
-            if (mrow) mrow[(int64_t)rb * (CHA / 8) + j * 32 + lane] = (uint8_t)bits;
+            if (MK) mrow[(int64_t)rb * (CHA / 8) + j * 32 + lane] = (uint8_t)(~bits);
           }
         }
         e0 = warp_sum(e0);
@@ -745,8 +747,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_mask_kernel(
           const uint32_t m1 = two ? sm[rb * MB + j * 32 + lane] : 0u;
 #pragma unroll
           for (int q = 0; q < 8; q++) {
-            macc[j * 8 + q] += ((m0 >> q) & 1u) ? de0 : 0.f;
-            macc[j * 8 + q] += ((m1 >> q) & 1u) ? de1 : 0.f;
+            if (m0 & (0x80u >> q)) macc[j * 8 + q] += de0;
+            if (m1 & (0x80u >> q)) macc[j * 8 + q] += de1;
           }
         }
       }
@@ -863,30 +865,39 @@ static inline bool use_cluster(int ns, int R) {
   return g_opt_att_cluster && ns >= 2 && ns <= 8 && ((R + ns - 1) / ns) * 4 <= 16 * 1024;
 }
 
-template <typename T, int NVA, int NVC, int ACT>
-static int fwd_launch_a(const AttFwdArgs& x, cudaStream_t st) {
+template <typename T, int NVA, int NVC, int ACT, bool MK>
+static int fwd_launch_m(const AttFwdArgs& x, cudaStream_t st) {
   using C = ApCfg<T, NVA, NVC>;
   constexpr int SM_MAX = C::SMEM + 16 * 1024;
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LO_CUDA(cudaFuncSetAttribute(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
   const int rpi = x.rows_per_img > 1 ? x.rows_per_img : 1;
   if (use_cluster(ns, x.R)) {
     const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc, x.att2,
-                       x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R, ns,
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT, MK>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc,
+                       x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R, ns,
                        (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi, x.mask_out));
   } else {
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1, (const T*)x.enc,
-                       x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R,
-                       ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi, x.mask_out));
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT, MK>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1,
+                       (const T*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx,
+                       x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi,
+                       x.mask_out));
   }
   LO_LAUNCH_OK();
   return LO_OK;
+}
+
+template <typename T, int NVA, int NVC, int ACT>
+static int fwd_launch_a(const AttFwdArgs& x, cudaStream_t st) {
+  if constexpr (ACT == 0) {
+    if (x.mask_out) return fwd_launch_m<T, NVA, NVC, ACT, true>(x, st);        // training: also emit the ReLU mask bits
+  }
+  return fwd_launch_m<T, NVA, NVC, ACT, false>(x, st);
 }
 
 template <typename T, int NVA, int NVC>
