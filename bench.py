@@ -217,9 +217,21 @@ def main():
     ms, ms_e2e = t[0].item(), t[1].item()
     log("e2e: %.2f ms/step" % ms_e2e)
     per_step_launches = bs.launches_per_step(model, img_dev, formula_dev)
-    if rank != 0:
+
+    def finish():
+        """N > 1: every rank waits here until rank 0 has printed its line, then the process leaves WITHOUT tearing the NCCL
+        communicator down — ncclCommDestroy blocks while captured CUDA graphs still hold the communicator's kernels (observed
+        as a teardown hang at N=2, run 46); the OS reclaims everything."""
         if world > 1:
-            dist.destroy_process_group()
+            model._graphs.clear()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     pk = peaks()
     total_imgs = c["B"] * world
@@ -253,8 +265,7 @@ def main():
     if not args.skip_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only (the scaling runs stay short)
         out["cpu_baseline"] = bs.cpu_baseline(c)
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
