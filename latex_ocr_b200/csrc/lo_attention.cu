@@ -21,7 +21,6 @@ int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
 int g_opt_att_policy_att1 = 2;
 int g_opt_att_nsplit = 0;        // 0 = automatic
 int g_opt_att_cluster = 1;
-int g_opt_att_mma = 1;           // bf16 storage: context accumulation of the forward kernel on mma.sync (attention_fwd_mma_kernel)
 int g_opt_att_maskbits = 1;      // 1: the forward attention kernel stores the ReLU mask bits, the backward streams them instead of att1       // 1: the splits of one batch row form a thread-block cluster and combine through DSMEM
 
 #define AP_THREADS 288
@@ -587,304 +586,6 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
-// Attention forward, tensor-core context (bf16 storage): the TMA-ring kernel above is limited by instruction issue, not by
-// HBM (adding 8 shifts per 8 elements cost 7 %), and half of its instructions are the context accumulation
-// ctx += p_r * enc_r (unpack bf16, multiply-add, rescale).  Here the scores stay on the CUDA cores in fp32 (two rows per warp,
-// exactly the arithmetic of the kernel above, so the ReLU masks and the raw scores are bit-identical), but the context of a
-// 16-row stage is ONE m16n8k16 MMA per 8 channels: A[16 x 16] carries the stage's softmax numerators p_r split into
-// hi + lo bf16 parts in rows 0 and 1 (p_hi + p_lo reproduces p to 2^-17), B is the enc stage read straight from the ring with
-// ldmatrix.trans, the fp32 accumulator rows 0 and 1 are summed at the end.  Each warp owns CHC/8 channels for ALL rows of the
-// CTA (no cross-warp combine); the running max / sum are computed redundantly (identically) by every warp.
-// ------------------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(saddr));
-}
-__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo_elem, hi_elem);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-template <int NVA, int NVC, bool CL, int ACT, bool MK>
-__global__ void __launch_bounds__(AP_THREADS) attention_fwd_mma_kernel(
-    const bf16* __restrict__ att1, const bf16* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
-    const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
-    float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
-    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, int pol_att1, int rpi, uint8_t* __restrict__ mask_out) {
-  using T = bf16;
-  using C = ApCfg<T, NVA, NVC>;
-  constexpr int CHA = C::CHA, CHC = C::CHC;
-  static_assert(C::ROWS == 16, "one MMA k-step per stage");
-  constexpr int NTW = CHC / 8 / AP_CWARPS;          // 8-channel MMA tiles per warp (8 for C = 512)
-  static_assert(NTW % 2 == 0, "ldmatrix.x4 covers two tiles");
-  extern __shared__ __align__(128) uint8_t ap_smem[];
-  T* ring = reinterpret_cast<T*>(ap_smem);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + AP_STAGES * C::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + AP_STAGES;
-  float* s_e = reinterpret_cast<float*>(ap_smem + AP_STAGES * C::STAGE_BYTES + 128);   // cluster mode: raw scores of this CTA's rows
-  __shared__ float s_es[2][16];                      // raw scores of the current stage (double buffered by stage parity)
-  __shared__ float s_scale[AP_MAXSPLIT];
-  __shared__ float s_ML[2];
-  __shared__ int s_last;
-
-  const int b = blockIdx.y, sp = blockIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int rps = (R + nsplit - 1) / nsplit;
-  const int r0 = sp * rps, r1 = min(R, r0 + rps);
-  const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
-  const T* a1b = att1 + (int64_t)(b / rpi) * R * CHA;
-  const T* eb = enc + (int64_t)(b / rpi) * R * CHC;
-  float* alb = alpha + (int64_t)b * alpha_stride;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < AP_STAGES; s++) {
-      mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, AP_CWARPS);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-  float m = -INFINITY, l = 0.f;
-  float acc[NTW][4];
-#pragma unroll
-  for (int i = 0; i < NTW; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-
-  if (wid == AP_CWARPS) {
-    if (lane == 0) {
-      const uint64_t pe = make_policy(pol_enc), pa = make_policy(pol_att1);
-      for (int i = 0; i < nst; i++) {
-        const int s = i % AP_STAGES;
-        const uint32_t ph = (i / AP_STAGES) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        const int row = r0 + i * C::ROWS;
-        const int rows = min(C::ROWS, r1 - row);
-        const uint32_t bytes_a = (uint32_t)rows * CHA * 2u, bytes_c = (uint32_t)rows * CHC * 2u;
-        T* sa = ring + (size_t)s * C::STAGE_ELEMS;
-        mbar_expect_tx(full_bar + s, bytes_a + bytes_c);
-        if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s);
-        else bulk_g2s(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s, pa);
-        if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_A, eb + (int64_t)row * CHC, bytes_c, full_bar + s);
-        else bulk_g2s(sa + C::HALF_A, eb + (int64_t)row * CHC, bytes_c, full_bar + s, pe);
-      }
-    }
-    __syncwarp();
-    pdl_wait();
-  } else {
-    float a2[NVA * 8], wv[NVA * 8];
-#pragma unroll
-    for (int j = 0; j < NVA; j++) ld8(wf + (j * 32 + lane) * 8, wv + j * 8);
-    pdl_wait();
-    pdl_trigger();
-#pragma unroll
-    for (int j = 0; j < NVA; j++) ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
-    const int g = lane >> 2, t4 = lane & 3;
-    for (int i = 0; i < nst; i++) {
-      const int s = i % AP_STAGES;
-      const uint32_t ph = (i / AP_STAGES) & 1;
-      const int row = r0 + i * C::ROWS;
-      const int rows = min(C::ROWS, r1 - row);
-      mbar_wait(full_bar + s, ph);
-      const uint32_t sa = smem_u32(ring + (size_t)s * C::STAGE_ELEMS);
-      const uint32_t se = sa + C::HALF_A * 2u;
-      const int ra = wid, rb = wid + AP_CWARPS;
-      const bool one = ra < rows, two = rb < rows;
-      // ---- scores of this warp's two rows (fp32, CUDA cores)
-      float e0 = 0.f, e1 = 0.f;
-      if (one) {
-        uint8_t* mrow = MK ? mask_out + ((int64_t)b * R + row) * (CHA / 8) : nullptr;
-#pragma unroll
-        for (int j = 0; j < NVA; j++) {
-          float v[8];
-          lds8(sa + ((uint32_t)ra * CHA + (j * 32 + lane) * 8) * 2u, v, (const T*)nullptr);
-          uint32_t bits = 0;
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const float pre = v[q] + a2[j * 8 + q];
-            if (MK) bits = __funnelshift_l(__float_as_uint(pre), bits, 1);
-            e0 = fmaf(wv[j * 8 + q], att_act<ACT, true>(pre), e0);
-          }
-          if (MK) mrow[(int64_t)ra * (CHA / 8) + j * 32 + lane] = (uint8_t)(~bits);
-          if (two) {
-            lds8(sa + ((uint32_t)rb * CHA + (j * 32 + lane) * 8) * 2u, v, (const T*)nullptr);
-            bits = 0;
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const float pre = v[q] + a2[j * 8 + q];
-              if (MK) bits = __funnelshift_l(__float_as_uint(pre), bits, 1);
-              e1 = fmaf(wv[j * 8 + q], att_act<ACT, true>(pre), e1);
-            }
-            if (MK) mrow[(int64_t)rb * (CHA / 8) + j * 32 + lane] = (uint8_t)(~bits);
-          }
-        }
-      }
-      e0 = warp_sum(e0);
-      e1 = warp_sum(e1);
-      if (lane == 0) {
-        s_es[i & 1][ra] = one ? e0 : -INFINITY;
-        s_es[i & 1][rb] = two ? e1 : -INFINITY;
-        if (one) {
-          if constexpr (CL) s_e[row + ra - r0] = e0; else alb[row + ra] = e0;
-        }
-        if (two) {
-          if constexpr (CL) s_e[row + rb - r0] = e1; else alb[row + rb] = e1;
-        }
-      }
-      // rows the producer did not fill in a partial last stage hold stale bytes: 0 * NaN would poison the MMA -> clear this
-      // warp's channel slice of those rows
-      if (rows < C::ROWS) {
-        for (int idx = lane; idx < (C::ROWS - rows) * (NTW * 8 / 8); idx += 32) {
-          const int rr = rows + idx / NTW, cc = wid * NTW * 8 + (idx % NTW) * 8;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(se + ((uint32_t)rr * CHC + cc) * 2u), "r"(0u) : "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes vs. later bulk-copy (async proxy) writes
-        __syncwarp();
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");               // the 8 consumer warps: all 16 scores of the stage are in s_es
-      // ---- online softmax state (identical in every warp)
-      const float ev = lane < 16 ? s_es[i & 1][lane] : -INFINITY;
-      const float mn = fmaxf(m, warp_max(ev));
-      const float sc = expf(m - mn);                               // m = -inf at the first stage -> 0
-      const float p = expf(ev - mn);                               // lanes >= 16 and missing rows: exp(-inf) = 0
-      l = l * sc + warp_sum(p);
-      m = mn;
-      // ---- A fragment: row 0 = bf16 hi parts, row 1 = lo parts of p_k, k = 0..15
-      const float pk0 = __shfl_sync(0xffffffffu, p, 2 * t4), pk1 = __shfl_sync(0xffffffffu, p, 2 * t4 + 1);
-      const float pk8 = __shfl_sync(0xffffffffu, p, 2 * t4 + 8), pk9 = __shfl_sync(0xffffffffu, p, 2 * t4 + 9);
-      const float h0 = roundto(pk0, (const bf16*)nullptr), h1 = roundto(pk1, (const bf16*)nullptr);
-      const float h8 = roundto(pk8, (const bf16*)nullptr), h9 = roundto(pk9, (const bf16*)nullptr);
-      uint32_t fa0 = 0u, fa2 = 0u;
-      if (g == 0) { fa0 = pack_bf16x2(h0, h1); fa2 = pack_bf16x2(h8, h9); }
-      else if (g == 1) { fa0 = pack_bf16x2(pk0 - h0, pk1 - h1); fa2 = pack_bf16x2(pk8 - h8, pk9 - h9); }
-      if (sc != 1.f) {
-#pragma unroll
-        for (int nt = 0; nt < NTW; nt++) { acc[nt][0] *= sc; acc[nt][1] *= sc; }
-      }
-      // ---- context: enc stage [16 rows][CHC] (row-major) as B operand via ldmatrix.trans; lane -> (matrix mi, row ri)
-      const int mi = lane >> 3, ri = lane & 7;
-#pragma unroll
-      for (int nt = 0; nt < NTW; nt += 2) {
-        const int c0 = (wid * NTW + nt) * 8;
-        uint32_t b0, b1, b2, b3;
-        ldmatrix_x4_trans(b0, b1, b2, b3, se + ((uint32_t)((mi & 1) * 8 + ri) * CHC + c0 + (mi >> 1) * 8) * 2u);
-        mma_16816(acc[nt], fa0, 0u, fa2, 0u, b0, b1);
-        mma_16816(acc[nt + 1], fa0, 0u, fa2, 0u, b2, b3);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar + s);
-    }
-  }
-  __syncthreads();     // every TMA write has landed and been consumed: the ring can be reused for the combine
-  float* s_part = reinterpret_cast<float*>(ap_smem);           // [CHC] context numerator of this CTA (relative to its max m)
-  __shared__ float s_MLp[2];
-  if (wid < AP_CWARPS) {
-    const int g = lane >> 2, t4 = lane & 3;
-#pragma unroll
-    for (int nt = 0; nt < NTW; nt++) {
-      // accumulator row 0 (hi parts) lives in lanes g == 0, row 1 (lo parts) in lanes g == 1
-      const float l0 = __shfl_sync(0xffffffffu, acc[nt][0], lane + 4), l1 = __shfl_sync(0xffffffffu, acc[nt][1], lane + 4);
-      if (g == 0) {
-        const int c = (wid * NTW + nt) * 8 + 2 * t4;
-        s_part[c] = acc[nt][0] + l0;
-        s_part[c + 1] = acc[nt][1] + l1;
-      }
-    }
-    if (wid == 0 && lane == 0) { s_MLp[0] = m; s_MLp[1] = l; }
-  }
-  const float M = m, L = l;            // the producer warp's copies are unused (it only helps in the loops below)
-  (void)M; (void)L;
-  if constexpr (CL) {
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();
-    float Mg = -INFINITY;
-    for (int q = 0; q < nsplit; q++) Mg = fmaxf(Mg, cluster.map_shared_rank(s_MLp, q)[0]);
-    float Lg = 0.f;
-    float scl[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      scl[q] = 0.f;
-      if (q < nsplit) {
-        const float* ml = cluster.map_shared_rank(s_MLp, q);
-        const float ms = ml[0];
-        scl[q] = (ms == -INFINITY) ? 0.f : expf(ms - Mg);
-        Lg += ml[1] * scl[q];
-      }
-    }
-    const float invL = 1.0f / Lg;
-    const int cps = (CHC + nsplit - 1) / nsplit;
-    for (int c = sp * cps + threadIdx.x; c < min(CHC, (sp + 1) * cps); c += AP_THREADS) {
-      float tt = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        if (q < nsplit) tt = fmaf(cluster.map_shared_rank(s_part, q)[c], scl[q], tt);
-      tt *= invL;
-      ctx[(int64_t)b * CHC + c] = tt;
-      if (gate_pre) {
-        const float gg = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
-        gate_pre[(int64_t)b * gate_stride + c] = gg;
-        gctx[(int64_t)b * CHC + c] = gg * tt;
-        if (gctx_bf) gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(gg * tt);
-      } else if (gctx_bf) {
-        gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(tt);
-      }
-    }
-    for (int r = r0 + threadIdx.x; r < r1; r += AP_THREADS) alb[r] = expf(s_e[r - r0] - Mg) * invL;
-    cluster.sync();
-    return;
-  }
-  __syncthreads();
-  float* part = partials + ((int64_t)b * nsplit + sp) * (CHC + 2);
-  for (int c = threadIdx.x; c < CHC; c += AP_THREADS) part[2 + c] = s_part[c];
-  if (threadIdx.x == 0) { part[0] = s_MLp[0]; part[1] = s_MLp[1]; }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(counters + b, 1);
-    s_last = (ticket == nsplit - 1);
-    if (s_last) counters[b] = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const float* pb = partials + (int64_t)b * nsplit * (CHC + 2);
-  if (threadIdx.x == 0) {
-    float Mg = -INFINITY;
-    for (int q = 0; q < nsplit; q++) Mg = fmaxf(Mg, __ldcg(pb + (int64_t)q * (CHC + 2)));
-    float Lg = 0.f;
-    for (int q = 0; q < nsplit; q++) {
-      const float ms = __ldcg(pb + (int64_t)q * (CHC + 2));
-      const float scl = (ms == -INFINITY) ? 0.f : expf(ms - Mg);
-      s_scale[q] = scl;
-      Lg += __ldcg(pb + (int64_t)q * (CHC + 2) + 1) * scl;
-    }
-    s_ML[0] = Mg;
-    s_ML[1] = 1.0f / Lg;
-  }
-  __syncthreads();
-  const float Mg = s_ML[0], invL = s_ML[1];
-  for (int c = threadIdx.x; c < CHC; c += AP_THREADS) {
-    float tt = 0.f;
-    for (int q = 0; q < nsplit; q++) tt = fmaf(__ldcg(pb + (int64_t)q * (CHC + 2) + 2 + c), s_scale[q], tt);
-    tt *= invL;
-    ctx[(int64_t)b * CHC + c] = tt;
-    if (gate_pre) {
-      const float gg = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
-      gate_pre[(int64_t)b * gate_stride + c] = gg;
-      gctx[(int64_t)b * CHC + c] = gg * tt;
-      if (gctx_bf) gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(gg * tt);
-    } else if (gctx_bf) {
-      gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(tt);
-    }
-  }
-  for (int r = threadIdx.x; r < R; r += AP_THREADS) alb[r] = expf(__ldcg(alb + r) - Mg) * invL;
-}
-
-// ------------------------------------------------------------------------------------------------------------------------------
 // Attention backward, mask-bit version (ReLU score): the forward kernel left 1 bit per att1 element (att1 + att2 > 0), so the
 // backward streams enc rows (CHC elements) + CHA/8 mask bytes per region instead of enc + att1 rows: 60.5 MB instead of
 // 114 MB per step at cfg #2.  Same math, same masks (the bits ARE the forward's comparisons), same combine order.
@@ -1178,30 +879,6 @@ static int fwd_launch_m(const AttFwdArgs& x, cudaStream_t st) {
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
   const int rpi = x.rows_per_img > 1 ? x.rows_per_img : 1;
-  if constexpr (sizeof(T) == 2 && NVC <= 2) {
-    if (g_opt_att_mma) {
-      static bool attr_m = false;
-      if (!attr_m) {
-        LO_CUDA(cudaFuncSetAttribute(attention_fwd_mma_kernel<NVA, NVC, false, ACT, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        LO_CUDA(cudaFuncSetAttribute(attention_fwd_mma_kernel<NVA, NVC, true, ACT, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX));
-        attr_m = true;
-      }
-      if (use_cluster(ns, x.R)) {
-        const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
-        LO_CUDA(launch_att(attention_fwd_mma_kernel<NVA, NVC, true, ACT, MK>, dim3(ns, x.B), smem, ns, st, (const bf16*)x.att1,
-                           (const bf16*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride,
-                           x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc,
-                           g_opt_att_policy_att1, rpi, x.mask_out));
-      } else {
-        LO_CUDA(launch_att(attention_fwd_mma_kernel<NVA, NVC, false, ACT, MK>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const bf16*)x.att1,
-                           (const bf16*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride,
-                           x.gctx, x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc,
-                           g_opt_att_policy_att1, rpi, x.mask_out));
-      }
-      LO_LAUNCH_OK();
-      return LO_OK;
-    }
-  }
   if (use_cluster(ns, x.R)) {
     const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
     LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT, MK>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc,
@@ -1344,7 +1021,6 @@ extern "C" int lo_get_option(const char* name) {
   if (!name) return -1;
   if (!strcmp(name, "att_pipe")) return lo::g_opt_att_pipe;
   if (!strcmp(name, "att_maskbits")) return lo::g_opt_att_maskbits;
-  if (!strcmp(name, "att_mma")) return lo::g_opt_att_mma;
   if (!strcmp(name, "att_cluster")) return lo::g_opt_att_cluster;
   if (!strcmp(name, "pdl")) return lo::g_opt_pdl;
   if (!strcmp(name, "conv_persist")) return lo::g_opt_conv_persist;
@@ -1365,7 +1041,6 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "pdl")) lo::g_opt_pdl = value;
   else if (!strcmp(name, "att_cluster")) lo::g_opt_att_cluster = value;
   else if (!strcmp(name, "att_maskbits")) lo::g_opt_att_maskbits = value;
-  else if (!strcmp(name, "att_mma")) lo::g_opt_att_mma = value;
   else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
   else if (!strcmp(name, "conv_persist")) lo::g_opt_conv_persist = value;
   else if (!strcmp(name, "dec_streams")) { lo::g_opt_dec_streams = value; lo::g_opt_skinny8 = value >= 2 ? 0 : 1; }
