@@ -359,6 +359,12 @@ int lo_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16
 int lo_adam_step_ranges(float* p, const float* g, float* m, float* v, void* shadow_bf16, const int64_t* ranges,
                         int n_ranges, float* state_dev, float beta1, float beta2, float eps, float grad_scale,
                         void* stream);
+/* The optimisers of the TF trainer (model/img2seq.py:98-111) with TensorFlow 1.12's update rules, on one flat buffer:
+ * kind 1 AdamOptimizer (epsilon outside the bias correction: lr_t = lr sqrt(1-b2^t)/(1-b1^t), p -= lr_t m/(sqrt(v)+eps)),
+ * 2 GradientDescentOptimizer, 3 AdagradOptimizer (s1 = accumulator, initial value 0.1), 4 RMSPropOptimizer (s1 = rms slot,
+ * initial value 1; beta2 = decay 0.9, eps 1e-10, momentum 0).  state_dev as in lo_adam_step. */
+int lo_tf_optim_step(int kind, float* p, const float* g, float* s1, float* s2, void* shadow_bf16, int64_t n,
+                     float* state_dev, float beta1, float beta2, float eps, float grad_scale, void* stream);
 int lo_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, void* stream);
 
 #ifdef __cplusplus

@@ -23,6 +23,12 @@ int g_opt_att_nsplit = 0;        // 0 = automatic
 int g_opt_att_cluster = 1;
 int g_opt_att_maskbits = 1;      // 1: the forward attention kernel stores the ReLU mask bits, the backward streams them instead of att1       // 1: the splits of one batch row form a thread-block cluster and combine through DSMEM
 
+#ifndef LO_ATT_RPW
+#define LO_ATT_RPW 2          // rows per consumer warp per stage (bf16): 2 -> 32 KB stages, 2 CTAs/SM ; 1 -> 16 KB stages, 3 CTAs/SM
+#endif
+#ifndef LO_ATT_MINB
+#define LO_ATT_MINB 2
+#endif
 #define AP_THREADS 288
 #define AP_CWARPS 8
 #define AP_STAGES 3
@@ -55,7 +61,7 @@ struct ApCfg {
   static constexpr int CHA = NVA * 256;
   static constexpr int CHC = NVC * 256;
   static constexpr int NVM = NVA > NVC ? NVA : NVC;
-  static constexpr int RPW = (sizeof(T) == 2 && NVM <= 2) ? 2 : 1;      // rows per consumer warp per stage
+  static constexpr int RPW = (sizeof(T) == 2 && NVM <= 2) ? LO_ATT_RPW : 1;      // rows per consumer warp per stage
   static constexpr int ROWS = AP_CWARPS * RPW;
   static constexpr int HALF_A = ROWS * CHA;                             // att1 part
   static constexpr int HALF_C = ROWS * CHC;                             // enc part
@@ -65,7 +71,7 @@ struct ApCfg {
 };
 
 template <typename T, int NVA, int NVC, bool CL, int ACT, bool MK>
-__global__ void __launch_bounds__(AP_THREADS) attention_fwd_pipe_kernel(
+__global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_kernel(
     const T* __restrict__ att1, const T* __restrict__ enc, const float* __restrict__ att2, int64_t att2_stride,
     const float* __restrict__ wf, float* __restrict__ alpha, int64_t alpha_stride, float* __restrict__ ctx,
     float* __restrict__ gate_pre, int64_t gate_stride, float* __restrict__ gctx, bf16* __restrict__ gctx_bf, int R, int nsplit,
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
 template <typename T, int NVA, int NVC>
 struct ApmCfg {
   static constexpr int CHA = NVA * 256, CHC = NVC * 256;
-  static constexpr int RPW = (sizeof(T) == 2 && NVC <= 2) ? 2 : 1;
+  static constexpr int RPW = (sizeof(T) == 2 && NVC <= 2) ? LO_ATT_RPW : 1;
   static constexpr int ROWS = AP_CWARPS * RPW;
   static constexpr int ENC_BYTES = ROWS * CHC * (int)sizeof(T);
   static constexpr int MSK_BYTES = ROWS * (CHA / 8);
@@ -605,7 +611,7 @@ struct ApmCfg {
 };
 
 template <typename T, int NVA, int NVC, bool CL>
-__global__ void __launch_bounds__(AP_THREADS) attention_bwd_mask_kernel(
+__global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_kernel(
     const uint8_t* __restrict__ mask, const T* __restrict__ enc, const float* __restrict__ gate, int64_t o1_stride,
     const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride, const float* __restrict__ ctx,
     const float* __restrict__ dgctx, int64_t dg_stride, const float* __restrict__ dreg, int64_t dreg_stride,
@@ -819,7 +825,7 @@ int att_pipe_splits(int B, int hint = 0) {
   // two CTAs per SM are resident (smem): one full wave of <= 296 CTAs.  Measured at B=64, R=868 (bf16): 4 splits
   // (256 CTAs, 14 stages each) 25.9 us vs 9 splits (576 CTAs = 2 waves) 32.8 us — per-CTA start-up/combine
   // costs dominate short CTAs (profiles/r1_attention_nsplit_sweep.txt)
-  int s = 296 / B;
+  int s = (148 * LO_ATT_MINB) / B;
   if (s < 1) s = 1;
   if (s > AP_MAXSPLIT) s = AP_MAXSPLIT;
   if (g_opt_att_cluster && s > 8) s = 8;       // portable cluster size limit

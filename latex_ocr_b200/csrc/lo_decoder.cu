@@ -327,6 +327,20 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
       const float4 q = *reinterpret_cast<const float4*>(&s_a2[tt][tx * 4]);
       const float4 d4 = *reinterpret_cast<const float4*>(&s_de[tt][ty * 4]);
       const float a2v[4] = {q.x, q.y, q.z, q.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      if constexpr (ACT == 0 && WACC) {
+        // d w_full[a] = sum de * relu(x + a2) = sum_i x[i][a] * (sum_t on * de) + sum_t a2_t[a] * (sum_i on * de): the first term is
+        // x * acc at the very end (x does not depend on t), the second needs only the per-step column sums s[j]
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const bool on = a2v[j] > nx[i][j];
+            if (on) { acc[i][j] += dv[i]; sc[j] += dv[i]; }
+          }
+#pragma unroll
+        for (int j = 0; j < 4; j++) wacc[j] = fmaf(a2v[j], sc[j], wacc[j]);
+      } else
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -335,7 +349,6 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
             // x + a2 > 0  <=>  a2 > -x exactly (an fp32 sum has the sign of the exact sum): one compare + one predicated add
             const bool on = a2v[j] > nx[i][j];
             acc[i][j] += on ? dv[i] : 0.f;
-            if (WACC) wacc[j] = fmaf(dv[i], on ? a2v[j] - nx[i][j] : 0.f, wacc[j]);   // (padded rows: nx = +inf -> never on)
           } else {
             const float pre = x[i][j] + a2v[j];
             // tanh score (Genthial cell); padded rows: tanh(-inf) = -1 -> derivative 0, dv = 0
@@ -358,6 +371,14 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
     for (int j = 0; j < 4; j++) stf(datt1 + ((int64_t)b * R + r) * A + a0 + tx * 4 + j, acc[i][j] * wv[j]);
   }
   if (!WACC) return;
+  if constexpr (ACT == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (r0 + ty * 4 + i < R) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) wacc[j] = fmaf(x[i][j], acc[i][j], wacc[j]);      // the x * (sum_t on * de) term
+      }
+  }
 #pragma unroll
   for (int j = 0; j < 4; j++) s_w[ty][tx * 4 + j] = wacc[j];
   __syncthreads();
@@ -597,6 +618,29 @@ __global__ void onehot_kernel(const int64_t* __restrict__ caps, int64_t caps_str
   }
 }
 
+// bf16 operands of the batched tensor-core GEMM d enc[b] += alphas[b]^T dctx[:, b, :]:
+//   alphas fp32 [B*T][R] -> bf16 [B*T][Rp] (rows padded to a multiple of 8 elements = 16 bytes, a TMA stride requirement)
+__global__ void cast_pad_rows_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t rows, int R, int Rp) {
+  const int64_t total = rows * Rp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Rp;
+    const int c = (int)(i % Rp);
+    y[i] = __float2bfloat16_rn(c < R ? x[r * R + c] : 0.f);
+  }
+}
+//   dctx fp32 [T][B][C] -> bf16 [B][T][C]
+__global__ void cast_tb_to_bt_kernel(const float* __restrict__ x, bf16* __restrict__ y, int T, int B, int C) {
+  const int64_t total = (int64_t)T * B * (C / 8);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % (C / 8));
+    const int64_t tb = i / (C / 8);
+    const int b = (int)(tb % B), t = (int)(tb / B);
+    float v[8];
+    ld8(x + tb * C + c8 * 8, v);
+    st8(y + ((int64_t)b * T + t) * C + c8 * 8, v);
+  }
+}
+
 // denc[b][r][:] += dmean[b][:] / R
 __global__ void add_rowbcast_kernel(float* __restrict__ denc, const float* __restrict__ dmean, int R, int C, float scale,
                                     int64_t total) {
@@ -799,10 +843,11 @@ static inline Dims dims(const lo_decoder_args* a) {
 // bf16 staging used when impl == TC: mirrors written by the step kernels feed the tcgen05 GEMMs directly
 struct BfViews {
   bool on;
-  bf16 *dcat, *hall, *gctx, *wet, *onehot, *hd, *dlogits, *wfct, *wil;
+  bf16 *dcat, *hall, *gctx, *wet, *onehot, *hd, *dlogits, *wfct, *wil, *alphas, *dctx, *dptab, *wihT;
 };
+static inline int64_t rpad8(int64_t r) { return (r + 7) / 8 * 8; }
 static BfViews bf_views(const lo_decoder_args* a, const Dims& d) {
-  BfViews v{false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  BfViews v{false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (a->impl == LO_IMPL_TC && a->dt == LO_BF16 && a->bfwork && tc_available()) {
     const int64_t TB = (int64_t)d.T * d.B;
     v.on = true;
@@ -815,6 +860,10 @@ static BfViews bf_views(const lo_decoder_args* a, const Dims& d) {
     v.dlogits = v.hd + TB * d.D;
     v.wfct = v.dlogits + TB * d.Vl;
     v.wil = v.wfct + (int64_t)d.D * d.Vl;
+    v.alphas = v.wil + (int64_t)4 * d.D * d.C;            // [B][T][roundup8(R)] (zero padded): A operand of the batched alpha^T dctx GEMM
+    v.dctx = v.alphas + TB * rpad8(d.R);                   // [B][T][C]
+    v.dptab = v.dctx + TB * d.C;                           // [V][4D] bf16 copy of the embedding-table gradient
+    v.wihT = v.dptab + (int64_t)d.V * d.G;                 // [E][4D] = (weight_ih[:, :E])^T
   }
   return v;
 }
@@ -1076,7 +1125,7 @@ int64_t lo_decoder_bfwork_bytes(const lo_decoder_args* a) {
   const int64_t Vp = (a->V + 7) / 8 * 8;
   const int64_t Vl = a->ldl > 0 ? a->ldl : a->V;
   return (TB * (O1 + a->D + a->C + Vp + a->D + Vl) + (int64_t)a->B * a->D + (int64_t)a->A * a->C + (int64_t)a->D * Vl +
-          (int64_t)4 * a->D * a->C) * 2 + 1024;
+          (int64_t)4 * a->D * a->C + TB * ((a->R + 7) / 8 * 8) + TB * a->C + (int64_t)(a->V + a->E) * 4 * a->D) * 2 + 1024;
 }
 
 int64_t lo_sizeof_decoder_args(void) { return (int64_t)sizeof(lo_decoder_args); }
@@ -1453,8 +1502,18 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
                                        d.B, d.T, d.G);
     LO_LAUNCH_OK();
   }
-  LO_TRY(gemm_nn(a->dptab, LO_F32, d.G, a->w_ih, dt, d.E + d.C, a->g_emb, LO_F32, d.E, d.V, d.E, d.G, 0, LO_IMPL_SIMT, st));
-  LO_TRY(gemm_tn(a->dptab, LO_F32, d.G, a->emb, dt, d.E, a->g_w_ih, LO_F32, d.E + d.C, d.G, d.E, d.V, 0, LO_IMPL_SIMT, st));
+  if (tc && d.E % 64 == 0 && d.G % 64 == 0 && d.V >= 64) {
+    // g_emb = dptab W_ih[:, :E] and g_W_ih[:, :E] = dptab^T emb on tcgen05 (bf16 copy of dptab, transposed weight slice)
+    LO_TRY(lo_cast(a->dptab, LO_F32, bv.dptab, LO_BF16, (int64_t)d.V * d.G, stream));
+    transpose_kernel<bf16><<<dim3(cdiv(d.E, 32), cdiv(d.G, 32)), dim3(32, 8), 0, st>>>((const bf16*)a->w_ih, d.E + d.C, bv.wihT, d.G, d.G, d.E);
+    LO_LAUNCH_OK();
+    LO_TRY(tc_gemm_nt(bv.dptab, d.G, bv.wihT, d.G, a->g_emb, LO_F32, d.E, d.V, d.E, d.G, nullptr, 0, 0, st));
+    LO_CUDA(cudaMemset2DAsync(a->g_w_ih, (size_t)(d.E + d.C) * 4, 0, (size_t)d.E * 4, d.G, st));
+    LO_TRY(tc_gemm_tn(bv.dptab, d.G, (const bf16*)a->emb, d.E, a->g_w_ih, d.E + d.C, d.G, d.E, d.V, st));
+  } else {
+    LO_TRY(gemm_nn(a->dptab, LO_F32, d.G, a->w_ih, dt, d.E + d.C, a->g_emb, LO_F32, d.E, d.V, d.E, d.G, 0, LO_IMPL_SIMT, st));
+    LO_TRY(gemm_tn(a->dptab, LO_F32, d.G, a->emb, dt, d.E, a->g_w_ih, LO_F32, d.E + d.C, d.G, d.E, d.V, 0, LO_IMPL_SIMT, st));
+  }
   // d att1 + d w_full in one sweep over att1
   LO_CUDA(cudaMemsetAsync(a->g_w_full, 0, (size_t)d.A * 4, st));
   LO_CUDA(cudaMemsetAsync(a->g_b_full, 0, 4, st));   // sum_r de = 0 exactly (softmax); reference value is rounding noise
@@ -1484,7 +1543,16 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   }
   LO_TRY(colsum(a->datt1, dt, a->g_b_enc_att, d.B * d.R, d.A, d.A, 0, st));
   // denc[b] += alphas[b]^T @ dctx[:, b, :]   (the context read, summed over time — a batched GEMM instead of a per-step RMW)
-  {
+  if (tc && d.C % 8 == 0) {
+    // tcgen05, one launch (3-D tensor maps, grid.y = batch); bf16 operands cast once after the loop
+    const int Rp = (int)rpad8(d.R);
+    cast_pad_rows_kernel<<<148 * 8, 256, 0, st>>>(a->alphas, bv.alphas, BT, d.R, Rp);
+    LO_LAUNCH_OK();
+    cast_tb_to_bt_kernel<<<148 * 8, 256, 0, st>>>(a->dctx, bv.dctx, d.T, d.B, d.C);
+    LO_LAUNCH_OK();
+    LO_TRY(tc_gemm_tn_batched(bv.alphas, Rp, (int64_t)d.T * Rp, bv.dctx, d.C, (int64_t)d.T * d.C, a->denc, d.C, (int64_t)d.R * d.C, d.R,
+                              d.C, d.T, d.B, st));
+  } else {
     GemmDesc g{d.R, d.C, d.T, 1, d.R, (int64_t)d.B * d.C, 1, d.C, d.B, (int64_t)d.T * d.R, d.C, (int64_t)d.R * d.C, nullptr, 1, 0};
     LO_TRY(gemm(a->alphas, LO_F32, a->dctx, LO_F32, a->denc, LO_F32, g, LO_IMPL_SIMT, st));
   }

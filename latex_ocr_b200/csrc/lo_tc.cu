@@ -37,6 +37,13 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
@@ -641,7 +648,9 @@ struct WgParams {
   int BW, BH, tiles_w, tiles_h, kstages, per_split, ci_tiles;
   float* dw;
   int plain;          // 1: plain C[M][N] += A[K][M]^T B[K][N] (2-D maps; Cout = M, Cin = N, tap ignored)
+                      // 2: the same, batched over blockIdx.y (3-D maps {M|N, K, batch}; C of batch b at dw + b * batch_c)
   int64_t ldc;
+  int64_t batch_c;
 };
 
 template <int NT, int STAGES>
@@ -657,7 +666,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = (blockIdx.x / p.ci_tiles) * 128, ci0 = (blockIdx.x % p.ci_tiles) * NT;
-  const int tap = blockIdx.y, r = tap / 3, q = tap % 3;
+  const int tap = p.plain == 2 ? 0 : blockIdx.y, r = tap / 3, q = tap % 3;
+  const int bz = p.plain == 2 ? blockIdx.y : 0;
   const int ks0 = blockIdx.z * p.per_split;
   const int ks1 = min(p.kstages, ks0 + p.per_split);
   const int KS = ks1 - ks0;
@@ -686,7 +696,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
           const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(full_bar + s, A_BYTES);
-          if (p.plain) {
+          if (p.plain == 2) {
+            tma_load_3d(sa, &mapDY, full_bar + s, co0, ks * 128, bz);
+            tma_load_3d(sa + BOX, &mapDY, full_bar + s, co0 + 64, ks * 128, bz);
+          } else if (p.plain) {
             tma_load_2d(sa, &mapDY, full_bar + s, co0, ks * 128);
             tma_load_2d(sa + BOX, &mapDY, full_bar + s, co0 + 64, ks * 128);
           } else {
@@ -708,7 +721,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
           const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
           uint8_t* sb = smem + s * STAGE_BYTES + A_BYTES;
           mbar_expect_tx(full_bar + s, B_BYTES);
-          if (p.plain) {
+          if (p.plain == 2) {
+#pragma unroll
+            for (int j = 0; j < NT / 64; j++) tma_load_3d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, ks * 128, bz);
+          } else if (p.plain) {
 #pragma unroll
             for (int j = 0; j < NT / 64; j++) tma_load_2d(sb + j * BOX, &mapX, full_bar + s, ci0 + 64 * j, ks * 128);
           } else {
@@ -759,7 +775,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
           const int co = co0 + quad * 32 + rr;
           const int ci = ci0 + c + lane;
           if (co < p.Cout && ci < p.Cin) {
-            float* o = p.plain ? p.dw + (int64_t)co * p.ldc + ci : p.dw + ((int64_t)co * 9 + tap) * p.Cin + ci;
+            float* o = p.plain ? p.dw + (int64_t)bz * p.batch_c + (int64_t)co * p.ldc + ci : p.dw + ((int64_t)co * 9 + tap) * p.Cin + ci;
             atomicAdd(o, stg[rr * 36 + lane]);
           }
         }
@@ -1118,6 +1134,39 @@ int tc_gemm_tn(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float* C,
   p.per_split = cdiv(p.kstages, splits);
   splits = cdiv(p.kstages, p.per_split);
   dim3 grid(mt * p.ci_tiles, 1, splits);
+  if (NT == 128) return launch_wgrad<128, 3>(mA, mB, p, grid, st);
+  return launch_wgrad<64, 4>(mA, mB, p, grid, st);
+}
+
+// Batched C[b][M][N] (fp32, += with atomics) += A[b][K][M]^T * B[b][K][N]; A, B bf16 with arbitrary (16-byte multiple) strides:
+// element (b, k, m) of A at A + b * sAb + k * sAk + m, likewise B.  One launch, grid.y = batch.  (decoder backward:
+// d enc[b] += alphas[b]^T dctx[:, b, :], the context read summed over time.)
+int tc_gemm_tn_batched(const bf16* A, int64_t sAk, int64_t sAb, const bf16* B, int64_t sBk, int64_t sBb, float* C, int64_t ldc,
+                       int64_t sCb, int M, int N, int K, int batch, cudaStream_t st) {
+  if (!tc_available()) return fail(LO_ENOTSUP, "%s: needs an sm_100 device", __func__);
+  LO_CHECK_ARG(sAk % 8 == 0 && sAb % 8 == 0 && sBk % 8 == 0 && sBb % 8 == 0, "strides must be multiples of 8 elements");
+  LO_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && batch >= 1 && batch <= 65535, "alignment / batch");
+  CUtensorMap mA, mB;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)K, (cuuint64_t)batch};
+    cuuint64_t str[2] = {(cuuint64_t)sAk * 2, (cuuint64_t)sAb * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    LO_TRY(make_map(&mA, A, 3, dims, str, box));
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)K, (cuuint64_t)batch};
+    cuuint64_t str[2] = {(cuuint64_t)sBk * 2, (cuuint64_t)sBb * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    LO_TRY(make_map(&mB, B, 3, dims, str, box));
+  }
+  WgParams p{};
+  p.plain = 2; p.Cout = M; p.Cin = N; p.dw = C; p.ldc = ldc; p.batch_c = sCb;
+  p.tiles_w = p.tiles_h = 1; p.BW = 128; p.BH = 1;
+  p.kstages = cdiv(K, 128);
+  p.per_split = p.kstages;                      // no split-K: the batch dimension supplies the parallelism
+  const int NT = N > 64 ? 128 : 64;
+  p.ci_tiles = cdiv(N, NT);
+  dim3 grid(cdiv(M, 128) * p.ci_tiles, batch, 1);
   if (NT == 128) return launch_wgrad<128, 3>(mA, mB, p, grid, st);
   return launch_wgrad<64, 4>(mA, mB, p, grid, st);
 }

@@ -51,9 +51,11 @@ class Img2SeqModel:
         config = config or self._config
         self._build()
         method = str(getattr(config, "lr_method", "adam")).lower()
-        if method != "adam":
-            # img2seq.py:100-111 also offers adagrad / sgd / rmsprop; only the optimiser of the shipped configs is built
-            raise NotImplementedError("lr_method=%r: only Adam is implemented" % method)
+        # img2seq.py:98-111: adam | adagrad | sgd | rmsprop, TF 1.12 update rules (csrc/lo_optim.cu:tf_optim_kernel)
+        kinds = {"adam": 1, "sgd": 2, "adagrad": 3, "rmsprop": 4}
+        if method not in kinds:
+            raise NotImplementedError("Unknown method {}".format(method))          # img2seq.py:111
+        self.lr_method, self._opt_kind = method, kinds[method]
         self.clip = float(getattr(config, "clip", -1))
         self.set_lr(float(getattr(config, "lr_init", 1e-3)))
         return self
@@ -70,9 +72,16 @@ class Img2SeqModel:
 
     def set_lr(self, lr):
         self.lr = float(lr)
+        kind = getattr(self, "_opt_kind", 1)
         for m in (self.encoder, self.decoder):
-            m.store.ensure_adam(lr)
-            m.store.set_lr(lr)
+            S = m.store
+            fresh = S.m is None
+            S.ensure_adam(lr)                     # slot buffers m (s1) / v (s2) + the device {step, lr} pair
+            if fresh and kind == 3:
+                S.m.fill_(0.1)                    # tf.train.AdagradOptimizer: initial_accumulator_value = 0.1
+            elif fresh and kind == 4:
+                S.m.fill_(1.0)                    # tf.train.RMSPropOptimizer: the rms slot starts at ones
+            S.set_lr(lr)
 
     # ---------------------------------------------------------------------------------------------
     def _to_device_images(self, images):
@@ -127,11 +136,18 @@ class Img2SeqModel:
         if self.clip > 0:                                                   # tf.clip_by_global_norm (img2seq.py:116-121)
             gn = float(torch.sqrt(self.encoder.store.grad.pow(2).sum() + self.decoder.store.grad.pow(2).sum()))
             scale = min(1.0, self.clip / max(gn, 1e-30))
+        import ctypes
+        fn = L.lo_tf_optim_step
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int64, ctypes.c_void_p] + [ctypes.c_float] * 4 + [ctypes.c_void_p]
+        kind = getattr(self, "_opt_kind", 1)
+        # TF defaults: Adam beta1 0.9, beta2 0.999, epsilon 1e-8 (outside the bias correction); RMSProp decay 0.9, epsilon 1e-10
+        b1, b2, eps = (0.9, 0.9, 1e-10) if kind == 4 else (0.9, 0.999, 1e-8)
         for m in (self.decoder, self.encoder):
             S = m.store
-            check(L.lo_adam_step(ptr(S.master), ptr(S.grad), ptr(S.m), ptr(S.v), ptr(S.shadow), S.numel, ptr(S.adam_state), 0.9, 0.999,
-                                 1e-8, float(scale), stream_ptr()))
-            m._shadow_fresh = True                                          # the fused Adam refreshed the bf16 shadow
+            check(fn(kind, ptr(S.master), ptr(S.grad), ptr(S.m), ptr(S.v), ptr(S.shadow), S.numel, ptr(S.adam_state), b1, b2, eps,
+                     float(scale), stream_ptr()))
+            m._shadow_fresh = True                                          # the fused update refreshed the bf16 shadow
 
     def train_step(self, images, formulas, dropout=1.0):
         """One update (img2seq.py:163-170).  Returns the device loss vector [mean CE, mean CE, 0, n_words]."""

@@ -283,3 +283,43 @@ def test_adam_ranges_skip_frozen_slices():
         else:
             assert (p[sl] - refs[i].detach()).abs().max().item() < 2e-6
     assert state[0].item() == 3.0
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+def test_tf_optimisers_follow_tf_update_rules(kind):
+    """lo_tf_optim_step: the four optimisers of model/img2seq.py:98-111 with TensorFlow 1.12's update rules restated in fp64
+    (parity unpinned: TF cannot run here).  1 Adam (epsilon outside the bias correction), 2 SGD, 3 Adagrad (accumulator starts at
+    0.1), 4 RMSProp (rms slot starts at 1, decay 0.9, epsilon 1e-10, momentum 0)."""
+    import ctypes
+    _lib, L = _L()
+    fn = L.lo_tf_optim_step
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int64, ctypes.c_void_p] + [ctypes.c_float] * 4 + [ctypes.c_void_p]
+    torch.manual_seed(kind)
+    n, lr = 5003, 1e-2
+    p = torch.randn(n, device="cuda")
+    ref = p.double().cpu()
+    s1 = torch.full((n,), {1: 0.0, 2: 0.0, 3: 0.1, 4: 1.0}[kind], device="cuda")
+    s2 = torch.zeros(n, device="cuda")
+    r1, r2 = s1.double().cpu(), s2.double().cpu()
+    state = torch.tensor([0.0, lr], device="cuda")
+    b1, b2, eps = (0.9, 0.9, 1e-10) if kind == 4 else (0.9, 0.999, 1e-8)
+    for t in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        _lib.check(fn(kind, _lib.ptr(p), _lib.ptr(g), _lib.ptr(s1), _lib.ptr(s2), None, n, _lib.ptr(state), b1, b2, eps, 0.5, _lib.stream_ptr()))
+        gd = g.double().cpu() * 0.5
+        if kind == 1:
+            r1 = b1 * r1 + (1 - b1) * gd
+            r2 = b2 * r2 + (1 - b2) * gd * gd
+            ref = ref - lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t) * r1 / (r2.sqrt() + eps)
+        elif kind == 2:
+            ref = ref - lr * gd
+        elif kind == 3:
+            r1 = r1 + gd * gd
+            ref = ref - lr * gd / r1.sqrt()
+        else:
+            r1 = b2 * r1 + (1 - b2) * gd * gd
+            ref = ref - lr * gd / (r1 + eps).sqrt()
+    torch.cuda.synchronize()
+    assert relerr(p, ref.float()) < 2e-6
+    assert state[0].item() == 3.0

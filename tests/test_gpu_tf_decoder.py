@@ -158,3 +158,23 @@ def test_tf_model_trains_and_predicts():
     hyps = m.predict_batch(imgs)
     assert len(hyps) == 2 and all(len(h) == 3 for h in hyps)
     assert all(vocab.id_end not in seq for seq in hyps[0])
+
+
+@pytest.mark.parametrize("method,lr", [("sgd", 0.5), ("adagrad", 0.1), ("rmsprop", 1e-3)])
+def test_tf_model_other_optimisers_reduce_the_loss(method, lr):
+    """img2seq.py:98-111 offers adagrad / sgd / rmsprop besides adam; with clip_by_global_norm (:116-121) switched on."""
+    import numpy as np
+    from latex_ocr_b200.data import SimpleVocab
+    from latex_ocr_b200.img2seq_tf import Img2SeqModel
+    rng = np.random.RandomState(2)
+    V = 30
+    data = [(rng.randint(0, 256, (32, 64, 1)).astype(np.uint8), list(rng.randint(0, V - 3, 3 + i % 3))) for i in range(3)]
+    cfg = _cfg(batch_size=3, n_epochs=1, decoding="greedy", dropout=1.0, lr_init=lr, lr_method=method, clip=5.0)
+    m = Img2SeqModel(cfg, vocab=SimpleVocab(V), device="cuda", precision="fp32").build_train(cfg)
+    imgs, forms = [d[0] for d in data], [d[1] for d in data]
+    first = float(m.train_step(imgs, forms)[0])
+    for _ in range(25):
+        last = float(m.train_step(imgs, forms)[0])
+    assert np.isfinite(last) and last < 0.9 * first, (method, first, last)
+    with pytest.raises(NotImplementedError):
+        Img2SeqModel(_cfg(lr_method="lbfgs"), vocab=SimpleVocab(V), device="cuda", precision="fp32").build_train()
