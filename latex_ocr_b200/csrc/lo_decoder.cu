@@ -877,8 +877,9 @@ static int check_args(const lo_decoder_args* a) {
   LO_CHECK_ARG(a->ldl == 0 || a->ldl >= a->V, "ldl >= V");
   LO_CHECK_ARG(a->rows_per_img <= 1 || a->B % a->rows_per_img == 0, "B must be a multiple of rows_per_img");
   LO_CHECK_ARG(a->bt_host && a->caps && a->enc && a->work, "null pointer");
-  LO_CHECK_ARG(a->has_dropout != 2 || (a->dropout_state && a->dropout_p >= 0.f && a->dropout_p < 1.f && !g_opt_fuse_lstm),
-               "has_dropout=2 needs dropout_state, 0 <= dropout_p < 1 and fuse_lstm=0");
+  LO_CHECK_ARG(a->has_dropout != 2 || (a->dropout_state && a->dropout_p >= 0.f && a->dropout_p < 1.f &&
+                                       (!g_opt_fuse_lstm || g_opt_skinny_mma)),
+               "has_dropout=2 needs dropout_state, 0 <= dropout_p < 1 (and the mma.sync kernel when fuse_lstm=1)");
   for (int t = 0; t < a->T; t++) {
     LO_CHECK_ARG(a->bt_host[t] >= 1 && a->bt_host[t] <= a->B, "bt_host out of range");
     if (t) LO_CHECK_ARG(a->bt_host[t] <= a->bt_host[t - 1], "bt_host must be non-increasing");
@@ -1060,7 +1061,8 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
     TcLstmEpi e{a->ptab, tok + r0 * tok_stride, tok_stride, o1 + d.A + d.C, d.O1, c_prev, a->gates + ((int64_t)t * d.B + r0) * d.G,
                 a->call + ((int64_t)(t + 1) * d.B + r0) * d.D, a->hall + ((int64_t)(t + 1) * d.B + r0) * d.D,
                 bv.hall + ((int64_t)(t + 1) * d.B + r0) * d.D, hd_t ? hd_t + r0 * hd_stride : (float*)nullptr, hd_stride,
-                dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, d.D, d.V};
+                dmask_t ? dmask_t + r0 * hd_stride : (const float*)nullptr, d.D, d.V,
+                (const unsigned long long*)((hd_t && a->has_dropout == 2) ? a->dropout_state : nullptr), a->dropout_p, (int)r0, t};
     if (g_opt_skinny_mma && nrows <= 64 && d.C <= 512)
       return skinny_gemm_nt_lstm(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, bv.wil, d.C, nrows, d.D, d.C, e, st);
     return tc_gemm_nt_lstm(bv.gctx + ((int64_t)t * d.B + r0) * d.C, d.C, bv.wil, d.C, nrows, d.D, d.C, e, st);
