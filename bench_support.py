@@ -175,8 +175,10 @@ def kernel_probes(model, c, pk):
 
     ms_tc = _time_ms(conv_tc, 3)
     flops_tc = B * 3 * 2 * 9.296e9     # layers 2-6: 9.296 GMAC/image, x3 passes (fwd, dgrad, wgrad)
-    conv_tc_r = {"kernel": "tcgen05 conv kernels only: tc_gemm_conv_kernel (fwd + dgrad) and tc_wgrad_kernel, layers 2-6", "bound": "tensor",
-                 "achieved": flops_tc / (ms_tc * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "traffic": None, "ms": ms_tc,
+    conv_tc_r = {"kernel": "tcgen05 conv kernels only: tc_conv_p_kernel (persistent, 128x256 tiles, fwd + dgrad) and tc_wgrad_kernel, "
+                           "layers 2-6 (15 launches)", "bound": "tensor",
+                 "achieved": flops_tc / (ms_tc * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                 "traffic": traffic_of("tc_conv_p_kernel"), "traffic_note": "mean DRAM bytes per tc_conv_p_kernel launch (ncu)", "ms": ms_tc,
                  "algorithmic_flops": flops_tc, "peak_source": pk["src"] + " (sustained cuBLAS bf16)"}
     conv_tc_r["frac"] = conv_tc_r["achieved"] / conv_tc_r["peak"]
 
