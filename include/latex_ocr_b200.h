@@ -94,6 +94,14 @@ int lo_conv1_pool_forward_norm(const void* img, int img_is_u8, float scale, floa
 int lo_conv1_pool_wgrad_norm(const void* img, int img_is_u8, float scale, float offset, const float* w,
                              const float* bias, const void* dpool, int dt, float* dw, float* db, int N, int H, int W,
                              void* stream);
+/* Training variant: the forward additionally stores one byte per pooled output and channel, [N][H/2][W/2][64] — bits 0-1 the
+ * window index (py*2+px) of the pool arg-max (first maximum in scan order, as nn.MaxPool2d), bit 2 the ReLU bit — and the
+ * weight gradient reads the codes instead of recomputing conv1.  img fp32 or uint8 (img_is_u8); scale/offset as above (1, 0 for
+ * the torch flavour). */
+int lo_conv1_pool_forward_code(const void* img, int img_is_u8, float scale, float offset, const float* w, const float* bias,
+                               void* out, uint8_t* code, int dt, int N, int H, int W, void* stream);
+int lo_conv1_pool_wgrad_code(const void* img, int img_is_u8, float scale, float offset, const uint8_t* code, const void* dpool,
+                             int dt, float* dw, float* db, int N, int H, int W, void* stream);
 /* General strided convolution = im2col + lo_gemm: the 'cnn' encoder variant's Conv2d(512,512,(2,4),stride=2,padding=1)
  * (seq2seq_torch.py:80).  col [N*Ho*Wo][R*S*C], taps-major, C % 8 == 0; forward y = relu(col W^T + b) with W [Cout][R][S][C];
  * weight gradient dW = dy^T col; data gradient dcol = dy W then lo_col2im (a gather over the windows covering each input

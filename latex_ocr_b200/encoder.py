@@ -180,7 +180,14 @@ class EncoderCNN(nn.Module):
         st, dt, impl, S = stream_ptr(), _dt(self.precision), self._impl(), self.store
         A = ws["acts"]
         ws["img"] = img
-        if self.input_norm == "tf":
+        sc, of = (1.0 / 128.0, -1.0) if self.input_norm == "tf" else (1.0, 0.0)
+        if need_grad:
+            # training: conv1 also stores the pool arg-max / ReLU code per output (1 byte) for its weight-gradient kernel
+            if ws.get("code0") is None:
+                ws["code0"] = torch.empty(A["P0"].shape, dtype=torch.uint8, device=img.device)
+            check(L.lo_conv1_pool_forward_code(ptr(img), int(img.dtype == torch.uint8), sc, of, ptr(S.f32("cnn.0.weight")),
+                                               ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), ptr(ws["code0"]), dt, N, H, W, st))
+        elif self.input_norm == "tf":
             check(L.lo_conv1_pool_forward_norm(ptr(img), int(img.dtype == torch.uint8), 1.0 / 128.0, -1.0, ptr(S.f32("cnn.0.weight")),
                                                ptr(S.f32("cnn.0.bias")), ptr(A["P0"]), dt, N, H, W, st))
         else:
@@ -272,7 +279,11 @@ class EncoderCNN(nn.Module):
                 ysrc = A[src]
                 check(L.lo_maxpool_backward(ptr(ysrc), ptr(A[xin]), ptr(G[xin]), ptr(G[src]), dt, N, ysrc.shape[1], ysrc.shape[2],
                                             ysrc.shape[3], pool_k[0], pool_k[1], st))
-        if self.input_norm == "tf":
+        sc, of = (1.0 / 128.0, -1.0) if self.input_norm == "tf" else (1.0, 0.0)
+        if ws.get("code0") is not None:
+            check(L.lo_conv1_pool_wgrad_code(ptr(ws["img"]), int(ws["img"].dtype == torch.uint8), sc, of, ptr(ws["code0"]), ptr(G["P0"]), dt,
+                                             ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))
+        elif self.input_norm == "tf":
             check(L.lo_conv1_pool_wgrad_norm(ptr(ws["img"]), int(ws["img"].dtype == torch.uint8), 1.0 / 128.0, -1.0,
                                              ptr(S.f32("cnn.0.weight")), ptr(S.f32("cnn.0.bias")), ptr(G["P0"]), dt,
                                              ptr(S.g("cnn.0.weight")), ptr(S.g("cnn.0.bias")), N, H, W, st))

@@ -212,12 +212,15 @@ class Img2SeqModel:
         losses = []
         t0 = time.time()
         nimg = 0
+        if getattr(self, "_batcher", None) is None:
+            from .data import PinnedBatcher
+            self._batcher = PinnedBatcher(self._vocab.id_pad, self._vocab.id_end)
         for i, (img, formula) in enumerate(minibatches(train_set, batch_size)):
-            img = pad_batch_images(img)                                            # utils/image.py:47 (255 padding)
-            img = torch.from_numpy(img).permute(0, 3, 1, 2)                        # img2seq_torch.py:115-117; kept uint8: conv1
-                                                                                   # casts on the GPU (4x less H2D, same values)
-            formula, _ = pad_batch_formulas(formula, self._vocab.id_pad, self._vocab.id_end)
-            formula = torch.from_numpy(formula.astype(np.int64))                   # :118
+            # pad_batch_images (utils/image.py:27-44, 255 padding) / pad_batch_formulas (utils/text.py:141-164) straight into pinned
+            # staging buffers (one per shape bucket): uint8 pixels [N,1,H,W] (img2seq_torch.py:115-117; conv1 casts on the GPU: 4x
+            # less H2D, same values) and int64 ids.  getLoss synchronises on the loss, so a buffer is free again when it returns.
+            img = self._batcher.images(img)
+            formula = self._batcher.formulas(formula)
             loss_eval = self.getLoss(img, formula=formula, lr=getattr(lr_schedule, "lr", None),
                                      dropout=getattr(config, "dropout", None), training=True)
             losses.append(loss_eval)

@@ -99,8 +99,9 @@ def test_predict_batch_surface():
     assert all(29 not in seq for seq in out[0])        # truncated at END
 
 
-def test_train_epoch_and_evaluate_surface():
-    """_run_train_epoch / evaluate with the reference's data conventions (lists of HWC uint8 arrays + token-id lists)."""
+def test_train_epoch_and_evaluate_surface(tmp_path):
+    """_run_train_epoch / evaluate with the reference's data conventions (lists of HWC uint8 arrays + token-id lists); answer files,
+    save-on-best epoch checkpoints and resume-from-latest (base.py:33-69, :95-140)."""
     import numpy as np
     from latex_ocr_b200.data import SimpleVocab
     from latex_ocr_b200.img2seq import Img2SeqModel
@@ -112,13 +113,30 @@ def test_train_epoch_and_evaluate_surface():
     data = [(rng.randint(0, 256, (32, 64 + 16 * (i % 2), 1)).astype(np.uint8), list(rng.randint(0, V - 3, 3 + i % 3))) for i in range(6)]
     # same-shape batches like the reference's bucketing (data_generator.py:84-122)
     data.sort(key=lambda d: d[0].shape)
-    cfg = Cfg(batch_size=3, n_epochs=1, max_length_formula=6, decoding="greedy")
-    m = Img2SeqModel(cfg, vocab=vocab, device="cuda", precision="fp32").build_train()
+    cfg = Cfg(batch_size=3, n_epochs=2, max_length_formula=6, decoding="greedy", dir_answers=str(tmp_path) + "/answers/")
+    m = Img2SeqModel(cfg, dir_output=str(tmp_path), vocab=vocab, device="cuda", precision="fp32").build_train()
     sched = LRSchedule(lr_init=1e-3, apply_to=m)
     score = m.train(cfg, data, data, sched)
     assert score < 0 and np.isfinite(score)                      # negated perplexity
     s = m.last_epoch_stats
     assert {"BLEU-4", "ExactMatchScore", "EditDistance", "perplexity", "images_per_s"} <= set(s)
+    # write_prediction wrote the answer files the scores were computed from (img2seq.py:215-254)
+    import os
+    assert sorted(os.listdir(str(tmp_path) + "/answers/")) == ["hyp_0.txt", "ref.txt"]
+    assert len(open(str(tmp_path) + "/answers/ref.txt").read().splitlines()) == len(data)
+    files, perp = m.write_prediction(cfg, data)
+    assert perp < 0 and files[0].endswith("ref.txt")
+    # train() saved a checkpoint on every new best score, keeping one (max_to_keep=1); a fresh model resumes from it
+    ck = os.listdir(str(tmp_path) + "/model_weights")
+    assert len(ck) == 1 and ck[0].startswith("model.cpkt-")
+    m.save_session(7)                                            # current state; the older checkpoint is dropped
+    ck = os.listdir(str(tmp_path) + "/model_weights")
+    assert ck == ["model.cpkt-7"]
+    m2 = Img2SeqModel(cfg, dir_output=str(tmp_path), vocab=vocab, device="cuda", precision="fp32").build_train()
+    ep = m2.restore_latest()
+    assert ep == int(ck[0].split("-")[1]) and m2.startepoch == ep
+    assert torch.equal(m2.decoder.store.master, m.decoder.store.master) and torch.equal(m2.encoder.store.m, m.encoder.store.m)
+    assert m2.predict_batch([d[0] for d in data[:3]]) == m.predict_batch([d[0] for d in data[:3]])
     # frozen encoder: fine_tune(False) leaves every conv weight untouched by the fused Adam
     before = m.encoder.store.master.clone()
     m.encoder.fine_tune(False)
