@@ -1031,6 +1031,7 @@ extern "C" int lo_get_option(const char* name) {
   if (!strcmp(name, "pdl")) return lo::g_opt_pdl;
   if (!strcmp(name, "conv_persist")) return lo::g_opt_conv_persist;
   if (!strcmp(name, "wgrad256")) return lo::g_opt_wgrad256;
+  if (!strcmp(name, "conv_mt2")) return lo::g_opt_conv_mt2;
   if (!strcmp(name, "dec_fuse")) return lo::g_opt_dec_fuse;
   if (!strcmp(name, "dec_fuse_bwd")) return lo::g_opt_dec_fuse_bwd;
   if (!strcmp(name, "fuse_lstm")) return lo::g_opt_fuse_lstm;
@@ -1051,6 +1052,7 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
   else if (!strcmp(name, "conv_persist")) lo::g_opt_conv_persist = value;
   else if (!strcmp(name, "wgrad256")) lo::g_opt_wgrad256 = value;
+  else if (!strcmp(name, "conv_mt2")) lo::g_opt_conv_mt2 = value;
   else if (!strcmp(name, "dec_streams")) { lo::g_opt_dec_streams = value; lo::g_opt_skinny8 = value >= 2 ? 0 : 1; }
   else if (!strcmp(name, "skinny8")) lo::g_opt_skinny8 = value;
   else if (!strcmp(name, "fuse_lstm")) lo::g_opt_fuse_lstm = value;

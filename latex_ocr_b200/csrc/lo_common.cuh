@@ -224,6 +224,7 @@ extern int g_opt_att_maskbits;
 extern int g_opt_conv_mc;
 extern int g_opt_conv_persist;
 extern int g_opt_wgrad256;
+extern int g_opt_conv_mt2;
 extern int g_opt_dec_streams;
 extern int g_opt_skinny8;
 int attention_fwd_pipe(const AttFwdArgs& x, int dt, int C, cudaStream_t st);

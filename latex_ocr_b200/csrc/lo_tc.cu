@@ -448,19 +448,23 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_conv_kernel(const __grid_c
 // per 64-wide K block a CTA pulls 16 KB of A + 32 KB of B from L2 for 4.2 MFLOP = 85 FLOP per L2 byte (128 x 128 tiles: 64).
 // The one-tile-per-CTA kernel above is L2-bandwidth bound at 45-56 % tensor-pipe activity (profiles/r1_tc_conv_r1_raw.csv).
 // ------------------------------------------------------------------------------------------------
-template <int NT, int STAGES>
+template <int NT, int STAGES, int MT>
 struct TcPSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;              // one 128-position sub-tile
   static constexpr int B_BYTES = NT * TC_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * NT * 4 /*bias, double buffered*/;
 };
 
-template <int NT, int STAGES>
+// MT = 2 (layers with <= 128 output channels): a CTA tile is TWO 128-position sub-tiles that share every weight (B) stage —
+// FLOP per byte of A equals N in an implicit GEMM, so with N <= 128 the B stage is as large as an A tile and sharing it
+// raises the FLOP per L2 byte from 64 to 87 (N = 128) / 43 to 52 (N = 64).
+template <int NT, int STAGES, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_p_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB, TcParams p, int ntiles_n,
-                                                                 int total_tiles) {
-  using SM = TcPSmem<NT, STAGES>;
+                                                                 int total_tiles, int mtiles) {
+  using SM = TcPSmem<NT, STAGES, MT>;
+  static_assert(2 * MT * NT <= 512, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_p_kernel(const __grid_c
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * NT);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * MT * NT);
   pdl_wait();
   pdl_trigger();
   tc_fence_before();
@@ -501,17 +505,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_p_kernel(const __grid_c
       // ===== TMA producer, A tiles (implicit im2col: tap = coordinate shift, halo = out-of-bounds zero fill) =====
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / ntiles_n;
-        const int img = mt / per_img, rem = mt % per_img;
-        const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+        const int mt0 = (tile / ntiles_n) * MT;
+        const int nsub = min(MT, mtiles - mt0);
+        int img[MT], h0[MT], w0[MT];
+#pragma unroll
+        for (int j = 0; j < MT; j++) {
+          const int mt = min(mt0 + j, mtiles - 1);
+          img[j] = mt / per_img;
+          const int rem = mt % per_img;
+          h0[j] = (rem / p.tiles_w) * p.BH;
+          w0[j] = (rem % p.tiles_w) * p.BW;
+        }
         for (int kb = 0; kb < KB; kb++, it++) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
-          mbar_expect_tx(full_bar + s, SM::A_BYTES);
+          mbar_expect_tx(full_bar + s, (uint32_t)nsub * SM::A_BYTES);
           const int tap = kb / cpb, cb = kb % cpb;
           const int r = tap / 3, q = tap % 3;
-          tma_load_4d(smem + s * SM::STAGE_BYTES, &mapA, full_bar + s, cb * TC_BK, w0 + q - p.pad, h0 + r - p.pad, img);
+#pragma unroll
+          for (int j = 0; j < MT; j++)
+            if (j < nsub)
+              tma_load_4d(smem + s * SM::STAGE_BYTES + j * SM::A_BYTES, &mapA, full_bar + s, cb * TC_BK, w0[j] + q - p.pad,
+                          h0[j] + r - p.pad, img[j]);
         }
       }
     }
@@ -528,7 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_p_kernel(const __grid_c
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
           mbar_expect_tx(full_bar + s, SM::B_BYTES);
-          tma_load_2d_hint(smem + s * SM::STAGE_BYTES + SM::A_BYTES, &mapB, full_bar + s, kb * TC_BK, n0, polB);
+          tma_load_2d_hint(smem + s * SM::STAGE_BYTES + MT * SM::A_BYTES, &mapB, full_bar + s, kb * TC_BK, n0, polB);
         }
       }
     }
@@ -540,19 +556,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_p_kernel(const __grid_c
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
         const uint32_t buf = lt & 1;
-        mbar_wait(tempty_bar + buf, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (2 tiles ago)
+        const int nsub = min(MT, mtiles - (tile / ntiles_n) * MT);
+        mbar_wait(tempty_bar + buf, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator set (2 tiles ago)
         tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * NT;
+        const uint32_t tacc = tmem_base + buf * (MT * NT);
         for (int kb = 0; kb < KB; kb++, it++) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(full_bar + s, ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
-          const uint64_t da = make_kmajor_sw128_desc(sa);
-          const uint64_t db = make_kmajor_sw128_desc(sa + SM::A_BYTES);
+          const uint64_t db = make_kmajor_sw128_desc(sa + MT * SM::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; k++) umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < MT; j++) {
+            if (j < nsub) {
+              const uint64_t da = make_kmajor_sw128_desc(sa + j * SM::A_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; k++)
+                umma_bf16(tacc + j * NT, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
           umma_commit(empty_bar + s);
         }
         umma_commit(tfull_bar + buf);
@@ -569,61 +592,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_p_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
       const uint32_t buf = lt & 1;
       const int n0 = (tile % ntiles_n) * NT;
-      const int mt = tile / ntiles_n;
-      const int img = mt / per_img, rem = mt % per_img;
-      const int h = (rem / p.tiles_w) * p.BH + row / p.BW, w = (rem % p.tiles_w) * p.BW + row % p.BW;
-      const bool row_ok = (h < p.Ho) && (w < p.Wo);
-      const int64_t row_off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
+      const int mt0 = (tile / ntiles_n) * MT;
+      const int nsub = min(MT, mtiles - mt0);
       float* sb = s_bias + buf * NT;
       for (int c = te; c < NT; c += 128) sb[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");               // bias of this tile staged (buffer last read 2 tiles ago)
       mbar_wait(tfull_bar + buf, (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + buf * NT + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < NT; c += 32) {
-        uint4 mk4[4];
-        if (use_mask && row_ok) {
+      for (int j = 0; j < nsub; j++) {
+        const int mt = mt0 + j;
+        const int img = mt / per_img, rem = mt % per_img;
+        const int h = (rem / p.tiles_w) * p.BH + row / p.BW, w = (rem % p.tiles_w) * p.BW + row % p.BW;
+        const bool row_ok = (h < p.Ho) && (w < p.Wo);
+        const int64_t row_off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.ldc;
+        const uint32_t tacc = tmem_base + buf * (MT * NT) + j * NT + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < NT; c += 32) {
+          uint4 mk4[4];
+          if (use_mask && row_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; g++)
-            if (n0 + c + g * 8 < p.N) mk4[g] = *reinterpret_cast<const uint4*>(p.mask + row_off + n0 + c + g * 8);
-        }
-        uint32_t v[32];
-        tmem_ld32(tacc + (uint32_t)c, v);
-        if (!row_ok) continue;
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const int n = n0 + c + g * 8;
-          if (n >= p.N) continue;
-          float f[8];
-          const float4 b0 = *reinterpret_cast<const float4*>(&sb[c + g * 8]);
-          const float4 b1 = *reinterpret_cast<const float4*>(&sb[c + g * 8 + 4]);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]) + bb[i];
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
+            for (int g = 0; g < 4; g++)
+              if (n0 + c + g * 8 < p.N) mk4[g] = *reinterpret_cast<const uint4*>(p.mask + row_off + n0 + c + g * 8);
           }
-          if (use_mask) {
-            const uint32_t wv[4] = {mk4[g].x, mk4[g].y, mk4[g].z, mk4[g].w};
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)c, v);
+          if (!row_ok) continue;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              if (!(__uint_as_float(wv[i] << 16) > 0.f)) f[2 * i] = 0.f;
-              if (!(__uint_as_float(wv[i] & 0xffff0000u) > 0.f)) f[2 * i + 1] = 0.f;
+          for (int g = 0; g < 4; g++) {
+            const int n = n0 + c + g * 8;
+            if (n >= p.N) continue;
+            float f[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(&sb[c + g * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sb[c + g * 8 + 4]);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = __uint_as_float(v[g * 8 + i]) + bb[i];
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], 0.f);
             }
+            if (use_mask) {
+              const uint32_t wv[4] = {mk4[g].x, mk4[g].y, mk4[g].z, mk4[g].w};
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                if (!(__uint_as_float(wv[i] << 16) > 0.f)) f[2 * i] = 0.f;
+                if (!(__uint_as_float(wv[i] & 0xffff0000u) > 0.f)) f[2 * i + 1] = 0.f;
+              }
+            }
+            st8(reinterpret_cast<bf16*>(p.out) + row_off + n, f);
           }
-          st8(reinterpret_cast<bf16*>(p.out) + row_off + n, f);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + buf);                  // this warp's quarter of the accumulator is free again
+      if (lane == 0) mbar_arrive(tempty_bar + buf);                  // this warp's quarter of the accumulators is free again
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * NT);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * MT * NT);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -966,22 +994,24 @@ int g_opt_wgrad256 = 0;       // conv weight gradient with 128 x 256 tiles when 
                               // cannot hide the loads: 3.64 vs 3.42 ms for the conv tensor kernels, run 50)
 int g_opt_conv_persist = 1;   // persistent double-accumulator kernel (tc_conv_p_kernel); 0 = one tile per CTA (tc_gemm_conv_kernel)
 
-template <int NT, int STAGES>
+int g_opt_conv_mt2 = 1;       // layers with <= 128 output channels: two 128-position sub-tiles per CTA tile share each weight stage
+
+template <int NT, int STAGES, int MT>
 static int launch_conv_p(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int mtiles, cudaStream_t st) {
-  using SM = TcPSmem<NT, STAGES>;
+  using SM = TcPSmem<NT, STAGES, MT>;
   static bool attr_set = false;
   static int n_sm = 0;
   if (!attr_set) {
-    LO_CUDA(cudaFuncSetAttribute(tc_conv_p_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    LO_CUDA(cudaFuncSetAttribute(tc_conv_p_kernel<NT, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     int dev = 0;
     LO_CUDA(cudaGetDevice(&dev));
     LO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
   const int ntn = cdiv(p.N, NT);
-  const int total = mtiles * ntn;
+  const int total = cdiv(mtiles, MT) * ntn;
   const int grid = total < n_sm ? total : n_sm;
-  LO_CUDA(launch_pdl(tc_conv_p_kernel<NT, STAGES>, dim3(grid), dim3(TC_THREADS), (size_t)SM::TOTAL, st, mA, mB, p, ntn, total));
+  LO_CUDA(launch_pdl(tc_conv_p_kernel<NT, STAGES, MT>, dim3(grid), dim3(TC_THREADS), (size_t)SM::TOTAL, st, mA, mB, p, ntn, total, mtiles));
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -1015,9 +1045,9 @@ int tc_conv3x3(const bf16* x, const bf16* w, const float* bias, const bf16* mask
     p.BW = BW; p.BH = BH; p.tiles_w = cdiv(Wo, BW); p.tiles_h = cdiv(Ho, BH);
     p.bias = bias; p.mask = mask; p.out = y; p.ldc = Cout; p.relu = relu;
     const int mtiles = N * p.tiles_w * p.tiles_h;
-    if (NTp == 256) return launch_conv_p<256, 4>(mA, mB, p, mtiles, st);
-    if (NTp == 128) return launch_conv_p<128, 6>(mA, mB, p, mtiles, st);
-    return launch_conv_p<64, 8>(mA, mB, p, mtiles, st);
+    if (NTp == 256) return launch_conv_p<256, 4, 1>(mA, mB, p, mtiles, st);
+    if (NTp == 128) return g_opt_conv_mt2 ? launch_conv_p<128, 4, 2>(mA, mB, p, mtiles, st) : launch_conv_p<128, 6, 1>(mA, mB, p, mtiles, st);
+    return g_opt_conv_mt2 ? launch_conv_p<64, 4, 2>(mA, mB, p, mtiles, st) : launch_conv_p<64, 8, 1>(mA, mB, p, mtiles, st);
   }
   CUtensorMap mA, mB;
   const int NT = Cout <= 64 ? 64 : 128;
