@@ -26,6 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG2 = dict(B=64, H=128, W=512, V=500, T=150)
+# EXTENSION workload (BASELINE.json configs[3], not in the reference): row-encoder biLSTM over the CNN feature rows + a second
+# decoder layer, 160x640 images (R = 18 * 78 = 1404 regions) — `--workload cfg4`, latex_ocr_b200/ext.py
+CFG4 = dict(B=64, H=160, W=640, V=500, T=150)
 FWD_BWD_GFLOP_PER_IMG = 56.0          # conv stack, SURVEY.md §8-d (18.67 fwd, x3 fwd+bwd)
 
 
@@ -131,6 +134,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-decode", action="store_true", help="omit the cfg #5 decode probe (N=1 only)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"], help="cfg4 = the row-encoder / two-layer EXTENSION")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,7 +153,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    c = dict(CFG2)
+    c = dict(CFG2 if args.workload == "cfg2" else CFG4)
     c["B"] = args.batch
     args.warmup = max(args.warmup, 3)
 
@@ -164,7 +168,11 @@ def main():
     kernels = args.kernels
     if kernels == "tc" and not bs.tc_ready():
         kernels = "simt"
-    model = Img2SeqModel(Cfg(), vocab=SimpleVocab(c["V"]), device="cuda:%d" % local, precision=args.precision, impl=kernels)
+    if args.workload == "cfg4":
+        from latex_ocr_b200.ext import Img2SeqRowModel as ModelCls
+    else:
+        ModelCls = Img2SeqModel
+    model = ModelCls(Cfg(), vocab=SimpleVocab(c["V"]), device="cuda:%d" % local, precision=args.precision, impl=kernels)
     model.build_train()
     model.train_mode(True)                     # dropout active, like the reference's training loop
     if world > 1:
@@ -236,6 +244,21 @@ def main():
     pk = peaks()
     total_imgs = c["B"] * world
     value = total_imgs / (ms / 1e3)
+    if args.workload == "cfg4":
+        out = {"metric": "formula-images/sec (train step, 160x640 px, seq<=150; row-encoder biLSTM + 2-layer decoder EXTENSION)",
+               "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+               "data": "synthetic",
+               "config": {"workload": "cfg4 (extension, not in the reference): batch %d/GPU, 1x160x640 images, 6-conv encoder + biLSTM(256) over "
+                                      "the 18 feature rows + attention LSTM + second LSTM layer, vocab 500, T=150" % c["B"],
+                          "global_batch": total_imgs, "parallelism": "dp%d" % world, "kernels": kernels, "cuda_graph": bool(Cfg.cuda_graph),
+                          "loss_after": final_loss},
+               "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": int(img.numel() * 1 + formula.numel() * 8), "d2h_bytes_per_step": 4},
+               "gpu_launches": int(per_step_launches * args.steps), "clocks": clocks, "roofline": None}
+        print(json.dumps(out), flush=True)
+        finish()
+        return
     probes = bs.kernel_probes(model, c, pk)
     log("probes done")
     out = {

@@ -184,6 +184,9 @@ typedef struct lo_decoder_args {
   int32_t ldl;             /* row stride of logits/dlogits (>= V; a multiple of 64 enables the tcgen05 fc GEMMs); 0 -> V */
   float alpha_c;           /* doubly-stochastic regulariser weight (img2seq_torch.py:157) */
   int32_t rows_per_img;    /* decode only: consecutive rows that share one image (beam size); 0/1 for training */
+  int32_t phase;           /* 0: whole call (default).  EXTENSION (a second decoder layer between the cell and fc): 1 = time loop
+                              only — lo_decoder_forward stops after writing hd, lo_decoder_backward starts from the dhd the caller
+                              put there; 2 = head only — logits + loss from whatever the caller left in hd, backward of fc -> dhd */
   const int32_t* bt_host;  /* HOST int[T]: rows active at step t (seq2seq_torch.py:308); non-increasing */
   const int64_t* caps;     /* [B][caps_stride] token ids (sorted rows) */
   int64_t caps_stride;
@@ -353,6 +356,39 @@ int lo_tfdec_beam(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t
 /* with the diversity penalty (see lo_decoder_beam_div) */
 int lo_tfdec_beam_div(const lo_tfdec_args* a, int64_t end_id, int max_steps, int64_t* ids, int64_t* parents, int32_t* fin_hist,
                       float* logp, float div_gamma, float div_prob, const float* div_u, const uint64_t* div_state, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * EXTENSION (not in the reference; BASELINE.json configs[3]): generic sequence LSTM with nn.LSTM semantics (gate order i,f,g,o,
+ * two bias vectors), forward over S steps for M independent sequences + hand-derived backward.  Used for the row-encoder biLSTM
+ * over the CNN feature rows (two calls, `reverse` = 0 / 1, writing the two halves of the output channels) and for a second decoder
+ * layer.  Element (t, m) of x / dx lives at m * row + t * step (+ channel); of hs / hs_st / dhs at m * hs_row + t * hs_step.
+ */
+typedef struct lo_lstm_seq_args {
+  int32_t S, M, I, H;      /* steps, sequences, input width, hidden width (I, H multiples of 8) */
+  int32_t dt;              /* storage of x / hs_st / the weight shadows: LO_F32 | LO_BF16 */
+  int32_t impl;            /* LO_IMPL_SIMT | LO_IMPL_TC (bf16 only) */
+  int32_t reverse;         /* 1: process t = S-1 .. 0 */
+  int32_t dx_accumulate;   /* backward: add onto dx instead of overwriting (second direction of a bidirectional layer) */
+  const void* x;           /* dt */
+  int64_t x_row, x_step;
+  const void* w_ih;        /* dt [4H][I] */
+  const void* w_hh;        /* dt [4H][H] */
+  const float* b_ih; const float* b_hh;   /* fp32 [4H] */
+  const float* h0; const float* c0;       /* optional fp32 [M][H] (NULL = zeros) */
+  float* hs;               /* optional out fp32 */
+  void* hs_st;             /* optional out, storage dtype */
+  int64_t hs_row, hs_step;
+  const float* dhs;        /* backward in: d loss / d hs (fp32, hs strides); NULL = zeros */
+  float* dx;               /* optional backward out fp32 */
+  int64_t dx_row, dx_step;
+  float* g_w_ih; float* g_w_hh; float* g_b_ih; float* g_b_hh;   /* backward out, fp32, overwritten */
+  float* dh0; float* dc0;  /* optional backward out fp32 [M][H] */
+  void* ws;                /* lo_lstm_seq_workspace_bytes(args) bytes; forward state is kept there for the backward */
+} lo_lstm_seq_args;
+int64_t lo_sizeof_lstm_seq_args(void);
+int64_t lo_lstm_seq_workspace_bytes(const lo_lstm_seq_args* a);
+int lo_lstm_seq_forward(const lo_lstm_seq_args* a, void* stream);
+int lo_lstm_seq_backward(const lo_lstm_seq_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimiser: torch.optim.Adam defaults (img2seq_torch.py:86-87, :168-170) on one flat buffer.

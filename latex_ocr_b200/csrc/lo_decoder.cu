@@ -1180,11 +1180,12 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const Dims d = dims(a);
   const bool ragged = a->bt_host[d.T - 1] < d.B;
-  if (ragged) {
+  if (ragged && a->phase != 2) {
     LO_CUDA(cudaMemsetAsync(a->alphas, 0, (size_t)d.B * d.T * d.R * 4, st));
     LO_CUDA(cudaMemsetAsync(a->hd, 0, (size_t)d.B * d.T * d.D * 4, st));
   }
   LO_TRY(upload_dlen(a, st));
+  if (a->phase != 2) {
   LO_TRY(forward_prologue(a, d, st));
   const int nchains = two_chains(a, d) ? 2 : 1;
   if (nchains == 2) {
@@ -1237,6 +1238,8 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
     LO_CUDA(cudaEventRecord(g_ev_join, g_side));
     LO_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
   }
+  }   // phase != 2
+  if (a->phase == 1) return LO_OK;       // extension: the caller runs a second layer over hd before the head
   // predictions = fc(dropout(h))  (seq2seq_torch.py:316), hoisted out of the loop
   const BfViews bvf = bf_views(a, d);
   const bool fc_tc = bvf.on && d.Vl % 64 == 0 && d.D % 64 == 0;
@@ -1296,16 +1299,20 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   const bool ragged = a->bt_host[d.T - 1] < d.B;
   const int ns = att_splits(d.B);
   const int64_t BT = (int64_t)d.B * d.T;
-  LO_TRY(lo_decoder_pack_bwd_weights(a, stream));
-  // sreg[b,t] = sum_r alpha dreg
   const float* dal = a->dalpha_ext ? a->dalpha_ext : a->dreg;
   const int64_t dal_b = a->dalpha_ext ? (int64_t)d.T * d.R : d.R, dal_t = a->dalpha_ext ? d.R : 0;
-  sreg_kernel<<<cdiv(BT, 8), 256, 0, st>>>(a->alphas, dal, dal_b, dal_t, a->sreg, d.B, d.T, d.R);
-  LO_LAUNCH_OK();
+  if (a->phase != 2) {
+    LO_TRY(lo_decoder_pack_bwd_weights(a, stream));
+    // sreg[b,t] = sum_r alpha dreg
+    sreg_kernel<<<cdiv(BT, 8), 256, 0, st>>>(a->alphas, dal, dal_b, dal_t, a->sreg, d.B, d.T, d.R);
+    LO_LAUNCH_OK();
+  }
   // fc backward (hoisted): g_w_fc = dlogits^T hd ; g_b_fc ; dhd = dlogits @ W_fc (* dropout mask)
   const BfViews bvf = bf_views(a, d);
   const bool fc_tc = bvf.on && d.Vl % 64 == 0 && d.D % 64 == 0 && !a->dalpha_ext;
-  if (fc_tc) {
+  if (a->phase == 1) {
+    // extension: d hd was put there by the caller (backward of the layer between the cell and fc)
+  } else if (fc_tc) {
     // (dlogits bf16 mirror was written by ce_kernel; generic-autograd callers that fill dlogits themselves use the SIMT path)
     LO_CUDA(cudaMemsetAsync(a->g_w_fc, 0, (size_t)d.V * d.D * 4, st));
     LO_TRY(tc_gemm_tn(bvf.dlogits, d.Vl, bvf.hd, d.D, a->g_w_fc, d.D, d.V, d.D, (int)BT, st));
@@ -1316,7 +1323,8 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     LO_TRY(gemm_tn(a->dlogits, LO_F32, d.Vl, a->hd, LO_F32, d.D, a->g_w_fc, LO_F32, d.D, d.V, d.D, (int)BT, 0, LO_IMPL_SIMT, st));
     LO_TRY(gemm_nn(a->dlogits, LO_F32, d.Vl, a->w_fc, dt, d.D, a->dhd, LO_F32, d.D, (int)BT, d.D, d.V, 0, LO_IMPL_SIMT, st));
   }
-  LO_TRY(colsum(a->dlogits, LO_F32, a->g_b_fc, (int)BT, d.V, d.Vl, 0, st));
+  if (a->phase != 1) LO_TRY(colsum(a->dlogits, LO_F32, a->g_b_fc, (int)BT, d.V, d.Vl, 0, st));
+  if (a->phase == 2) return LO_OK;
   LO_CUDA(cudaMemsetAsync(a->dxh, 0, (size_t)d.B * (d.C + d.D) * 4, st));
   LO_CUDA(cudaMemsetAsync(a->dc, 0, (size_t)d.B * d.D * 4, st));
   if (ragged) {
@@ -1676,3 +1684,5 @@ int lo_decoder_beam_div(const lo_decoder_args* a, int64_t start_id, int64_t end_
 
 // TensorFlow-flavour (Genthial) decoder: same translation unit, shares the kernels above
 #include "lo_tfdecoder.cuh"
+// generic sequence LSTM (extension: row-encoder biLSTM, second decoder layer)
+#include "lo_lstmseq.cuh"

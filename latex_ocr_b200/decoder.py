@@ -316,7 +316,21 @@ class DecoderWithAttention(nn.Module):
                                 1, 0, 0, 0, ptr(S.f32(n + ".bias")), 0, 0, _lib.LO_IMPL_SIMT, st))
             return hc[0], hc[1]
 
-    def run_forward(self, enc_flat, caps_sorted, decode_lengths, with_loss, need_grad, dropout_mask=None):
+    def run_phase(self, ws, phase, backward):
+        """Extension hook (a second layer between the cell and fc, latex_ocr_b200/ext.py): re-enter the C entry points with
+        ``lo_decoder_args.phase`` = 1 (time loop only) or 2 (fc head + loss only) on the argument block of run_forward."""
+        a = ws["args"]
+        a.phase = int(phase)
+        try:
+            L = _lib.lib()
+            if backward:
+                check(L.lo_decoder_backward(ctypes.byref(a), stream_ptr()))
+            else:
+                check(L.lo_decoder_forward(ctypes.byref(a), 1, stream_ptr()))
+        finally:
+            a.phase = 0
+
+    def run_forward(self, enc_flat, caps_sorted, decode_lengths, with_loss, need_grad, dropout_mask=None, phase=0):
         """enc_flat: storage-dtype CUDA [B,R,C] (sorted rows); caps_sorted: CUDA int64 [B,T+1].
         dropout_mask: None (no dropout), a [B,T,D] tensor of multipliers (injected, parity tests) or the string "philox"
         (mask drawn inside the kernels)."""
@@ -334,7 +348,11 @@ class DecoderWithAttention(nn.Module):
                 ws.pop("args", None)
             ws["t"]["dropout_mask"].copy_(dropout_mask)
         a = self.fill_args(ws, enc_flat, B, T, R, has_do)
-        check(L.lo_decoder_forward(ctypes.byref(a), 1 if with_loss else 0, stream_ptr()))
+        a.phase = int(phase)
+        try:
+            check(L.lo_decoder_forward(ctypes.byref(a), 1 if with_loss else 0, stream_ptr()))
+        finally:
+            a.phase = 0
         return ws
 
     def run_backward(self, ws):

@@ -137,6 +137,14 @@ class Img2SeqModel:
         self._adam(self.encoder.store, scale, self.encoder)
         return ws["t"]["loss"]
 
+    def _keepalive(self):
+        """Everything a captured graph replays on (the bounded workspace caches may evict their entries later)."""
+        return [list(self.decoder._ws.values()), list(self.encoder._ws.values())]
+
+    def _stores(self):
+        """Every flat parameter store the step updates (snapshotted around the pre-capture warm-up steps)."""
+        return tuple(getattr(self, n).store for n in ("encoder", "decoder", "row_encoder", "layer2") if getattr(self, n, None) is not None)
+
     def train_step(self, img, formula, sync=False):
         """img: float tensor [N,1,H,W] (CPU pinned or CUDA); formula: int64 [N,L] (CPU or CUDA).
         Returns the device loss vector [total, ce, reg, n_valid] (no host sync unless sync=True)."""
@@ -171,7 +179,7 @@ class Img2SeqModel:
             st["caps"].copy_(caps_d)
             # warm-up outside capture (allocates workspaces, sets kernel attributes); it must not train:
             # parameters, Adam moments/step and the bf16 shadows are restored afterwards
-            stores = (self.encoder.store, self.decoder.store)
+            stores = self._stores()
             snap = [{k: getattr(S, k).clone() for k in ("master", "m", "v", "adam_state", "shadow") if getattr(S, k) is not None}
                     for S in stores]
             side = torch.cuda.Stream()
@@ -192,7 +200,7 @@ class Img2SeqModel:
             st["graph"] = graph          # capture records the launches, it does not execute them
             # the graph replays on the workspaces that were live during capture: keep them alive even if the bounded
             # workspace caches evict their entries
-            st["keep"] = (list(self.decoder._ws.values()), list(self.encoder._ws.values()))
+            st["keep"] = self._keepalive()
             g = self._graphs[key] = st
         g["img"].copy_(img_d, non_blocking=True)
         g["caps"].copy_(caps_d, non_blocking=True)
