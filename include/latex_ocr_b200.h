@@ -145,8 +145,10 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
                          const float* wf, float* alpha, int64_t alpha_stride, float* ctx,
                          float* gate_pre, int64_t gate_stride, float* gctx,
                          int B, int R, int A, int C, void* work, void* stream);
-/* the same, additionally storing the ReLU mask bits [B][R][A/8] (bit 7 - a % 8 of byte a / 8 = att1 + att2 > 0) for
- * lo_attention_backward(relu_mask = ...) */
+/* the same, additionally storing the ReLU mask bits for lo_attention_backward(relu_mask = ...): relu_mask_out is
+ * [B][Rp][A/8] bytes with Rp = R rounded up to an even count; bit 7 - a % 8 of the byte of (r, a / 8) = att1 + att2 > 0, and that
+ * byte lives at (r / 2) * 2 * (A/8) + (a / 8) * 2 + (r & 1) within image b (the bytes of an even/odd row pair are adjacent).
+ * The buffer is opaque to callers: only its size matters. */
 int lo_attention_forward_mask(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                               const float* wf, float* alpha, int64_t alpha_stride, float* ctx,
                               float* gate_pre, int64_t gate_stride, float* gctx, uint8_t* relu_mask_out,
@@ -212,7 +214,7 @@ typedef struct lo_decoder_args {
   float* call;             /* [T+1][B][D] */
   float* out1;             /* [T][B][A+C+4D]: att2 | gate (sigmoid applied) | h@w_hh^T+b_hh */
   float* alphas;           /* [B][T][R] */
-  uint8_t* att_mask;       /* optional, training only: [T][B][R][A/8] — bit 7 - (a % 8) of byte a/8 = (att1[b][r][a] + att2_t[b][a] > 0),
+  uint8_t* att_mask;       /* optional, training only: [T][B][Rp][A/8], Rp = R rounded up to even (layout: lo_attention_forward_mask) — bit = (att1[b][r][a] + att2_t[b][a] > 0),
                               written by the forward attention kernel; the backward then streams enc + these 64 bytes per region
                               instead of enc + att1 (60.5 MB instead of 114 MB per step at cfg #2).  NULL: att1 is re-read. */
   float* ctx;              /* [T][B][C] */
@@ -332,7 +334,7 @@ typedef struct lo_tfdec_args {
   /* results */
   float* logits;           /* [T][B][ldl] time-major */
   float* alphas;           /* [B][T][R] */
-  uint8_t* att_mask;       /* optional, training only: [T][B][R][A/8] — bit 7 - (a % 8) of byte a/8 = (att1[b][r][a] + att2_t[b][a] > 0),
+  uint8_t* att_mask;       /* optional, training only: [T][B][Rp][A/8], Rp = R rounded up to even (layout: lo_attention_forward_mask) — bit = (att1[b][r][a] + att2_t[b][a] > 0),
                               written by the forward attention kernel; the backward then streams enc + these 64 bytes per region
                               instead of enc + att1 (60.5 MB instead of 114 MB per step at cfg #2).  NULL: att1 is re-read. */
   float* loss;             /* [4]: mean CE over valid tokens (x2), 0, n_words — ce_words (img2seq.py:74) = loss[0] * loss[3] */

@@ -21,6 +21,7 @@ int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
 int g_opt_att_policy_att1 = 2;
 int g_opt_att_nsplit = 0;        // 0 = automatic
 int g_opt_att_cluster = 1;
+int g_opt_att_bwd_mma = 1;       // 1: 512-wide bf16 backward with both contractions on mma.sync (attention_bwd_mma_kernel)
 int g_opt_att_maskbits = 1;      // 1: the forward attention kernel stores the ReLU mask bits, the backward streams them instead of att1       // 1: the splits of one batch row form a thread-block cluster and combine through DSMEM
 
 #ifndef LO_ATT_RPW
@@ -33,6 +34,22 @@ int g_opt_att_maskbits = 1;      // 1: the forward attention kernel stores the R
 #define AP_CWARPS 8
 #define AP_STAGES 3
 #define AP_MAXSPLIT 16
+
+
+// ---- timing build only (-DLO_ATT_TIMING, tools/att_timeline.py): per-CTA %globaltimer stamps of the last attention launch
+#ifdef LO_ATT_TIMING
+__device__ long long* g_att_ts = nullptr;
+__device__ __forceinline__ void att_ts(int k) {
+  if (g_att_ts) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_att_ts[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + k] = t;
+  }
+}
+#define ATT_TS(k, cond) do { if (cond) att_ts(k); } while (0)
+#else
+#define ATT_TS(k, cond) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t make_policy(int kind) {
   return kind == 1 ? l2_policy_evict_last() : (kind == 2 ? l2_policy_evict_first() : l2_policy_evict_normal());
@@ -54,6 +71,9 @@ __device__ __forceinline__ float att_dact(float pre, float post) {
   if constexpr (ACT == 0) return pre > 0.f ? 1.f : 0.f;
   else return 1.f - post * post;
 }
+
+// rows per split of the BACKWARD mask kernels: even, so that every stage starts on an (even, odd) row pair of the mask layout
+__host__ __device__ __forceinline__ int att_rows_per_split(int R, int nsplit) { return (((R + nsplit - 1) / nsplit) + 1) & ~1; }
 
 // NVA / NVC: 256-element groups per att1 row / per enc row (the torch flavour has A = C; the Genthial cell dim_e = 256 < C = 512)
 template <typename T, int NVA, int NVC>
@@ -96,6 +116,7 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
   const T* a1b = att1 + (int64_t)(b / rpi) * R * CHA;      // beam search: rpi consecutive rows attend over one image
   const T* eb = enc + (int64_t)(b / rpi) * R * CHC;
   float* alb = alpha + (int64_t)b * alpha_stride;
+  ATT_TS(0, threadIdx.x == 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < AP_STAGES; s++) {
@@ -125,6 +146,8 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
         const uint32_t bytes_a = (uint32_t)rows * CHA * (uint32_t)sizeof(T), bytes_c = (uint32_t)rows * CHC * (uint32_t)sizeof(T);
         T* sa = ring + (size_t)s * C::STAGE_ELEMS;
         mbar_expect_tx(full_bar + s, bytes_a + bytes_c);
+        ATT_TS(6, i == 0);
+        ATT_TS(7, i == nst - 1);
         if (pol_att1 == 3) bulk_g2s_nohint(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s);
         else bulk_g2s(sa, a1b + (int64_t)row * CHA, bytes_a, full_bar + s, pa);
         if (pol_enc == 3) bulk_g2s_nohint(sa + C::HALF_A, eb + (int64_t)row * CHC, bytes_c, full_bar + s);
@@ -139,15 +162,18 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
 #pragma unroll
     for (int j = 0; j < NVA; j++) ld8(wf + (j * 32 + lane) * 8, wv + j * 8);        // a parameter: independent of the preceding launch
     pdl_wait();
+    ATT_TS(1, threadIdx.x == 0);
     pdl_trigger();
 #pragma unroll
     for (int j = 0; j < NVA; j++) ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
+    ATT_TS(2, threadIdx.x == 0);
     for (int i = 0; i < nst; i++) {
       const int s = i % AP_STAGES;
       const uint32_t ph = (i / AP_STAGES) & 1;
       const int row = r0 + i * C::ROWS;
       const int rows = min(C::ROWS, r1 - row);
       mbar_wait(full_bar + s, ph);
+      ATT_TS(3, threadIdx.x == 0 && i == 0);
       const uint32_t sa = smem_u32(ring + (size_t)s * C::STAGE_ELEMS);
       const uint32_t se = sa + C::HALF_A * (uint32_t)sizeof(T);
       constexpr uint32_t ES = (uint32_t)sizeof(T);
@@ -158,7 +184,9 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
         float e0 = 0.f, e1 = 0.f;
         // training (ReLU score): bit 7 - (c % 8) of byte c/8 of row r = (att1[r][c] + att2[c] > 0); the backward reads these
         // 64 bytes per row instead of the 1 KB att1 row
-        uint8_t* mrow = MK ? mask_out + ((int64_t)b * R + row) * (CHA / 8) : nullptr;
+        // layout: byte (r, c/8) at (r/2) * 2*(CHA/8) + (c/8)*2 + (r&1) — the bytes of an (even, odd) row pair are adjacent, which
+        // is what the tensor-core backward wants (one 32-bit word per lane = its four A fragments of a 16 x 16 block)
+        uint8_t* mrow = MK ? mask_out + (int64_t)b * ((R + 1) & ~1) * (CHA / 8) : nullptr;
 #pragma unroll
         for (int j = 0; j < NVA; j++) {
           float v[8];
@@ -172,7 +200,7 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
             if (MK) bits = __funnelshift_l(__float_as_uint(pre), bits, 1);
             e0 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(pre), e0);
           }
-          if (MK) mrow[(int64_t)ra * (CHA / 8) + j * 32 + lane] = (uint8_t)(~bits);
+          if (MK) mrow[(int64_t)((row + ra) >> 1) * (CHA / 4) + (j * 32 + lane) * 2 + ((row + ra) & 1)] = (uint8_t)(~bits);
           if (two) {
             lds8(sa + ((uint32_t)rb * CHA + (j * 32 + lane) * 8) * ES, v, (const T*)nullptr);
             bits = 0;
@@ -182,7 +210,7 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
               if (MK) bits = __funnelshift_l(__float_as_uint(pre), bits, 1);
               e1 = fmaf(wv[j * 8 + q], att_act<ACT, sizeof(T) == 2>(pre), e1);
             }
-            if (MK) mrow[(int64_t)rb * (CHA / 8) + j * 32 + lane] = (uint8_t)(~bits);
+            if (MK) mrow[(int64_t)((row + rb) >> 1) * (CHA / 4) + (j * 32 + lane) * 2 + ((row + rb) & 1)] = (uint8_t)(~bits);
           }
         }
         e0 = warp_sum(e0);
@@ -219,7 +247,9 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
       if (lane == 0) mbar_arrive(empty_bar + s);
     }
   }
+  ATT_TS(4, threadIdx.x == 0);
   __syncthreads();     // every TMA write has landed and been consumed: the ring can be reused for the combine
+  ATT_TS(8, threadIdx.x == 0);
   float* s_acc = reinterpret_cast<float*>(ap_smem);          // [AP_CWARPS][CHC]
   if (wid < AP_CWARPS) {
     if (lane == 0) { s_m[wid] = m; s_l[wid] = l; }
@@ -288,6 +318,7 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
     // ... and normalises the attention weights of its own rows (scores never leave shared memory)
     for (int r = r0 + threadIdx.x; r < r1; r += AP_THREADS) alb[r] = expf(s_e[r - r0] - Mg) * invL;
     cluster.sync();                                          // peers may still be reading this CTA's shared memory
+    ATT_TS(5, threadIdx.x == 0);
     return;
   }
   float* part = partials + ((int64_t)b * nsplit + sp) * (CHC + 2);
@@ -595,7 +626,8 @@ __global__ void __launch_bounds__(AP_THREADS) attention_bwd_pipe_kernel(
 // Attention backward, mask-bit version (ReLU score): the forward kernel left 1 bit per att1 element (att1 + att2 > 0), so the
 // backward streams enc rows (CHC elements) + CHA/8 mask bytes per region instead of enc + att1 rows: 60.5 MB instead of
 // 114 MB per step at cfg #2.  Same math, same masks (the bits ARE the forward's comparisons), same combine order.
-// d w_full is not accumulated here (it needs relu(att1 + att2) itself): the post-loop sweep (datt1_kernel<.., WACC=true>) adds it.
+// d w_full: only its att2 term (sum_r on * de times att2) is accumulated here (dwf_part); the term that needs att1 itself is added by
+// the post-loop sweep (datt1_kernel<.., WACC = 2>).
 // ------------------------------------------------------------------------------------------------------------------------------
 #define APM_STAGES 5
 template <typename T, int NVA, int NVC>
@@ -617,7 +649,8 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_ke
     const float* __restrict__ dgctx, int64_t dg_stride, const float* __restrict__ dreg, int64_t dreg_stride,
     const float* __restrict__ sreg, int64_t sreg_stride, float* __restrict__ de, float* __restrict__ datt2, float* __restrict__ dgp,
     int64_t dcat_stride, bf16* __restrict__ datt2_bf, bf16* __restrict__ dgp_bf, float* __restrict__ dctx_out, int R, int nsplit,
-    int* __restrict__ counters, float* __restrict__ partials, int pol_enc) {
+    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, const float* __restrict__ att2,
+    float* __restrict__ dwf_part) {
   using C = ApmCfg<T, NVA, NVC>;
   constexpr int CHA = C::CHA, CHC = C::CHC, MB = CHA / 8;
   extern __shared__ __align__(128) uint8_t ap_smem[];
@@ -626,11 +659,11 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_ke
   __shared__ int s_last;
   const int b = blockIdx.y, sp = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int rps = (R + nsplit - 1) / nsplit;
+  const int rps = att_rows_per_split(R, nsplit);          // even (and ROWS is even): stages start on an (even, odd) row pair
   const int r0 = sp * rps, r1 = min(R, r0 + rps);
   const int nst = r1 > r0 ? (r1 - r0 + C::ROWS - 1) / C::ROWS : 0;
   const T* eb = enc + (int64_t)b * R * CHC;
-  const uint8_t* mb = mask + (int64_t)b * R * MB;
+  const uint8_t* mb = mask + (int64_t)b * ((R + 1) & ~1) * MB;      // pair layout, see attention_fwd_pipe_kernel
   if (threadIdx.x == 0) {
     for (int s = 0; s < APM_STAGES; s++) {
       mbar_init(full_bar + s, 1);
@@ -654,7 +687,7 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_ke
         mbar_wait(empty_bar + s, ph ^ 1);
         const int row = r0 + i * C::ROWS;
         const int rows = min(C::ROWS, r1 - row);
-        const uint32_t bytes_c = (uint32_t)rows * CHC * (uint32_t)sizeof(T), bytes_m = (uint32_t)rows * MB;
+        const uint32_t bytes_c = (uint32_t)rows * CHC * (uint32_t)sizeof(T), bytes_m = (uint32_t)((rows + 1) >> 1) * 2u * MB;
         uint8_t* st = ap_smem + (size_t)s * C::STAGE_BYTES;
         mbar_expect_tx(full_bar + s, bytes_c + bytes_m);
         bulk_g2s(st, eb + (int64_t)row * CHC, bytes_c, full_bar + s, pe);
@@ -751,8 +784,8 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_ke
         }
 #pragma unroll
         for (int j = 0; j < NVA; j++) {
-          const uint32_t m0 = sm[ra * MB + j * 32 + lane];
-          const uint32_t m1 = two ? sm[rb * MB + j * 32 + lane] : 0u;
+          const uint32_t m0 = sm[(ra >> 1) * 2 * MB + (j * 32 + lane) * 2 + (ra & 1)];
+          const uint32_t m1 = two ? sm[(rb >> 1) * 2 * MB + (j * 32 + lane) * 2 + (rb & 1)] : 0u;
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             if (m0 & (0x80u >> q)) macc[j * 8 + q] += de0;
@@ -787,6 +820,7 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_ke
     for (int c = sp * cps + threadIdx.x; c < min(CHA, (sp + 1) * cps); c += AP_THREADS) {
       float t = 0.f;
       for (int q = 0; q < nsplit; q++) t += cluster.map_shared_rank(s_part, q)[c];      // fixed order -> deterministic
+      if (dwf_part) dwf_part[(int64_t)b * CHA + c] += t * att2[(int64_t)b * o1_stride + c];    // att2 term of d w_full (one owner per (b, c))
       datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
       if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
     }
@@ -814,14 +848,305 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_ke
   for (int c = threadIdx.x; c < CHA; c += AP_THREADS) {
     float t = 0.f;
     for (int sidx = 0; sidx < nsplit; sidx++) t += __ldcg(pb + (int64_t)sidx * (CHA + 2) + 2 + c);
+    if (dwf_part) dwf_part[(int64_t)b * CHA + c] += t * att2[(int64_t)b * o1_stride + c];
+    datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+    if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// [r2b] Tensor-core backward for the 512-wide torch flavour (bf16): the two contractions of the step run on mma.sync instead of
+// CUDA-core FMAs / predicated adds, which made attention_bwd_mask_kernel instruction-issue bound (0.54 of the HBM peak):
+//   d[r]     = sum_c enc[r][c] * dctx[c]          A = 16 enc rows straight from the ring (ldmatrix), B = dctx split into bf16 hi+lo
+//                                                  (columns 0/1 of B, products exact, fp32 accumulation)
+//   datt2[a] = sum_r bit[r][a] * de[r]            A = mask bits expanded to bf16 {0, 2.0} with ONE shift + ONE and per register,
+//                                                  B = de split into bf16 hi+lo
+// A stage is 16 region rows; all 8 consumer warps share it: warp w takes channels [64w, 64w+64) of the dot product (4 k-steps),
+// the 16 partial sums per warp meet in shared memory behind one 256-thread named barrier, every warp then forms de for the 16
+// rows (redundantly: 16 lanes) and runs the mask contraction for ITS 64 attention columns (4 blocks of 16).  ~110 warp
+// instructions per warp and stage instead of ~260 per 2 rows.
+// Ring rows are padded to 1040 B (one bulk copy per row) so that the 8 rows of an ldmatrix phase hit 8 different 16-byte bank
+// groups.  Mask layout (written by the forward kernel): byte (r, a/8) lives at (r/2) * 2*(A/8) + (a/8)*2 + (r&1), i.e. the bytes
+// of an even/odd row pair are adjacent: a lane's four A registers per 16 x 16 block are then shifts of ONE 32-bit word
+// [even(q) | even(q+4) | odd(q) | odd(q+4)] (q = lane % 4: fragment k index = region row).  Fragment row m = g + 8h of block j
+// stands for attention column 64w + 8g + 2j + h (g = lane / 4): any bijection works, this one makes a lane's 8 columns one byte.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int ABM_STAGES = 5;
+constexpr int ABM_ROWS = 16;
+constexpr int ABM_CH = 512;
+constexpr int ABM_PITCH = ABM_CH * 2 + 16;                    // bytes per ring row
+constexpr int ABM_ENC_BYTES = ABM_ROWS * ABM_PITCH;
+constexpr int ABM_MSK_BYTES = ABM_ROWS * (ABM_CH / 8);
+constexpr int ABM_STAGE_BYTES = ABM_ENC_BYTES + ABM_MSK_BYTES;
+constexpr int ABM_SMEM = ABM_STAGES * ABM_STAGE_BYTES + 128 + 2 * AP_CWARPS * ABM_ROWS * 4;
+static_assert(ABM_STAGE_BYTES % 128 == 0, "stage alignment");
+
+__device__ __forceinline__ void att_ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
+}
+__device__ __forceinline__ void att_mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// (x, y) -> packed bf16 pair of the high parts (sel 0) or of the residuals x - hi(x) (sel 1); low half = x
+__device__ __forceinline__ uint32_t pack_split(float x, float y, int sel) {
+  const bf16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
+  __nv_bfloat162 r;
+  if (sel == 0) {
+    r.x = hx; r.y = hy;
+  } else {
+    r.x = __float2bfloat16_rn(x - __bfloat162float(hx));
+    r.y = __float2bfloat16_rn(y - __bfloat162float(hy));
+  }
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <bool CL>
+__global__ void __launch_bounds__(AP_THREADS, 2) attention_bwd_mma_kernel(
+    const uint8_t* __restrict__ mask, const bf16* __restrict__ enc, const float* __restrict__ gate, int64_t o1_stride,
+    const float* __restrict__ wf, const float* __restrict__ alpha, int64_t alpha_stride, const float* __restrict__ ctx,
+    const float* __restrict__ dgctx, int64_t dg_stride, const float* __restrict__ dreg, int64_t dreg_stride,
+    const float* __restrict__ sreg, int64_t sreg_stride, float* __restrict__ de, float* __restrict__ datt2, float* __restrict__ dgp,
+    int64_t dcat_stride, bf16* __restrict__ datt2_bf, bf16* __restrict__ dgp_bf, float* __restrict__ dctx_out, int R, int nsplit,
+    int* __restrict__ counters, float* __restrict__ partials, int pol_enc, const float* __restrict__ att2,
+    float* __restrict__ dwf_part) {
+  constexpr int CH = ABM_CH, MB = CH / 8;
+  extern __shared__ __align__(128) uint8_t ap_smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ap_smem + ABM_STAGES * ABM_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + ABM_STAGES;
+  float* s_pd = reinterpret_cast<float*>(ap_smem + ABM_STAGES * ABM_STAGE_BYTES + 128);      // [2][8 warps][16 rows] partial dots
+  __shared__ int s_last;
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rps = att_rows_per_split(R, nsplit);                // even: a stage starts on an even/odd row pair
+  const int r0 = sp * rps, r1 = min(R, r0 + rps);
+  const int nst = r1 > r0 ? (r1 - r0 + ABM_ROWS - 1) / ABM_ROWS : 0;
+  const int Rp = (R + 1) & ~1;
+  ATT_TS(0, threadIdx.x == 0);
+  const bf16* eb = enc + (int64_t)b * R * CH;
+  const uint8_t* mb = mask + (int64_t)b * Rp * MB;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ABM_STAGES; s++) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, AP_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int g = lane >> 2, q = lane & 3;
+  float macc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) macc[j][i] = 0.f;
+
+  if (wid == AP_CWARPS) {
+    // producer warp: enc and the mask bits of this step were written long before the preceding launch -> no griddepcontrol.wait
+    const uint64_t pe = make_policy(pol_enc), pm = l2_policy_evict_first();
+    for (int i = 0; i < nst; i++) {
+      const int s = i % ABM_STAGES;
+      const uint32_t ph = (i / ABM_STAGES) & 1;
+      const int row = r0 + i * ABM_ROWS;
+      const int rows = min(ABM_ROWS, r1 - row);
+      const uint32_t bytes_m = (uint32_t)((rows + 1) >> 1) * 2u * MB;
+      uint8_t* st = ap_smem + (size_t)s * ABM_STAGE_BYTES;
+      if (lane == 0) {
+        mbar_wait(empty_bar + s, ph ^ 1);
+        mbar_expect_tx(full_bar + s, (uint32_t)rows * CH * 2u + bytes_m);
+        ATT_TS(6, i == 0);
+        ATT_TS(7, i == nst - 1);
+      }
+      __syncwarp();
+      if (lane < rows) bulk_g2s(st + lane * ABM_PITCH, eb + (int64_t)(row + lane) * CH, CH * 2u, full_bar + s, pe);
+      else if (lane == ABM_ROWS) bulk_g2s(st + ABM_ENC_BYTES, mb + (int64_t)(row >> 1) * 2 * MB, bytes_m, full_bar + s, pm);
+    }
+    __syncwarp();
+    pdl_wait();
+  } else {
+    float sdot = 0.f;
+    float gv[16], cxv[16];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int c0 = (j * 32 + lane) * 8;
+      if (gate) ld8(gate + (int64_t)b * o1_stride + c0, gv + j * 8);
+      ld8(ctx + (int64_t)b * CH + c0, cxv + j * 8);
+    }
+    // this lane's slice of the B operand of the dot product: k = 64*wid + 16*s + 2q + {0,1,8,9}; columns 0 / 1 = hi / lo parts
+    float gq[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int k0 = 64 * wid + 16 * s + 2 * q;
+      if (gate && g < 2) {
+        const float2 u = *reinterpret_cast<const float2*>(gate + (int64_t)b * o1_stride + k0);
+        const float2 v = *reinterpret_cast<const float2*>(gate + (int64_t)b * o1_stride + k0 + 8);
+        gq[s][0] = u.x; gq[s][1] = u.y; gq[s][2] = v.x; gq[s][3] = v.y;
+      } else {
+        gq[s][0] = gq[s][1] = gq[s][2] = gq[s][3] = 1.f;
+      }
+    }
+    const float sreg_b = sreg ? sreg[(int64_t)b * sreg_stride] : 0.f;
+    // alpha and the regulariser gradient are forward-pass results: the first stage's values are fetched before the wait as well
+    const float* alb = alpha + (int64_t)b * alpha_stride;
+    float* deb = de + (int64_t)b * alpha_stride;
+    const float* drb = dreg + (int64_t)b * dreg_stride;
+    const int rr = lane & 15;
+    float pa = 0.f, pd = 0.f;
+    auto prefetch = [&](int i) {
+      const int r = r0 + i * ABM_ROWS + rr;
+      if (i < nst && r < r1) {
+        pa = alb[r];
+        pd = dreg ? drb[r] : 0.f;
+      }
+    };
+    prefetch(0);
+    pdl_wait();
+    ATT_TS(1, threadIdx.x == 0);
+    pdl_trigger();
+    uint32_t bd[4][2];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      bd[s][0] = bd[s][1] = 0u;
+      if (g < 2) {
+        const int k0 = 64 * wid + 16 * s + 2 * q;
+        const float2 u = *reinterpret_cast<const float2*>(dgctx + (int64_t)b * dg_stride + k0);
+        const float2 v = *reinterpret_cast<const float2*>(dgctx + (int64_t)b * dg_stride + k0 + 8);
+        bd[s][0] = pack_split(u.x * gq[s][0], u.y * gq[s][1], g);
+        bd[s][1] = pack_split(v.x * gq[s][2], v.y * gq[s][3], g);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int c0 = (j * 32 + lane) * 8;
+      float dg[8], gp[8], dc[8];
+      ld8(dgctx + (int64_t)b * dg_stride + c0, dg);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float gi = gate ? gv[j * 8 + i] : 1.f;
+        dc[i] = dg[i] * gi;
+        sdot = fmaf(dc[i], cxv[j * 8 + i], sdot);
+        gp[i] = dg[i] * cxv[j * 8 + i] * gi * (1.f - gi);
+      }
+      if (sp == 0 && wid == 0) {
+        if (dgp) st8(dgp + (int64_t)b * dcat_stride + c0, gp);
+        if (dgp_bf) st8(dgp_bf + (int64_t)b * dcat_stride + c0, gp);
+        if (dctx_out) st8(dctx_out + (int64_t)b * CH + c0, dc);
+      }
+    }
+    const float sall = warp_sum(sdot) + sreg_b;
+    ATT_TS(2, threadIdx.x == 0);
+    const uint32_t ring = smem_u32(ap_smem);
+    const uint32_t a_off = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * ABM_PITCH + (uint32_t)(64 * wid + (lane >> 4) * 8) * 2u;
+    const uint32_t m_off = ABM_ENC_BYTES + (uint32_t)q * 2u * MB + (uint32_t)(8 * wid + g) * 2u;
+    for (int i = 0; i < nst; i++) {
+      const int s = i % ABM_STAGES;
+      const uint32_t ph = (i / ABM_STAGES) & 1;
+      const int row = r0 + i * ABM_ROWS;
+      const int rows = min(ABM_ROWS, r1 - row);
+      const float al = pa, dr = pd;
+      prefetch(i + 1);
+      mbar_wait(full_bar + s, ph);
+      ATT_TS(3, threadIdx.x == 0 && i == 0);
+      const uint32_t sb = ring + (uint32_t)s * ABM_STAGE_BYTES;
+      // ---- partial dot products of the 16 rows over this warp's 64 channels
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t a0, a1, a2, a3;
+        att_ldsm_x4(a0, a1, a2, a3, sb + a_off + k * 32);
+        att_mma_16816(d4, a0, a1, a2, a3, bd[k][0], bd[k][1]);
+      }
+      // this lane's mask word (read now: the ring slot is released right after the barrier-independent part)
+      const uint32_t u_lo = *reinterpret_cast<const uint16_t*>(ap_smem + (size_t)s * ABM_STAGE_BYTES + m_off);
+      const uint32_t u_hi = *reinterpret_cast<const uint16_t*>(ap_smem + (size_t)s * ABM_STAGE_BYTES + m_off + 4 * 2 * MB);
+      const uint32_t mw = __byte_perm(u_lo, u_hi, 0x5140);      // [even(q) | even(q+4) | odd(q) | odd(q+4)]
+      float* pdw = s_pd + (i & 1) * (AP_CWARPS * ABM_ROWS);
+      if (q == 0) {
+        pdw[wid * ABM_ROWS + g] = d4[0] + d4[1];
+        pdw[wid * ABM_ROWS + g + 8] = d4[2] + d4[3];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + s);                 // every lane of this warp has read what it needs from the slot
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float dsum = 0.f;
+#pragma unroll
+      for (int w = 0; w < AP_CWARPS; w++) dsum += pdw[w * ABM_ROWS + rr];
+      const float dev = rr < rows ? al * (dsum + dr - sall) : 0.f;
+      if (wid == (i & 7) && lane < rows) deb[row + lane] = dev;
+      // ---- mask contraction: B = de of rows (2q, 2q+1, 2q+8, 2q+9), hi parts in column 0 (g == 0), residuals in column 1
+      const float v0 = __shfl_sync(0xffffffffu, dev, 2 * q), v1 = __shfl_sync(0xffffffffu, dev, 2 * q + 1);
+      const float v2 = __shfl_sync(0xffffffffu, dev, 2 * q + 8), v3 = __shfl_sync(0xffffffffu, dev, 2 * q + 9);
+      uint32_t bm0 = 0u, bm1 = 0u;
+      if (g < 2) {
+        bm0 = pack_split(v0, v1, g);
+        bm1 = pack_split(v2, v3, g);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t af[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) {
+          // element e=0 (low half): bit 8*rs + 7 - (2j + h); e=1: 16 above.  -> bit 14 / 30 (bf16 2.0)
+          const int h = ii & 1, rs = ii >> 1;
+          const int sh = 14 - (8 * rs + 7 - (2 * j + h));
+          af[ii] = (sh >= 0 ? (mw << sh) : (mw >> (-sh))) & 0x40004000u;
+        }
+        att_mma_16816(macc[j], af[0], af[1], af[2], af[3], bm0, bm1);
+      }
+    }
+  }
+  ATT_TS(4, threadIdx.x == 0);
+  __syncthreads();
+  ATT_TS(8, threadIdx.x == 0);
+  float* s_part = reinterpret_cast<float*>(ap_smem);             // [CH] mask sums of this CTA (every column has ONE owner lane)
+  if (wid < AP_CWARPS && q == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      s_part[64 * wid + 8 * g + 2 * j] = 0.5f * (macc[j][0] + macc[j][1]);
+      s_part[64 * wid + 8 * g + 2 * j + 1] = 0.5f * (macc[j][2] + macc[j][3]);
+    }
+  }
+  __syncthreads();
+  if constexpr (CL) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    const int cps = (CH + nsplit - 1) / nsplit;
+    for (int c = sp * cps + threadIdx.x; c < min(CH, (sp + 1) * cps); c += AP_THREADS) {
+      float t = 0.f;
+      for (int qq = 0; qq < nsplit; qq++) t += cluster.map_shared_rank(s_part, qq)[c];      // fixed order -> deterministic
+      if (dwf_part) dwf_part[(int64_t)b * CH + c] += t * att2[(int64_t)b * o1_stride + c];      // att2 term of d w_full (one owner per (b, c))
+      datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
+      if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
+    }
+    cluster.sync();
+    ATT_TS(5, threadIdx.x == 0);
+    return;
+  }
+  float* part = partials + ((int64_t)b * nsplit + sp) * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += AP_THREADS) part[2 + c] = s_part[c];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + b, 1);
+    s_last = (ticket == nsplit - 1);
+    if (s_last) counters[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = partials + (int64_t)b * nsplit * (CH + 2);
+  for (int c = threadIdx.x; c < CH; c += AP_THREADS) {
+    float t = 0.f;
+    for (int sidx = 0; sidx < nsplit; sidx++) t += __ldcg(pb + (int64_t)sidx * (CH + 2) + 2 + c);
+    if (dwf_part) dwf_part[(int64_t)b * CH + c] += t * att2[(int64_t)b * o1_stride + c];
     datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
     if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
   }
 }
 
 int att_pipe_splits(int B, int hint = 0) {
+  if (g_opt_att_nsplit > 0) return g_opt_att_nsplit > AP_MAXSPLIT ? AP_MAXSPLIT : g_opt_att_nsplit;      // explicit option wins
   if (hint > 0) return hint > 8 ? 8 : hint;
-  if (g_opt_att_nsplit > 0) return g_opt_att_nsplit > AP_MAXSPLIT ? AP_MAXSPLIT : g_opt_att_nsplit;
   // two CTAs per SM are resident (smem): one full wave of <= 296 CTAs.  Measured at B=64, R=868 (bf16): 4 splits
   // (256 CTAs, 14 stages each) 25.9 us vs 9 splits (576 CTAs = 2 waves) 32.8 us — per-CTA start-up/combine
   // costs dominate short CTAs (profiles/r1_attention_nsplit_sweep.txt)
@@ -937,6 +1262,26 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
+  if constexpr (ACT == 0 && sizeof(T) == 2 && NVA == 2 && NVC == 2) if (x.mask_in && g_opt_att_bwd_mma) {
+    static bool attr_t = false;
+    if (!attr_t) {
+      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
+      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
+      attr_t = true;
+    }
+#define LO_BWDT_ARGS                                                                                                                  \
+  x.mask_in, (const bf16*)x.enc, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride, x.dreg,            \
+      x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,           \
+      (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, x.att2, x.dwf_part
+    if (use_cluster(ns, x.R)) {
+      LO_CUDA(launch_att(attention_bwd_mma_kernel<true>, dim3(ns, x.B), (size_t)ABM_SMEM, ns, st, LO_BWDT_ARGS));
+    } else {
+      LO_CUDA(launch_att(attention_bwd_mma_kernel<false>, dim3(ns, x.B), (size_t)ABM_SMEM, 1, st, LO_BWDT_ARGS));
+    }
+#undef LO_BWDT_ARGS
+    LO_LAUNCH_OK();
+    return LO_OK;
+  }
   if constexpr (ACT == 0) if (x.mask_in) {
     using CM = ApmCfg<T, NVA, NVC>;
     static bool attr_m = false;
@@ -948,7 +1293,7 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
 #define LO_BWDM_ARGS                                                                                                                  \
   x.mask_in, (const T*)x.enc, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride, x.dreg, x.dreg_stride, \
       x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns, (int*)x.work,           \
-      (float*)((char*)x.work + 4096), g_opt_att_policy_enc
+      (float*)((char*)x.work + 4096), g_opt_att_policy_enc, x.att2, x.dwf_part
     if (use_cluster(ns, x.R)) {
       LO_CUDA(launch_att(attention_bwd_mask_kernel<T, NVA, NVC, true>, dim3(ns, x.B), (size_t)CM::SMEM, ns, st, LO_BWDM_ARGS));
     } else {
@@ -993,7 +1338,15 @@ int attention_bwd_pipe(const AttBwdArgs& x, int dt, int C, cudaStream_t st) {
 }  // namespace lo
 
 namespace lo { extern long long* g_tc_dbg; }
-extern "C" int lo_debug_buffer(void* p) { lo::g_tc_dbg = (long long*)p; return LO_OK; }
+extern "C" int lo_debug_buffer(void* p) {
+  lo::g_tc_dbg = (long long*)p;
+  LO_TRY(lo::cl_set_ts((long long*)p));
+#ifdef LO_ATT_TIMING
+  long long* q = (long long*)p;
+  LO_CUDA(cudaMemcpyToSymbol(lo::g_att_ts, &q, sizeof(q)));
+#endif
+  return LO_OK;
+}
 
 // L2 persistence experiment: access-policy window of `stream` over [base, base+bytes) (hit -> persisting, miss -> streaming) and
 // the persisting carve-out sized to fit; bytes = 0 resets both.  Attention loads honour it with att_policy_* = 3 (no cache hint).
@@ -1027,12 +1380,15 @@ extern "C" int lo_get_option(const char* name) {
   if (!name) return -1;
   if (!strcmp(name, "att_pipe")) return lo::g_opt_att_pipe;
   if (!strcmp(name, "att_maskbits")) return lo::g_opt_att_maskbits;
+  if (!strcmp(name, "att_bwd_mma")) return lo::g_opt_att_bwd_mma;
   if (!strcmp(name, "att_cluster")) return lo::g_opt_att_cluster;
   if (!strcmp(name, "pdl")) return lo::g_opt_pdl;
   if (!strcmp(name, "conv_persist")) return lo::g_opt_conv_persist;
   if (!strcmp(name, "wgrad256")) return lo::g_opt_wgrad256;
   if (!strcmp(name, "conv_mt2")) return lo::g_opt_conv_mt2;
   if (!strcmp(name, "dec_fuse")) return lo::g_opt_dec_fuse;
+  if (!strcmp(name, "dec_cl")) return lo::g_opt_dec_cl;
+  if (!strcmp(name, "dec_cl_bwd")) return lo::g_opt_dec_cl_bwd;
   if (!strcmp(name, "dec_fuse_bwd")) return lo::g_opt_dec_fuse_bwd;
   if (!strcmp(name, "fuse_lstm")) return lo::g_opt_fuse_lstm;
   if (!strcmp(name, "skinny_mma")) return lo::g_opt_skinny_mma;
@@ -1049,6 +1405,8 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "pdl")) lo::g_opt_pdl = value;
   else if (!strcmp(name, "att_cluster")) lo::g_opt_att_cluster = value;
   else if (!strcmp(name, "att_maskbits")) lo::g_opt_att_maskbits = value;
+  else if (!strcmp(name, "att_bwd_mma")) lo::g_opt_att_bwd_mma = value;
+  else if (!strcmp(name, "dbg_skip")) lo::g_opt_dbg_skip = value;
   else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
   else if (!strcmp(name, "conv_persist")) lo::g_opt_conv_persist = value;
   else if (!strcmp(name, "wgrad256")) lo::g_opt_wgrad256 = value;
@@ -1057,6 +1415,8 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "skinny8")) lo::g_opt_skinny8 = value;
   else if (!strcmp(name, "fuse_lstm")) lo::g_opt_fuse_lstm = value;
   else if (!strcmp(name, "dec_fuse")) lo::g_opt_dec_fuse = value;
+  else if (!strcmp(name, "dec_cl")) lo::g_opt_dec_cl = value;
+  else if (!strcmp(name, "dec_cl_bwd")) lo::g_opt_dec_cl_bwd = value;
   else if (!strcmp(name, "dec_fuse_bwd")) lo::g_opt_dec_fuse_bwd = value;
   else if (!strcmp(name, "skinny_mma")) lo::g_opt_skinny_mma = value;
   else if (!strcmp(name, "l2_persist_mb")) {

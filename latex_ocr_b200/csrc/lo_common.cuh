@@ -221,6 +221,7 @@ struct AttBwdArgs {
 };
 extern int g_opt_att_pipe;
 extern int g_opt_att_maskbits;
+extern int g_opt_dbg_skip;
 extern int g_opt_conv_mc;
 extern int g_opt_conv_persist;
 extern int g_opt_wgrad256;
@@ -277,6 +278,14 @@ struct DecStepBwd {
 int dec_step_bwd(const DecStepBwd& p, cudaStream_t st);
 extern int g_opt_dec_fuse_bwd;
 extern int g_opt_dec_fuse;
+// cluster-fused step kernels (lo_cluster.cu): the same DecStepFwd / DecStepBwd contracts, rows split into blocks of 16 (one 16-CTA cluster
+// each), no grid barrier (bar / bar_target unused), dxh written instead of accumulated
+extern int g_opt_dec_cl, g_opt_dec_cl_bwd;
+bool dec_cl_fwd_ok(int D, int C, int N2);
+bool dec_cl_bwd_ok(int D, int C, int A);
+int dec_cl_fwd(const DecStepFwd& p, cudaStream_t st);
+int dec_cl_bwd(const DecStepBwd& p, cudaStream_t st);
+int cl_set_ts(long long* p);      // timing build only
 int tc_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st);
 extern int g_opt_fuse_lstm;
 extern int g_opt_skinny_mma;

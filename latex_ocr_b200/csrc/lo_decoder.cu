@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(LO_ATT_THREADS) attention_bwd_kernel(
 //   dwf[a]      += sum_{b,r,t} de[b,t,r] * relu(att1[b,r,a] + att2[t,b,a])
 // grid (A/64, ceil(R/32), B), 128 threads, thread tile 4(r) x 4(a), time chunks of 32 staged in smem.
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool WACC, int ACT = 0>
+// WACC: 0 = d att1 only; 1 = also all of d w_full; 2 = only the `x * (sum_t on * de)` term of d w_full (ReLU): the other term,
+// sum_{t,b} att2_t[b,a] * sum_r on * de_t[b,r], was accumulated per step by the mask-bit attention backward kernels (dwf_part)
+template <typename T, int WACC, int ACT = 0>
 __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, const float* __restrict__ out1,
                                                      int64_t o1_row, int64_t o1_step, const float* __restrict__ de,
                                                      const float* __restrict__ wf, T* __restrict__ datt1,
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(128) datt1_kernel(const T* __restrict__ att1, 
       const float4 q = *reinterpret_cast<const float4*>(&s_a2[tt][tx * 4]);
       const float4 d4 = *reinterpret_cast<const float4*>(&s_de[tt][ty * 4]);
       const float a2v[4] = {q.x, q.y, q.z, q.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-      if constexpr (ACT == 0 && WACC) {
+      if constexpr (ACT == 0 && WACC == 1) {
         // d w_full[a] = sum de * relu(x + a2) = sum_i x[i][a] * (sum_t on * de) + sum_t a2_t[a] * (sum_i on * de): the first term is
         // x * acc at the very end (x does not depend on t), the second needs only the per-step column sums s[j]
         float sc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -891,7 +893,7 @@ static int* work_counters(const lo_decoder_args* a) { return (int*)a->work; }
 // ReLU mask bits of step t, first row r0 (NULL when the scheme is off)
 static inline uint8_t* att_mask_at(const lo_decoder_args* a, int t, int64_t r0) {
   if (!a->att_mask || !g_opt_att_maskbits || !g_opt_att_pipe || a->rows_per_img > 1) return nullptr;
-  return a->att_mask + ((int64_t)t * a->B + r0) * a->R * (a->A / 8);
+  return a->att_mask + ((int64_t)t * a->B + r0) * ((a->R + 1) & ~1) * (a->A / 8);      // rows padded to an even count (pair layout)
 }
 static float* work_partials(const lo_decoder_args* a) { return (float*)((char*)a->work + 4096); }
 static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a->work + 2048); }
@@ -1007,7 +1009,7 @@ static int forward_prologue(const lo_decoder_args* a, const Dims& d, cudaStream_
   const BfViews bv = bf_views(a, d);
   if (bv.on) {
     LO_TRY(lo_cast(a->hall, LO_F32, bv.hall, LO_BF16, (int64_t)d.B * d.D, (void*)st));
-    if ((g_opt_fuse_lstm || g_opt_dec_fuse) && d.E % 8 == 0 && d.C % 8 == 0) {
+    if ((g_opt_fuse_lstm || g_opt_dec_fuse || g_opt_dec_cl) && d.E % 8 == 0 && d.C % 8 == 0) {
       interleave_wih_kernel<<<148 * 2, 256, 0, st>>>((const bf16*)a->w_ih, bv.wil, d.D, d.E, d.C);
       LO_LAUNCH_OK();
     }
@@ -1024,6 +1026,9 @@ struct Rows {
   int nsplit;       // attention split hint (0 = automatic)
 };
 int g_opt_dec_streams = 1;
+// timing dissection only (tools/dec_breakdown.py; results are garbage): 1 = skip the hoisted part of the backward, 2 = skip the
+// attention launches of the time loops, 4 = skip the per-step GEMM / LSTM launches, 8 = skip the hoisted part of the forward
+int g_opt_dbg_skip = 0;
 
 // one decoder step t for the rows of `rs`; tok: token ids consumed at this step (row 0 of the batch)
 static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Rows& rs, const int64_t* tok, int64_t tok_stride,
@@ -1042,7 +1047,8 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
   const char* enc = (const char*)a->enc + (size_t)(r0 / rpi) * d.R * d.C * es;
   // [att2 | gate_pre | hh_pre] = h_prev @ [W_d; W_beta; W_hh]^T + b   (seq2seq_torch.py:187, :311, LSTMCell hh part)
   const BfViews bv = bf_views(a, d);
-  if (bv.on && g_opt_skinny_mma && nrows <= 64) {
+  if (g_opt_dbg_skip & 4) {
+  } else if (bv.on && g_opt_skinny_mma && nrows <= 64) {
     LO_TRY(skinny_gemm_nt(bv.hall + ((int64_t)t * d.B + r0) * d.D, d.D, (const bf16*)a->wcat1, d.D, o1, d.O1, nrows, d.O1, d.D, a->bcat1, 1,
                           0, st));
   } else if (bv.on) {
@@ -1051,10 +1057,12 @@ static int forward_step(const lo_decoder_args* a, const Dims& d, int t, const Ro
   } else {
     LO_TRY(gemm_nt(h_prev, LO_F32, d.D, a->wcat1, dt, d.D, o1, LO_F32, d.O1, nrows, d.O1, d.D, a->bcat1, 0, 0, LO_IMPL_SIMT, st));
   }
+  if (!(g_opt_dbg_skip & 2))
   LO_TRY(attention_forward_launch(att1, enc, dt, o1, d.O1, a->w_full, a->alphas + (r0 * d.T + t) * d.R, (int64_t)d.T * d.R,
                                   a->ctx + ((int64_t)t * d.B + r0) * d.C, o1 + d.A, d.O1, a->gctx + ((int64_t)t * d.B + r0) * d.C,
                                   bv.on ? bv.gctx + ((int64_t)t * d.B + r0) * d.C : nullptr, nrows, d.R, d.C, rs.work, st,
                                   a->rows_per_img, rs.nsplit, hd_t ? att_mask_at(a, t, r0) : nullptr));
+  if (g_opt_dbg_skip & 4) return LO_OK;
   // gates_x = (gate*ctx) @ W_ih[:, E:]^T
   if (bv.on && g_opt_fuse_lstm) {
     // ... with the LSTM cell fused into the GEMM epilogue (no gates_x round trip, one launch less per step)
@@ -1196,7 +1204,34 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
   const BfViews bvs = bf_views(a, d);
   const bool fused = bvs.on && g_opt_dec_fuse && g_opt_skinny_mma && !g_opt_fuse_lstm && g_opt_att_pipe && nchains == 1 && d.B <= 64 &&
                      d.C == d.D && d.D <= 512 && d.D % 16 == 0 && d.O1 % 16 == 0 && d.E % 8 == 0 && a->rows_per_img <= 1;
-  if (fused) {
+  const bool clf = bvs.on && !fused && !(g_opt_dbg_skip & 4) && g_opt_skinny_mma && !g_opt_fuse_lstm && g_opt_att_pipe && nchains == 1 && d.E % 8 == 0 &&
+                   a->rows_per_img <= 1 && dec_cl_fwd_ok(d.D, d.C, d.O1);
+  if (clf) {
+    // two launches per step: attention(t) -> dec_cl_fwd(t) = [gates GEMM + LSTM cell | cluster all-gather | projection of h_{t+1}],
+    // one 16-CTA cluster per block of 16 batch rows (lo_cluster.cu)
+    LO_TRY(skinny_gemm_nt(bvs.hall, d.D, (const bf16*)a->wcat1, d.D, a->out1, d.O1, a->bt_host[0], d.O1, d.D, a->bcat1, 1, 0, st));
+    for (int t = 0; t < d.T; t++) {
+      const int nrows = a->bt_host[t];
+      float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+      if (!(g_opt_dbg_skip & 2))
+      LO_TRY(attention_forward_launch(a->att1, a->enc, a->dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+                                      a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C,
+                                      bvs.gctx + (int64_t)t * d.B * d.C, nrows, d.R, d.C, a->work, st, 1, 0, att_mask_at(a, t, 0)));
+      DecStepFwd p{};
+      p.gctx = bvs.gctx + (int64_t)t * d.B * d.C; p.ld_gctx = d.C;
+      p.wil = bvs.wil; p.ld_wil = d.C;
+      const float* dm = (a->has_dropout == 1 && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+      p.e = TcLstmEpi{a->ptab, a->caps + t, a->caps_stride, o1 + d.A + d.C, d.O1, a->call + (int64_t)t * d.B * d.D,
+                      a->gates + (int64_t)t * d.B * d.G, a->call + (int64_t)(t + 1) * d.B * d.D, a->hall + (int64_t)(t + 1) * d.B * d.D,
+                      bvs.hall + (int64_t)(t + 1) * d.B * d.D, a->hd + (int64_t)t * d.D, (int64_t)d.T * d.D, dm, d.D, d.V,
+                      (const unsigned long long*)(a->has_dropout == 2 ? a->dropout_state : nullptr), a->dropout_p, 0, t};
+      p.wcat = (const bf16*)a->wcat1; p.ld_wcat = d.D; p.bcat = a->bcat1;
+      p.o1_next = t + 1 < d.T ? a->out1 + (int64_t)(t + 1) * d.B * d.O1 : nullptr;
+      p.ld_o1 = d.O1; p.N2 = d.O1;
+      p.M = nrows; p.K = d.C;
+      LO_TRY(dec_cl_fwd(p, st));
+    }
+  } else if (fused) {
     // two launches per step: attention(t) -> dec_step_fwd(t) = [gates GEMM + LSTM cell | grid barrier | projection of h_{t+1}]
     unsigned int* bar = (unsigned int*)((char*)a->work + lo_attention_workspace_bytes(d.B, d.C));      // chain-1 region is unused here
     LO_CUDA(cudaMemsetAsync(bar, 0, 4, st));
@@ -1240,6 +1275,7 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
   }
   }   // phase != 2
   if (a->phase == 1) return LO_OK;       // extension: the caller runs a second layer over hd before the head
+  if (g_opt_dbg_skip & 8) return LO_OK;
   // predictions = fc(dropout(h))  (seq2seq_torch.py:316), hoisted out of the loop
   const BfViews bvf = bf_views(a, d);
   const bool fc_tc = bvf.on && d.Vl % 64 == 0 && d.D % 64 == 0;
@@ -1345,7 +1381,48 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
   const cudaStream_t st_main = st;
   const bool fusedb = bv.on && g_opt_dec_fuse_bwd && g_opt_skinny_mma && g_opt_att_pipe && nchains == 1 && d.B <= 64 && d.C == d.D &&
                       (d.A + d.C) % 512 == 0 && d.G % 512 == 0 && ((d.C + d.D) / 16) * (d.G / 512) <= 296 && a->rows_per_img <= 1;
-  if (fusedb) {
+  const bool clb = bv.on && !fusedb && !(g_opt_dbg_skip & 4) && g_opt_skinny_mma && g_opt_att_pipe && nchains == 1 && a->rows_per_img <= 1 &&
+                   dec_cl_bwd_ok(d.D, d.C, d.A);
+  if (clb) {
+    // two launches per step: attention_bwd(t) -> dec_cl_bwd = [dh_t += (datt2|dgate)_t W | LSTM bwd (t-1) | cluster all-gather | dG_{t-1} W]
+    auto fill_bc = [&](DecStepBwd& p, int t) {       // LSTM backward + dG projection of step t
+      p.dhd = a->dhd + (int64_t)t * d.D; p.dhd_stride = (int64_t)d.T * d.D;
+      p.dmask = (a->has_dropout == 1 && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D : nullptr;
+      p.dstate = (const unsigned long long*)(a->has_dropout == 2 ? a->dropout_state : nullptr);
+      p.dp = a->dropout_p; p.t_idx = t;
+      p.dc = a->dc; p.gates = a->gates + (int64_t)t * d.B * d.G;
+      p.c_prev = a->call + (int64_t)t * d.B * d.D; p.c_cur = a->call + (int64_t)(t + 1) * d.B * d.D;
+      p.dG = a->dcat + (int64_t)t * d.B * d.O1 + d.A + d.C; p.dG_bf = bv.dcat + (int64_t)t * d.B * d.O1 + d.A + d.C; p.dG_stride = d.O1;
+      p.Mb = a->bt_host[t];
+    };
+    auto fill_common = [&](DecStepBwd& p) {
+      p.wbwd1 = (const bf16*)a->wbwd1; p.ld_w1 = d.G; p.K1 = d.G;
+      p.wbwd2 = (const bf16*)a->wbwd2; p.ld_w2 = d.A + d.C; p.K2 = d.A + d.C;
+      p.dxh = a->dxh; p.C = d.C; p.D = d.D; p.ld_dcat = d.O1;
+    };
+    {
+      DecStepBwd p{};
+      fill_common(p);
+      fill_bc(p, d.T - 1);
+      LO_TRY(dec_cl_bwd(p, st));
+    }
+    for (int t = d.T - 1; t >= 0; t--) {
+      const int nrows = a->bt_host[t];
+      float* dcat_t = a->dcat + (int64_t)t * d.B * d.O1;
+      bf16* dcat_bf_t = bv.dcat + (int64_t)t * d.B * d.O1;
+      const float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+      AttBwdArgs x{a->att1, a->enc, o1, o1 + d.A, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
+                   a->ctx + (int64_t)t * d.B * d.C, a->dxh, d.C + d.D, dal + (int64_t)t * dal_t, dal_b, a->sreg + t, d.T,
+                   a->de + (int64_t)t * d.R, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t + d.A, a->dctx + (int64_t)t * d.B * d.C,
+                   nrows, d.R, a->work, a->dmean, 0, 0, 0, att_mask_at(a, t, 0)};
+      if (!(g_opt_dbg_skip & 2)) LO_TRY(attention_bwd_pipe(x, dt, d.C, st));
+      DecStepBwd p{};
+      fill_common(p);
+      p.dcat_a = dcat_bf_t; p.Ma = nrows;
+      if (t > 0) fill_bc(p, t - 1);
+      LO_TRY(dec_cl_bwd(p, st));
+    }
+  } else if (fusedb) {
     // two launches per step: attention_bwd(t) -> dec_step_bwd = [dh += (datt2|dgate) W | barrier | LSTM bwd (t-1) | barrier | dG W]
     unsigned int* bar = (unsigned int*)((char*)a->work + lo_attention_workspace_bytes(d.B, d.C)) + 16;   // chain-1 region, unused here
     LO_CUDA(cudaMemsetAsync(bar, 0, 4, st));
@@ -1404,6 +1481,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     const float* o1 = a->out1 + ((int64_t)t * d.B + r0) * d.O1;
     float* dxh = a->dxh + r0 * (d.C + d.D);
     const float* dmul = (a->has_dropout == 1 && a->dropout_mask) ? a->dropout_mask + (int64_t)t * d.D + r0 * d.T * d.D : nullptr;
+    if (!(g_opt_dbg_skip & 4))
     LO_CUDA(launch_pdl(lstm_pw_bwd_kernel, dim3(cdiv((long)nrows * d.D, 256)), dim3(256), (size_t)0, st,
                        (const float*)(a->dhd + (int64_t)t * d.D + r0 * d.T * d.D), (int64_t)d.T * d.D, dmul, (const float*)(dxh + d.C),
                        (int64_t)(d.C + d.D), a->dc + r0 * d.D, (const float*)(a->gates + ((int64_t)t * d.B + r0) * d.G),
@@ -1413,7 +1491,8 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
                        (const unsigned long long*)(a->has_dropout == 2 ? a->dropout_state : nullptr), a->dropout_p, (int)r0, t));
     LO_LAUNCH_OK();
     // [dgctx | dh_prev] = dG @ [W_ih[:, E:] | W_hh]
-    if (bv.on && g_opt_skinny_mma && nrows <= 64) {
+    if (g_opt_dbg_skip & 4) {
+    } else if (bv.on && g_opt_skinny_mma && nrows <= 64) {
       LO_TRY(skinny_gemm_nt(dcat_bf_t + d.A + d.C, d.O1, (const bf16*)a->wbwd1, d.G, dxh, d.C + d.D, nrows, d.C + d.D, d.G, nullptr, 4, 1,
                             st));
     } else if (bv.on) {
@@ -1431,7 +1510,8 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     const float* sreg_t = a->sreg + r0 * d.T + t;
     float* de_t = a->de + (r0 * d.T + t) * d.R;
     float* dctx_t = a->dctx + ((int64_t)t * d.B + r0) * d.C;
-    if (g_opt_att_pipe) {
+    if (g_opt_dbg_skip & 2) {
+    } else if (g_opt_att_pipe) {
       AttBwdArgs x{att1, enc, o1, o1 + d.A, d.O1, a->w_full, alpha_t, (int64_t)d.T * d.R, ctx_t, dxh, d.C + d.D, dal_t_ptr, dal_b, sreg_t,
                    d.T, de_t, dcat_t, dcat_t + d.A, d.O1, dcat_bf_t, dcat_bf_t ? dcat_bf_t + d.A : nullptr, dctx_t, nrows, d.R, rs.work,
                    a->dmean + r0 * d.A, rs.nsplit, 0, 0, att_mask_at(a, t, r0)};
@@ -1454,7 +1534,8 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     LO_LAUNCH_OK();
     }
     // dh_prev += [datt2 | dgate_pre] @ [W_d ; W_beta]
-    if (bv.on && g_opt_skinny_mma && nrows <= 64) {
+    if (g_opt_dbg_skip & 4) {
+    } else if (bv.on && g_opt_skinny_mma && nrows <= 64) {
       LO_TRY(skinny_gemm_nt(dcat_bf_t, d.O1, (const bf16*)a->wbwd2, d.A + d.C, dxh + d.C, d.C + d.D, nrows, d.D, d.A + d.C, nullptr, 4, 1,
                             st));
     } else if (bv.on) {
@@ -1476,6 +1557,7 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
                             cudaMemcpyDeviceToDevice, st));
   LO_CUDA(cudaMemcpy2DAsync(a->dinit + d.D, (size_t)2 * d.D * 4, a->dc, (size_t)d.D * 4, (size_t)d.D * 4, d.B,
                             cudaMemcpyDeviceToDevice, st));
+  if (g_opt_dbg_skip & 1) return LO_OK;
   // ---- hoisted gradients
   const bool tc = bv.on;
   bf16* dcat_bf = bv.dcat;
@@ -1532,11 +1614,16 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     if (g_opt_att_pipe && !att_mask_at(a, 0, 0)) {
       // d w_full was accumulated per batch row by the attention backward kernels (dmean doubles as the [B][A] scratch)
       LO_TRY(colsum(a->dmean, LO_F32, a->g_w_full, d.B, d.A, d.A, 0, st));
-      LO_DISPATCH_DT(dt, T, (datt1_kernel<T, false><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,
-                                                                           a->w_full, (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
+      LO_DISPATCH_DT(dt, T, (datt1_kernel<T, 0><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,
+                                                                       a->w_full, (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
+    } else if (g_opt_att_pipe) {
+      // mask-bit scheme: the att2 term of d w_full came out of the per-step kernels (dmean scratch), the sweep adds the x term
+      LO_TRY(colsum(a->dmean, LO_F32, a->g_w_full, d.B, d.A, d.A, 0, st));
+      LO_DISPATCH_DT(dt, T, (datt1_kernel<T, 2><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,
+                                                                       a->w_full, (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
     } else {
-      LO_DISPATCH_DT(dt, T, (datt1_kernel<T, true><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,
-                                                                          a->w_full, (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
+      LO_DISPATCH_DT(dt, T, (datt1_kernel<T, 1><<<grid, 128, 0, st>>>((const T*)a->att1, a->out1, d.O1, (int64_t)d.B * d.O1, a->de,
+                                                                       a->w_full, (T*)a->datt1, a->g_w_full, d.T, d.R, d.A)));
     }
     LO_LAUNCH_OK();
   }

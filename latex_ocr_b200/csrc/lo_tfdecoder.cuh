@@ -529,7 +529,7 @@ int lo_tfdec_backward(const lo_tfdec_args* a, void* stream) {
   // d att_img[b,r,a] = beta[a] sum_t de[b,t,r] (1 - tanh^2(att_img + att_h_t))   (one sweep over t)
   {
     dim3 grid(d.A / 64, cdiv(d.R, 32), d.B);
-    LO_DISPATCH_DT(dt, T, (datt1_kernel<T, false, 1><<<grid, 128, 0, st>>>((const T*)w.att_img, w.out2, d.N2, (int64_t)d.B * d.N2, w.de, a->beta,
+    LO_DISPATCH_DT(dt, T, (datt1_kernel<T, 0, 1><<<grid, 128, 0, st>>>((const T*)w.att_img, w.out2, d.N2, (int64_t)d.B * d.N2, w.de, a->beta,
                                                                             (T*)w.datt_img, nullptr, d.T, d.R, d.A)));
     LO_LAUNCH_OK();
   }

@@ -231,7 +231,7 @@ class DecoderWithAttention(nn.Module):
             t["dinit"] = z(B, 2 * D)
             t["dmean"] = z(B, max(A, C))
             # ReLU mask bits of every step (forward attention kernel -> backward attention kernel), 1 bit per att1 element
-            t["att_mask"] = torch.empty(T, B, R, A // 8, dtype=torch.uint8, device=dev)
+            t["att_mask"] = torch.empty(T, B, (R + 1) // 2 * 2, A // 8, dtype=torch.uint8, device=dev)      # rows padded to an even count
             ws["need_grad"] = True
         return ws
 

@@ -133,10 +133,15 @@ def test_tc_conv3x3_wgrad(N, H, W, Cin, Cout, pad):
     assert relerr(db, dy.double().sum(dim=(0, 2, 3)).float()) < 1e-5
 
 
-@pytest.mark.parametrize("opt", ["fuse_lstm", "dec_streams", "skinny_mma", "dec_fuse", "dec_fuse_bwd", "att_maskbits", "conv_persist", "wgrad256", "conv_mt2"])
+_SCHEDULE_OPTS = {"fuse_lstm": (0, 1), "dec_streams": (1, 2), "skinny_mma": (1, 0), "dec_fuse": (0, 1), "dec_fuse_bwd": (0, 1), "att_maskbits": (1, 0),
+                  "conv_persist": (1, 0), "wgrad256": (0, 1), "conv_mt2": (1, 0), "dec_cl": (0, 1), "dec_cl_bwd": (0, 1), "att_bwd_mma": (1, 0)}
+
+
+@pytest.mark.parametrize("opt", sorted(_SCHEDULE_OPTS))
 def test_optional_decoder_schedules_match_default(opt):
-    """The LSTM-cell-in-GEMM-epilogue variant and the two-chain (two stream) time loop are kept as run-time options
-    (both measured no faster); they must give the default schedule's numbers."""
+    """Every optional schedule (first value = default) must give the default schedule's numbers: the measured-no-faster variants kept
+    as run-time options and, the other way round, the separate-launch time loop and the CUDA-core attention backward
+    that the cluster-fused step kernels / the tensor-core backward replaced."""
     from util import build_model, load_golden
     from latex_ocr_b200 import _lib
     from oracle import ref_model as rm
@@ -147,22 +152,15 @@ def test_optional_decoder_schedules_match_default(opt):
     B, T = formula.shape[0], formula.shape[1] - 1
     res = {}
     try:
-        for val in {"fuse_lstm": (0, 1), "dec_streams": (1, 2), "skinny_mma": (1, 0), "dec_fuse": (0, 1), "dec_fuse_bwd": (0, 1), "att_maskbits": (1, 0), "conv_persist": (1, 0), "wgrad256": (0, 1), "conv_mt2": (1, 0)}[opt]:
+        for val in _SCHEDULE_OPTS[opt]:
             _lib.set_option(opt, val)
             m = build_model(V, pe, pd, "bf16", impl="tc")
             loss = m._step_body(img.cuda(), formula.cuda(), [T] * B, None)
             torch.cuda.synchronize()
             res[val] = (loss[0].item(), m.decoder.store.grad.clone())
     finally:
-        _lib.set_option("fuse_lstm", 0)
-        _lib.set_option("dec_streams", 1)
-        _lib.set_option("skinny_mma", 1)
-        _lib.set_option("dec_fuse", 0)
-        _lib.set_option("dec_fuse_bwd", 0)
-        _lib.set_option("att_maskbits", 1)
-        _lib.set_option("conv_persist", 1)
-        _lib.set_option("wgrad256", 0)
-        _lib.set_option("conv_mt2", 1)
+        for name, (default, _) in _SCHEDULE_OPTS.items():
+            _lib.set_option(name, default)
     (l0, g0), (l1, g1) = res.values()
     assert abs(l0 - l1) / abs(l0) < 1e-4
     assert (g0 - g1).norm().item() / g0.norm().item() < 2e-2

@@ -1,0 +1,59 @@
+"""Per-CTA timeline of the cluster-fused decoder step kernels (timing build: LO_LIB_DIR=_C_timing, -DLO_ATT_TIMING).  The stamps of the
+LAST launch of a decoder forward / backward pass (time loops only, attention switched off or on) are reported.
+Stamps: 0 entry, 1 ring prefill + operand loads issued, 2 past griddepcontrol.wait, 3 A operand landed, 4 phase boundary reached,
+9 cell done, 5 past the cluster barrier, 6 all-gather done, 7 main loop done, 8 exit."""
+import ctypes, os, sys
+os.environ.setdefault("LO_LIB_DIR", "_C_timing")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import bench_support as bs
+from latex_ocr_b200 import _lib
+from latex_ocr_b200.img2seq import Img2SeqModel
+from latex_ocr_b200.data import SimpleVocab
+
+B, T = 64, 150
+class Cfg:
+    encoder_cnn = "vanilla"; positional_embeddings = True; lr_init = 1e-3; lr_method = "adam"; cuda_graph = False
+m = Img2SeqModel(Cfg(), vocab=SimpleVocab(500), device="cuda:0", precision="bf16", impl="tc")
+m.build_train(); m.train_mode(True)
+img, formula = bs.synthetic_batch(B, 128, 512, 500, T, seed=1234)
+img, formula = img.cuda(), formula.cuda()
+for _ in range(2):
+    m.train_step(img, formula)
+torch.cuda.synchronize()
+L = _lib.lib()
+dec = m.decoder
+key = [k for k in dec._ws if k[0] == B and k[1] == T][0]
+a = dec._ws[key]["args"]
+buf = torch.zeros(1024 * 16, dtype=torch.int64, device="cuda")
+
+
+def report(name, n=64):
+    x = buf.cpu().numpy().reshape(-1, 16)[:n].astype(np.float64)
+    t0 = x[:, 0].min()
+    print("== %s (us after the first CTA's entry; min / median / max over %d CTAs)" % (name, n))
+    for k, lab in ((0, "entry"), (1, "ring prefill issued"), (2, "past griddepcontrol.wait"), (3, "A operand landed"), (4, "phase boundary"),
+                   (9, "cell done"), (5, "past cluster barrier"), (6, "all-gather done"), (7, "main loop done"), (8, "exit")):
+        v = (x[:, k] - t0) / 1e3
+        print("  %-28s %7.2f / %7.2f / %7.2f" % (lab, v.min(), np.median(v), v.max()))
+    sys.stdout.flush()
+
+
+for mask, lab in ((9 | 2, "smalls only"), (9, "with attention")):
+    _lib.set_option("dbg_skip", mask)
+    for fn, nm in ((L.lo_decoder_forward, "forward"), (L.lo_decoder_backward, "backward")):
+        for rep in range(2):
+            buf.zero_()
+            _lib.check(L.lo_debug_buffer(_lib.ptr(buf)))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if fn is L.lo_decoder_forward:
+                _lib.check(fn(ctypes.byref(a), 1, _lib.stream_ptr()))
+            else:
+                _lib.check(fn(ctypes.byref(a), _lib.stream_ptr()))
+            e1.record(); torch.cuda.synchronize()
+        print("%s loop, %s: %.2f us per step (eager launches)" % (nm, lab, e0.elapsed_time(e1) / T * 1e3))
+        report("%s, %s: last launch of the loop" % (nm, lab))
+_lib.set_option("dbg_skip", 0)
+_lib.check(L.lo_debug_buffer(None))
