@@ -127,9 +127,11 @@ def kernel_probes(model, c, pk):
     # algorithmic bytes of the backward: enc read once + 1 mask bit per att1 element (or att1 itself without the mask scheme)
     # + alpha read and d e written
     attb_bytes = (B * R * C * bpe + B * R * A // 8 + 2 * B * R * 4) if maskbits else att_bytes
-    kname = "attention_bwd_mask_kernel" if maskbits else "attention_bwd_pipe_kernel"
+    mma = maskbits and bool(_lib.lib().lo_get_option(b"att_bwd_mma")) and bpe == 2
+    kname = ("attention_bwd_mma_kernel" if mma else "attention_bwd_mask_kernel") if maskbits else "attention_bwd_pipe_kernel"
     attb = {"kernel": kname + " (d alpha, softmax backward, ReLU-mask sums, one decode step, TMA ring"
-                      + ("; streams enc + the forward's mask bits instead of enc + att1)" if maskbits else ")"), "bound": "hbm",
+                      + ("; streams enc + the forward's mask bits instead of enc + att1" if maskbits else "")
+                      + ("; both contractions on mma.sync)" if mma else ")"), "bound": "hbm",
             "achieved": attb_bytes / (ms_attb * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
             "traffic": traffic_of(kname), "us_per_launch": ms_attb * 1e3, "algorithmic_bytes": attb_bytes,
             "peak_source": pk["src"]}

@@ -986,20 +986,19 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_bwd_mma_kernel(
       }
     }
     const float sreg_b = sreg ? sreg[(int64_t)b * sreg_stride] : 0.f;
-    // alpha and the regulariser gradient are forward-pass results: the first stage's values are fetched before the wait as well
+    // alpha and the regulariser gradient of this CTA's rows are forward-pass results: ALL of them are staged in shared memory before
+    // the wait.  (Fetching them stage by stage with a one-stage lookahead made every 16-row stage cost one L2 round trip, ~0.8 us: the
+    // main loop then ran at 3.5 TB/s whatever the arithmetic was — run 62 timeline.)
     const float* alb = alpha + (int64_t)b * alpha_stride;
     float* deb = de + (int64_t)b * alpha_stride;
     const float* drb = dreg + (int64_t)b * dreg_stride;
     const int rr = lane & 15;
-    float pa = 0.f, pd = 0.f;
-    auto prefetch = [&](int i) {
-      const int r = r0 + i * ABM_ROWS + rr;
-      if (i < nst && r < r1) {
-        pa = alb[r];
-        pd = dreg ? drb[r] : 0.f;
-      }
-    };
-    prefetch(0);
+    float* s_al = s_pd + 2 * AP_CWARPS * ABM_ROWS;      // [rps] alpha | [rps] d reg
+    float* s_dr = s_al + rps;
+    for (int r = threadIdx.x; r < r1 - r0; r += AP_CWARPS * 32) {
+      s_al[r] = alb[r0 + r];
+      s_dr[r] = dreg ? drb[r0 + r] : 0.f;
+    }
     pdl_wait();
     ATT_TS(1, threadIdx.x == 0);
     pdl_trigger();
@@ -1038,13 +1037,13 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_bwd_mma_kernel(
     const uint32_t ring = smem_u32(ap_smem);
     const uint32_t a_off = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * ABM_PITCH + (uint32_t)(64 * wid + (lane >> 4) * 8) * 2u;
     const uint32_t m_off = ABM_ENC_BYTES + (uint32_t)q * 2u * MB + (uint32_t)(8 * wid + g) * 2u;
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // s_al / s_dr complete
     for (int i = 0; i < nst; i++) {
       const int s = i % ABM_STAGES;
       const uint32_t ph = (i / ABM_STAGES) & 1;
       const int row = r0 + i * ABM_ROWS;
       const int rows = min(ABM_ROWS, r1 - row);
-      const float al = pa, dr = pd;
-      prefetch(i + 1);
+      const float al = rr < rows ? s_al[i * ABM_ROWS + rr] : 0.f, dr = rr < rows ? s_dr[i * ABM_ROWS + rr] : 0.f;
       mbar_wait(full_bar + s, ph);
       ATT_TS(3, threadIdx.x == 0 && i == 0);
       const uint32_t sb = ring + (uint32_t)s * ABM_STAGE_BYTES;
@@ -1262,21 +1261,23 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
     attr = true;
   }
   const int ns = att_pipe_splits(x.B, x.nsplit_hint);
-  if constexpr (ACT == 0 && sizeof(T) == 2 && NVA == 2 && NVC == 2) if (x.mask_in && g_opt_att_bwd_mma) {
+  if constexpr (ACT == 0 && sizeof(T) == 2 && NVA == 2 && NVC == 2)
+  if (x.mask_in && g_opt_att_bwd_mma && att_rows_per_split(x.R, ns) <= 2048) {
     static bool attr_t = false;
     if (!attr_t) {
-      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
-      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
+      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM + 2048 * 8));
+      LO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM + 2048 * 8));
       attr_t = true;
     }
 #define LO_BWDT_ARGS                                                                                                                  \
   x.mask_in, (const bf16*)x.enc, x.gate, x.o1_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.dgctx, x.dg_stride, x.dreg,            \
       x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,           \
       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, x.att2, x.dwf_part
+    const size_t smem_t = (size_t)ABM_SMEM + (size_t)att_rows_per_split(x.R, ns) * 8;      // + alpha / d reg of the CTA's rows
     if (use_cluster(ns, x.R)) {
-      LO_CUDA(launch_att(attention_bwd_mma_kernel<true>, dim3(ns, x.B), (size_t)ABM_SMEM, ns, st, LO_BWDT_ARGS));
+      LO_CUDA(launch_att(attention_bwd_mma_kernel<true>, dim3(ns, x.B), smem_t, ns, st, LO_BWDT_ARGS));
     } else {
-      LO_CUDA(launch_att(attention_bwd_mma_kernel<false>, dim3(ns, x.B), (size_t)ABM_SMEM, 1, st, LO_BWDT_ARGS));
+      LO_CUDA(launch_att(attention_bwd_mma_kernel<false>, dim3(ns, x.B), smem_t, 1, st, LO_BWDT_ARGS));
     }
 #undef LO_BWDT_ARGS
     LO_LAUNCH_OK();
@@ -1341,6 +1342,7 @@ namespace lo { extern long long* g_tc_dbg; }
 extern "C" int lo_debug_buffer(void* p) {
   lo::g_tc_dbg = (long long*)p;
   LO_TRY(lo::cl_set_ts((long long*)p));
+  LO_TRY(lo::sk_set_ts((long long*)p));
 #ifdef LO_ATT_TIMING
   long long* q = (long long*)p;
   LO_CUDA(cudaMemcpyToSymbol(lo::g_att_ts, &q, sizeof(q)));
@@ -1392,6 +1394,7 @@ extern "C" int lo_get_option(const char* name) {
   if (!strcmp(name, "dec_fuse_bwd")) return lo::g_opt_dec_fuse_bwd;
   if (!strcmp(name, "fuse_lstm")) return lo::g_opt_fuse_lstm;
   if (!strcmp(name, "skinny_mma")) return lo::g_opt_skinny_mma;
+  if (!strcmp(name, "skinny_tma")) return lo::g_opt_skinny_tma;
   if (!strcmp(name, "dec_streams")) return lo::g_opt_dec_streams;
   return -1;
 }
@@ -1419,6 +1422,7 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "dec_cl_bwd")) lo::g_opt_dec_cl_bwd = value;
   else if (!strcmp(name, "dec_fuse_bwd")) lo::g_opt_dec_fuse_bwd = value;
   else if (!strcmp(name, "skinny_mma")) lo::g_opt_skinny_mma = value;
+  else if (!strcmp(name, "skinny_tma")) lo::g_opt_skinny_tma = value;
   else if (!strcmp(name, "l2_persist_mb")) {
     // size of the L2 set-aside that evict_last / persisting accesses may occupy (0 = driver default)
     cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)value << 20);

@@ -286,9 +286,11 @@ bool dec_cl_bwd_ok(int D, int C, int A);
 int dec_cl_fwd(const DecStepFwd& p, cudaStream_t st);
 int dec_cl_bwd(const DecStepBwd& p, cudaStream_t st);
 int cl_set_ts(long long* p);      // timing build only
+int sk_set_ts(long long* p);      // timing build only
 int tc_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st);
 extern int g_opt_fuse_lstm;
 extern int g_opt_skinny_mma;
+extern int g_opt_skinny_tma;
 int skinny_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw, int M, int D, int K, const TcLstmEpi& e, cudaStream_t st);
 int skinny_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                    int splits, int atomic_acc, cudaStream_t st);

@@ -411,35 +411,44 @@ __global__ void lstm_pw_fwd_kernel(const float* __restrict__ gtmp, const float* 
                                    float* __restrict__ c_out, float* __restrict__ h_out, bf16* __restrict__ h_bf,
                                    float* __restrict__ hd, int64_t hd_stride, const float* __restrict__ dmask, int nrows, int D,
                                    int V, const unsigned long long* __restrict__ dstate, float dp, int row0, int t_idx) {
+  // Everything but the gates GEMM result is at least two launches old (token -> table row, the recurrent projection of this step,
+  // c_t; the dropout draw depends on nothing): fetched / computed BEFORE griddepcontrol.wait, so only one L2 round trip (gtmp) is left
+  // on the critical path of the time loop instead of two dependent ones.
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = idx < nrows * D;
+  const int b = live ? idx / D : 0, j = live ? idx % D : 0;
+  float a4[4] = {0.f, 0.f, 0.f, 0.f}, cp = 0.f, mult = 1.f;
+  if (live) {
+    int64_t tk = tok[(int64_t)b * tok_stride];
+    if (tk < 0) tk = 0;
+    if (tk >= V) tk = V - 1;
+    const float* pt = ptab + tk * 4 * D;
+    const float* h0 = hh + (int64_t)b * hh_stride;
+#pragma unroll
+    for (int q = 0; q < 4; q++) a4[q] = pt[q * D + j] + h0[q * D + j];
+    cp = c_prev[(int64_t)b * D + j];
+    if (hd) {
+      if (dmask) mult = dmask[(int64_t)b * hd_stride + j];                                           // injected mask (parity tests)
+      else if (dstate) mult = philox_dropout_mult(dstate, row0 + b, t_idx, j, dp, 1.f / (1.f - dp));  // drawn here, redrawn in the backward
+    }
+  }
   pdl_wait();
   pdl_trigger();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nrows * D) return;
-  const int b = idx / D, j = idx % D;
-  int64_t tk = tok[(int64_t)b * tok_stride];
-  if (tk < 0) tk = 0;
-  if (tk >= V) tk = V - 1;
-  const float* pt = ptab + tk * 4 * D;
+  if (!live) return;
   const float* g0 = gtmp + (int64_t)b * 4 * D;
-  const float* h0 = hh + (int64_t)b * hh_stride;
-  const float pi = g0[j] + pt[j] + h0[j];
-  const float pf = g0[D + j] + pt[D + j] + h0[D + j];
-  const float pg = g0[2 * D + j] + pt[2 * D + j] + h0[2 * D + j];
-  const float po = g0[3 * D + j] + pt[3 * D + j] + h0[3 * D + j];
+  const float pi = g0[j] + a4[0];
+  const float pf = g0[D + j] + a4[1];
+  const float pg = g0[2 * D + j] + a4[2];
+  const float po = g0[3 * D + j] + a4[3];
   const float i = sigmoidf_(pi), f = sigmoidf_(pf), g = tanhf(pg), o = sigmoidf_(po);
-  const float c = f * c_prev[(int64_t)b * D + j] + i * g;
+  const float c = f * cp + i * g;
   const float h = o * tanhf(c);
   float* gt = gates + (int64_t)b * 4 * D;
   gt[j] = i; gt[D + j] = f; gt[2 * D + j] = g; gt[3 * D + j] = o;
   c_out[(int64_t)b * D + j] = c;
   h_out[(int64_t)b * D + j] = h;
   if (h_bf) h_bf[(int64_t)b * D + j] = __float2bfloat16_rn(h);
-  if (hd) {
-    float mult = 1.f;
-    if (dmask) mult = dmask[(int64_t)b * hd_stride + j];                                           // injected mask (parity tests)
-    else if (dstate) mult = philox_dropout_mult(dstate, row0 + b, t_idx, j, dp, 1.f / (1.f - dp));  // drawn here, redrawn in the backward
-    hd[(int64_t)b * hd_stride + j] = h * mult;
-  }
+  if (hd) hd[(int64_t)b * hd_stride + j] = h * mult;
 }
 
 // backward of the cell pointwise part: dh = dhd[b,t] + dh_next ; writes d(pre-activations), dc_prev in place
@@ -450,22 +459,30 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ dhd, int64_t dhd_st
                                    float* __restrict__ dG, int64_t dG_stride, bf16* __restrict__ dG_bf, float* __restrict__ dxh_zero,
                                    int C, int nrows, int D, const unsigned long long* __restrict__ dstate, float dp, int row0,
                                    int t_idx) {
+  // gates / cells come from the forward pass, dhd from the hoisted fc backward, dc from this kernel's previous launch (three launches
+  // back), the dropout draw depends on nothing: all fetched before griddepcontrol.wait; only dh_next (the GEMM just before) is after it
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = idx < nrows * D;
+  const int b = live ? idx / D : 0, j = live ? idx % D : 0;
+  float i = 0.f, f = 0.f, g = 0.f, o = 0.f, tc = 0.f, cpv = 0.f, dhv = 0.f, dcv = 0.f;
+  if (live) {
+    const float* gt = gates + (int64_t)b * 4 * D;
+    i = gt[j]; f = gt[D + j]; g = gt[2 * D + j]; o = gt[3 * D + j];
+    tc = tanhf(c_cur[(int64_t)b * D + j]);
+    cpv = c_prev[(int64_t)b * D + j];
+    dhv = dhd[(int64_t)b * dhd_stride + j];
+    if (dmask) dhv *= dmask[(int64_t)b * dhd_stride + j];
+    else if (dstate) dhv *= philox_dropout_mult(dstate, row0 + b, t_idx, j, dp, 1.f / (1.f - dp));
+    dcv = dc[(int64_t)b * D + j];
+  }
   pdl_wait();
   pdl_trigger();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nrows * D) return;
-  const int b = idx / D, j = idx % D;
-  const float* gt = gates + (int64_t)b * 4 * D;
-  const float i = gt[j], f = gt[D + j], g = gt[2 * D + j], o = gt[3 * D + j];
-  const float tc = tanhf(c_cur[(int64_t)b * D + j]);
-  float dh = dhd[(int64_t)b * dhd_stride + j];
-  if (dmask) dh *= dmask[(int64_t)b * dhd_stride + j];
-  else if (dstate) dh *= philox_dropout_mult(dstate, row0 + b, t_idx, j, dp, 1.f / (1.f - dp));
-  dh += dh_next[(int64_t)b * dhn_stride + j];
-  const float dct = dc[(int64_t)b * D + j] + dh * o * (1.f - tc * tc);
+  if (!live) return;
+  const float dh = dhv + dh_next[(int64_t)b * dhn_stride + j];
+  const float dct = dcv + dh * o * (1.f - tc * tc);
   float* d = dG + (int64_t)b * dG_stride;
   d[j] = dct * g * i * (1.f - i);
-  d[D + j] = dct * c_prev[(int64_t)b * D + j] * f * (1.f - f);
+  d[D + j] = dct * cpv * f * (1.f - f);
   d[2 * D + j] = dct * i * (1.f - g * g);
   d[3 * D + j] = dh * tc * o * (1.f - o);
   dc[(int64_t)b * D + j] = dct * f;
@@ -1234,13 +1251,14 @@ int lo_decoder_forward(const lo_decoder_args* a, int with_loss, void* stream) {
   } else if (fused) {
     // two launches per step: attention(t) -> dec_step_fwd(t) = [gates GEMM + LSTM cell | grid barrier | projection of h_{t+1}]
     unsigned int* bar = (unsigned int*)((char*)a->work + lo_attention_workspace_bytes(d.B, d.C));      // chain-1 region is unused here
-    LO_CUDA(cudaMemsetAsync(bar, 0, 4, st));
+    LO_CUDA(cudaMemsetAsync(bar, 0, 16 * 128, st));                                                    // 16 arrival counters, one cache line each
     const int grid = cdiv(d.O1, 16) > cdiv(d.G, 16) ? cdiv(d.O1, 16) : cdiv(d.G, 16);
     LO_TRY(skinny_gemm_nt(bvs.hall, d.D, (const bf16*)a->wcat1, d.D, a->out1, d.O1, a->bt_host[0], d.O1, d.D, a->bcat1, 1, 0, st));
     unsigned int epoch = 0;
     for (int t = 0; t < d.T; t++) {
       const int nrows = a->bt_host[t];
       float* o1 = a->out1 + (int64_t)t * d.B * d.O1;
+      if (!(g_opt_dbg_skip & 2))
       LO_TRY(attention_forward_launch(a->att1, a->enc, a->dt, o1, d.O1, a->w_full, a->alphas + (int64_t)t * d.R, (int64_t)d.T * d.R,
                                       a->ctx + (int64_t)t * d.B * d.C, o1 + d.A, d.O1, a->gctx + (int64_t)t * d.B * d.C,
                                       bvs.gctx + (int64_t)t * d.B * d.C, nrows, d.R, d.C, a->work, st, 1, 0, att_mask_at(a, t, 0)));
@@ -1424,8 +1442,8 @@ int lo_decoder_backward(const lo_decoder_args* a, void* stream) {
     }
   } else if (fusedb) {
     // two launches per step: attention_bwd(t) -> dec_step_bwd = [dh += (datt2|dgate) W | barrier | LSTM bwd (t-1) | barrier | dG W]
-    unsigned int* bar = (unsigned int*)((char*)a->work + lo_attention_workspace_bytes(d.B, d.C)) + 16;   // chain-1 region, unused here
-    LO_CUDA(cudaMemsetAsync(bar, 0, 4, st));
+    unsigned int* bar = (unsigned int*)((char*)a->work + lo_attention_workspace_bytes(d.B, d.C)) + 1024;   // chain-1 region, unused here
+    LO_CUDA(cudaMemsetAsync(bar, 0, 16 * 128, st));
     const unsigned int grid = (unsigned int)(((d.C + d.D) / 16) * (d.G / 512));
     unsigned int nb = 0;
     auto fill_bc = [&](DecStepBwd& p, int t) {       // phases B/C for step t

@@ -12,6 +12,7 @@
 namespace lo {
 
 int g_opt_skinny_mma = 1;
+int g_opt_skinny_tma = 1;       // operands of skinny_mma_kernel by cp.async.bulk (one copy per row) instead of 16-byte cp.async
 
 constexpr int SK_KC = 512;        // K elements per CTA
 constexpr int SK_NT = 16;         // output columns per CTA
@@ -34,6 +35,10 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
 }
 
 // grid (N/16, ksplit, row blocks of 64), 128 threads (warp w owns rows 16w..16w+15 of its row block)
+// TMA = true: both operands arrive as 1-D bulk copies (cp.async.bulk, one per row, issued by warp 0, completion on two mbarriers)
+// instead of 16-byte cp.async: the fused-step timeline (run 70) showed the post-wait 64 KB activation load taking ~3 us per CTA at
+// the ~30 GB/s an SM sustains with LDGSTS.
+template <bool TMA>
 __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ W, int64_t ldw,
                                                           float* __restrict__ C, int64_t ldc, int M, int N, int K, int kc,
                                                           const float* __restrict__ bias, int atomic) {
@@ -48,6 +53,40 @@ __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict_
   const int kn = min(kc, K - k0);                            // multiple of 16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cpr = kn / 8;                                    // 16-byte chunks per row
+  if constexpr (TMA) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sk_smem + SK_SMEM);      // [0] weights, [1] activations
+    if (tid == 0) {
+      mbar_init(bars, 1);
+      mbar_init(bars + 1, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    const uint32_t row_bytes = (uint32_t)kn * 2u;
+    if (warp == 0) {
+      // PDL: the weight slice never depends on the preceding launch -> fetched before griddepcontrol.wait
+      const int wrows = min(SK_NT, N - n0);
+      const uint64_t pol = l2_policy_evict_last();
+      if (lane == 0) mbar_expect_tx(bars, (uint32_t)wrows * row_bytes);
+      __syncwarp();
+      if (lane < wrows) bulk_g2s(sW + lane * SK_PITCH, W + (int64_t)(n0 + lane) * ldw + k0, row_bytes, bars, pol);
+    }
+    // rows the copies do not write are zero (cp.async zero-fill semantics of the other path)
+    for (int i = tid; i < (SK_NT - min(SK_NT, N - n0)) * cpr; i += 128)
+      *reinterpret_cast<uint4*>(sW + (min(SK_NT, N - n0) + i / cpr) * SK_PITCH + (i % cpr) * 8) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (64 - M) * cpr; i += 128)
+      *reinterpret_cast<uint4*>(sA + (M + i / cpr) * SK_PITCH + (i % cpr) * 8) = make_uint4(0, 0, 0, 0);
+    pdl_wait();
+    pdl_trigger();
+    if (warp == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      if (lane == 0) mbar_expect_tx(bars + 1, (uint32_t)M * row_bytes);
+      __syncwarp();
+      for (int r = lane; r < M; r += 32) bulk_g2s(sA + r * SK_PITCH, A + (int64_t)r * lda + k0, row_bytes, bars + 1, pol);
+    }
+    mbar_wait(bars, 0);
+    mbar_wait(bars + 1, 0);
+    __syncthreads();                                         // the zero-filled rows
+  } else {
   // PDL: the weight slice never depends on the preceding launch -> fetch it before griddepcontrol.wait
   for (int i = tid; i < SK_NT * cpr; i += 128) {
     const int r = i / cpr, c = i % cpr;
@@ -61,17 +100,37 @@ __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict_
   }
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  }
+  // two independent accumulator sets (even / odd k-steps): the 32-step chain of dependent mma.sync per warp was a visible part of
+  // these latency-bound launches (4 warps per CTA, ~1.3 CTAs per SM: nothing else hides it)
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float acd[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const bf16* a_ptr = sA + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SK_PITCH + (lane >> 4) * 8;
   const bf16* b_ptr = sW + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
+  int k = 0;
 #pragma unroll 4
-  for (int k = 0; k < kn; k += 16) {
+  for (; k + 32 <= kn; k += 32) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3, d0, d1, d2, d3;
+    ldmatrix_x4(a0, a1, a2, a3, a_ptr + k);
+    ldmatrix_x4(b0, b1, b2, b3, b_ptr + k);
+    ldmatrix_x4(c0, c1, c2, c3, a_ptr + k + 16);
+    ldmatrix_x4(d0, d1, d2, d3, b_ptr + k + 16);
+    mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);          // columns n0 .. n0+7
+    mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);          // columns n0+8 .. n0+15
+    mma_bf16_16816(acd[0], c0, c1, c2, c3, d0, d1);
+    mma_bf16_16816(acd[1], c0, c1, c2, c3, d2, d3);
+  }
+  if (k < kn) {
     uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
     ldmatrix_x4(a0, a1, a2, a3, a_ptr + k);
     ldmatrix_x4(b0, b1, b2, b3, b_ptr + k);
-    mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);          // columns n0 .. n0+7
-    mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);          // columns n0+8 .. n0+15
+    mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);
+    mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);
   }
+#pragma unroll
+  for (int j = 0; j < 2; j++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) acc[j][q] += acd[j][q];
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int j = 0; j < 2; j++) {
@@ -100,21 +159,28 @@ __global__ void __launch_bounds__(128) skinny_lstm_kernel(const bf16* __restrict
   extern __shared__ __align__(16) uint8_t sk_smem[];
   bf16* sA = reinterpret_cast<bf16*>(sk_smem);
   bf16* sW = sA + 64 * SK_PITCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sk_smem + SK_SMEM);      // [0] weights, [1] activations
   const int n0 = blockIdx.x * SK_NT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cpr = K / 8;
-  for (int i = tid; i < SK_NT * cpr; i += 128) {
-    const int r = i / cpr, c = i % cpr;
-    cp_async16(sW + r * SK_PITCH + c * 8, Wil + (int64_t)(n0 + r) * ldw + c * 8, true);
+  const uint32_t row_bytes = (uint32_t)K * 2u;
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    fence_barrier_init();
   }
-  pdl_wait();
-  pdl_trigger();
-  for (int i = tid; i < 64 * cpr; i += 128) {
-    const int r = i / cpr, c = i % cpr;
-    cp_async16(sA + r * SK_PITCH + c * 8, A + (int64_t)min(r, M - 1) * lda + c * 8, r < M);
+  __syncthreads();
+  if (warp == 0) {                         // weights: a parameter, bulk copies issued before griddepcontrol.wait
+    const uint64_t pol = l2_policy_evict_last();
+    if (lane == 0) mbar_expect_tx(bars, (uint32_t)SK_NT * row_bytes);
+    __syncwarp();
+    if (lane < SK_NT) bulk_g2s(sW + lane * SK_PITCH, Wil + (int64_t)(n0 + lane) * ldw, row_bytes, bars, pol);
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  // epilogue operands of this thread's (row, unit) pairs, in flight during the loads and the MMA loop
+  for (int i = tid; i < (64 - M) * cpr; i += 128)
+    *reinterpret_cast<uint4*>(sA + (M + i / cpr) * SK_PITCH + (i % cpr) * 8) = make_uint4(0, 0, 0, 0);
+  // epilogue operands of this thread's (row, unit) pairs.  The token's table row, the recurrent projection of THIS step (written by the
+  // projection kernel two launches back: the attention kernel in between has waited for it) and c_t are all older than the preceding
+  // launch: fetched before griddepcontrol.wait, so the two dependent round trips (token, then its table row) leave the critical path
   const int D = e.D;
   const int g = lane >> 2, t = lane & 3;
   const bool even = (t & 1) == 0;
@@ -141,8 +207,17 @@ __global__ void __launch_bounds__(128) skinny_lstm_kernel(const bf16* __restrict
       for (int q = 0; q < 4; q++) add[j][q] = pt[q * D + u] + hh[q * D + u];
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  if (warp == 0) {
+    const uint64_t pol = l2_policy_evict_first();
+    if (lane == 0) mbar_expect_tx(bars + 1, (uint32_t)M * row_bytes);
+    __syncwarp();
+    for (int r = lane; r < M; r += 32) bulk_g2s(sA + r * SK_PITCH, A + (int64_t)r * lda, row_bytes, bars + 1, pol);
+  }
+  mbar_wait(bars, 0);
+  mbar_wait(bars + 1, 0);
+  __syncthreads();                         // the zero-filled rows
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const bf16* a_ptr = sA + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SK_PITCH + (lane >> 4) * 8;
   const bf16* b_ptr = sW + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
@@ -173,7 +248,12 @@ __global__ void __launch_bounds__(128) skinny_lstm_kernel(const bf16* __restrict
     e.c_out[(int64_t)row * D + u] = c;
     e.h_out[(int64_t)row * D + u] = h;
     if (e.h_bf) e.h_bf[(int64_t)row * D + u] = __float2bfloat16_rn(h);
-    if (e.hd) e.hd[(int64_t)row * e.hd_stride + u] = e.dmask ? h * e.dmask[(int64_t)row * e.hd_stride + u] : h;
+    if (e.hd) {
+      float mult = 1.f;
+      if (e.dmask) mult = e.dmask[(int64_t)row * e.hd_stride + u];
+      else if (e.dstate) mult = philox_dropout_mult(e.dstate, e.row0 + row, e.t_idx, u, e.dp, 1.f / (1.f - e.dp));
+      e.hd[(int64_t)row * e.hd_stride + u] = h * mult;
+    }
   }
 }
 
@@ -193,20 +273,45 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Arrival counters are spread over GB_NC cache lines (one L2 atomic unit each): a CTA adds 1 to counter (blockIdx.x % GB_NC) with a
+// fire-and-forget red.release, warp 0 polls all GB_NC counters with ONE acquire load per lane and sums them with a warp reduce.  192
+// arrivals on a single counter serialise in the L2 atomic unit (~27 cycles each: 2.7 us, as much as a kernel boundary, which is why
+// the fused step kernels first measured no faster, run 42); 12 arrivals per counter cost ~0.2 us.  Counters are monotonic: `target` is the
+// total number of arrivals after this barrier.
+constexpr int GB_NC = 16;
 __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();                       // this CTA's global writes are visible before its arrival is
-    atomicAdd(ctr, 1u);
-    if (ld_acquire_u32(ctr) < target) {
-      const long long t0 = clock64();
-      while (ld_acquire_u32(ctr) < target) {
-        if (clock64() - t0 > 4000000000LL) __trap();          // a protocol bug must fail loudly, not hang the GPU
-      }
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + (blockIdx.x % GB_NC) * 32) : "memory");
+    const long long t0 = clock64();
+    while (true) {
+      unsigned int v = threadIdx.x < GB_NC ? ld_acquire_u32(ctr + threadIdx.x * 32) : 0u;
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (v >= target) break;
+      if (clock64() - t0 > 4000000000LL) __trap();          // a protocol bug must fail loudly, not hang the GPU
     }
   }
   __syncthreads();
 }
+
+
+// ---- timing build only (-DLO_ATT_TIMING, tools/fuse_timeline.py): per-CTA %globaltimer stamps of the last fused-step launch
+#ifdef LO_ATT_TIMING
+__device__ long long* g_sk_ts = nullptr;
+__device__ __forceinline__ void sk_ts(int k) {
+  if (g_sk_ts && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_sk_ts[(int64_t)blockIdx.x * 16 + k] = t;
+  }
+}
+#define SK_TS(k) do { if (ts_on) sk_ts(k); } while (0)
+int sk_set_ts(long long* p) { return cudaMemcpyToSymbol(g_sk_ts, &p, sizeof(p)) == cudaSuccess ? LO_OK : LO_ECUDA; }
+#else
+#define SK_TS(k) do { } while (0)
+int sk_set_ts(long long*) { return LO_OK; }
+#endif
 
 constexpr int SKF_SMEM = (64 + 2 * SK_NT) * SK_PITCH * 2;
 
@@ -221,6 +326,9 @@ __global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
   const TcLstmEpi& e = p.e;
   const bool ph1 = n0 < 4 * e.D;
   const bool ph2 = p.o1_next != nullptr && n0 < p.N2;
+  const bool ts_on = p.o1_next != nullptr;
+  (void)ts_on;
+  SK_TS(0);
   // ---- weights of both phases: parameters, independent of the preceding launches
   if (ph1)
     for (int i = tid; i < SK_NT * cpr; i += 128) {
@@ -232,8 +340,38 @@ __global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
       const int r = i / cpr, c = i % cpr;
       cp_async16(sW2 + r * SK_PITCH + c * 8, p.wcat + (int64_t)min(n0 + r, p.N2 - 1) * p.ld_wcat + c * 8, n0 + r < p.N2);
     }
-  pdl_wait();
+  // the LSTM epilogue's operands (token -> table row, recurrent projection of THIS step, c_t) were all written at least two launches
+  // back (the attention kernel in between has waited for them): fetched before griddepcontrol.wait, two dependent L2 round trips
+  // (token, then its table row) leave the critical path
   const int g = lane >> 2, t = lane & 3;
+  const int D = e.D;
+  const bool even = (t & 1) == 0;
+  const int row = warp * 16 + g + (even ? 0 : 8);
+  const bool live = row < M;
+  float add[2][4], cprev[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    cprev[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) add[j][q] = 0.f;
+  }
+  if (ph1 && live) {
+    int64_t tk = e.tok[(int64_t)row * e.tok_stride];
+    if (tk < 0) tk = 0;
+    if (tk >= e.V) tk = e.V - 1;
+    const float* pt = e.ptab + tk * 4 * D;
+    const float* hh = e.hh + (int64_t)row * e.hh_stride;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int u = n0 / 4 + 2 * j + (t >> 1);
+      cprev[j] = e.c_prev[(int64_t)row * D + u];
+#pragma unroll
+      for (int q = 0; q < 4; q++) add[j][q] = pt[q * D + u] + hh[q * D + u];
+    }
+  }
+  SK_TS(1);
+  pdl_wait();
+  SK_TS(2);
   const bf16* a_ptr = sA + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SK_PITCH + (lane >> 4) * 8;
   if (ph1) {
     for (int i = tid; i < 64 * cpr; i += 128) {
@@ -241,33 +379,9 @@ __global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
       cp_async16(sA + r * SK_PITCH + c * 8, p.gctx + (int64_t)min(r, M - 1) * p.ld_gctx + c * 8, r < M);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    const int D = e.D;
-    const bool even = (t & 1) == 0;
-    const int row = warp * 16 + g + (even ? 0 : 8);
-    const bool live = row < M;
-    float add[2][4], cprev[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      cprev[j] = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; q++) add[j][q] = 0.f;
-    }
-    if (live) {
-      int64_t tk = e.tok[(int64_t)row * e.tok_stride];
-      if (tk < 0) tk = 0;
-      if (tk >= e.V) tk = e.V - 1;
-      const float* pt = e.ptab + tk * 4 * D;
-      const float* hh = e.hh + (int64_t)row * e.hh_stride;
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        const int u = n0 / 4 + 2 * j + (t >> 1);
-        cprev[j] = e.c_prev[(int64_t)row * D + u];
-#pragma unroll
-        for (int q = 0; q < 4; q++) add[j][q] = pt[q * D + u] + hh[q * D + u];
-      }
-    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    SK_TS(3);
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     const bf16* b_ptr = sW1 + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
 #pragma unroll 4
@@ -311,7 +425,9 @@ __global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
     pdl_trigger();
     return;
   }
+  SK_TS(4);
   grid_barrier(p.bar, p.bar_target);       // h_{t+1} of every CTA is in L2 (also orders this CTA's reads of sA before reuse)
+  SK_TS(5);
   pdl_trigger();
   if (!ph2) return;
   for (int i = tid; i < 64 * cpr; i += 128) {
@@ -320,6 +436,7 @@ __global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
   }
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  SK_TS(6);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const bf16* b_ptr = sW2 + ((lane & 7) + (lane >> 4) * 8) * SK_PITCH + ((lane >> 3) & 1) * 8;
 #pragma unroll 4
@@ -342,9 +459,10 @@ __global__ void __launch_bounds__(128) dec_step_fwd_kernel(DecStepFwd p) {
       *reinterpret_cast<float2*>(p.o1_next + (int64_t)r * p.ld_o1 + n) = make_float2(acc[j][2 * h] + bx, acc[j][2 * h + 1] + by);
     }
   }
+  SK_TS(7);
 }
 
-int g_opt_dec_fuse = 0;       // measured: 13.46 vs 13.35 ms decoder fwd+bwd (run 42) - PDL already hides what the fusion removes
+int g_opt_dec_fuse = 0;       // run 42 (single-counter barrier): 13.46 vs 13.35 ms decoder fwd+bwd; see grid_barrier for the spread counters
 
 int dec_step_fwd(const DecStepFwd& p, cudaStream_t st) {
   LO_CHECK_ARG(p.M >= 1 && p.M <= 64 && p.K % 16 == 0 && p.K <= SK_KC && p.e.D == p.K && p.e.D % 4 == 0 && p.N2 % 2 == 0, "M<=64, K=D<=512");
@@ -509,10 +627,10 @@ int skinny_gemm_nt_lstm(const bf16* A, int64_t lda, const bf16* Wil, int64_t ldw
   LO_CHECK_ARG(M >= 1 && M <= 64 && K % 16 == 0 && K <= SK_KC && lda % 8 == 0 && ldw % 8 == 0 && D % 4 == 0, "M<=64, K%16, K<=512");
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(skinny_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+    LO_CUDA(cudaFuncSetAttribute(skinny_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM + 16));
     attr = true;
   }
-  LO_CUDA(launch_pdl(skinny_lstm_kernel, dim3(4 * D / SK_NT), dim3(128), (size_t)SK_SMEM, st, A, lda, Wil, ldw, M, K, e));
+  LO_CUDA(launch_pdl(skinny_lstm_kernel, dim3(4 * D / SK_NT), dim3(128), (size_t)SK_SMEM + 16, st, A, lda, Wil, ldw, M, K, e));
   LO_LAUNCH_OK();
   return LO_OK;
 }
@@ -523,7 +641,8 @@ int skinny_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, float
   LO_CHECK_ARG(M >= 1 && M <= 64 * 1024 && K % 16 == 0 && N % 2 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 2 == 0, "K%16, ld%8");
   static bool attr = false;
   if (!attr) {
-    LO_CUDA(cudaFuncSetAttribute(skinny_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+    LO_CUDA(cudaFuncSetAttribute(skinny_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+    LO_CUDA(cudaFuncSetAttribute(skinny_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM + 16));
     attr = true;
   }
   int ks = cdiv(K, SK_KC);
@@ -533,8 +652,13 @@ int skinny_gemm_nt(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, float
   ks = cdiv(K, kc);
   const int atomic = (ks > 1 || atomic_acc) ? 1 : 0;
   if (ks > 1 && !atomic_acc) LO_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
-  LO_CUDA(launch_pdl(skinny_mma_kernel, dim3(cdiv(N, SK_NT), ks, cdiv(M, 64)), dim3(128), (size_t)SK_SMEM, st, A, lda, W, ldw, C, ldc, M, N,
-                     K, kc, bias, atomic));
+  if (g_opt_skinny_tma) {
+    LO_CUDA(launch_pdl(skinny_mma_kernel<true>, dim3(cdiv(N, SK_NT), ks, cdiv(M, 64)), dim3(128), (size_t)SK_SMEM + 16, st, A, lda, W, ldw, C,
+                       ldc, M, N, K, kc, bias, atomic));
+  } else {
+    LO_CUDA(launch_pdl(skinny_mma_kernel<false>, dim3(cdiv(N, SK_NT), ks, cdiv(M, 64)), dim3(128), (size_t)SK_SMEM, st, A, lda, W, ldw, C, ldc,
+                       M, N, K, kc, bias, atomic));
+  }
   LO_LAUNCH_OK();
   return LO_OK;
 }
