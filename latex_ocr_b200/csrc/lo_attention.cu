@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
   // PDL: the producer's bulk copies read only loop-invariant tensors (att1, enc: written long before the preceding kernel), so they
   // are issued BEFORE griddepcontrol.wait and overlap the tail of the preceding launch; consumers wait before touching its results.
   float m = -INFINITY, l = 0.f;
+  float gate_pf = 0.f;
   float acc[NVC * 8];
 #pragma unroll
   for (int i = 0; i < NVC * 8; i++) acc[i] = 0.f;
@@ -166,6 +167,9 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
     pdl_trigger();
 #pragma unroll
     for (int j = 0; j < NVA; j++) ld8(att2 + (int64_t)b * att2_stride + (j * 32 + lane) * 8, a2 + j * 8);
+    // cluster mode: the gate pre-activation of the channel this thread finalises after the combine (one L2 round trip off the tail)
+    if (CL && gate_pre && (int)threadIdx.x < (CHC + nsplit - 1) / nsplit && sp * ((CHC + nsplit - 1) / nsplit) + (int)threadIdx.x < CHC)
+      gate_pf = gate_pre[(int64_t)b * gate_stride + sp * ((CHC + nsplit - 1) / nsplit) + threadIdx.x];
     ATT_TS(2, threadIdx.x == 0);
     for (int i = 0; i < nst; i++) {
       const int s = i % AP_STAGES;
@@ -307,7 +311,8 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_fwd_pipe_ke
       t *= invL;
       ctx[(int64_t)b * CHC + c] = t;
       if (gate_pre) {
-        const float g = sigmoidf_(gate_pre[(int64_t)b * gate_stride + c]);
+        const bool pf = c == sp * cps + (int)threadIdx.x && (int)threadIdx.x < AP_CWARPS * 32;     // fetched before the main loop
+        const float g = sigmoidf_(pf ? gate_pf : gate_pre[(int64_t)b * gate_stride + c]);
         gate_pre[(int64_t)b * gate_stride + c] = g;
         gctx[(int64_t)b * CHC + c] = g * t;
         if (gctx_bf) gctx_bf[(int64_t)b * CHC + c] = __float2bfloat16_rn(g * t);
@@ -935,6 +940,15 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_bwd_mma_kernel(
   }
   __syncthreads();
   const int g = lane >> 2, q = lane & 3;
+  // cluster mode: the full_att weight and the att2 value of the column this thread finalises after the combine are forward-pass
+  // data -> fetched up front, off the tail
+  const int cps_pf = (CH + nsplit - 1) / nsplit;
+  const int c_pf = sp * cps_pf + (int)threadIdx.x;
+  float wf_pf = 0.f, a2_pf = 0.f;
+  if (CL && (int)threadIdx.x < cps_pf && c_pf < CH) {
+    wf_pf = wf[c_pf];
+    if (dwf_part) a2_pf = att2[(int64_t)b * o1_stride + c_pf];
+  }
   float macc[4][4];
 #pragma unroll
   for (int j = 0; j < 4; j++)
@@ -1113,9 +1127,11 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_bwd_mma_kernel(
     for (int c = sp * cps + threadIdx.x; c < min(CH, (sp + 1) * cps); c += AP_THREADS) {
       float t = 0.f;
       for (int qq = 0; qq < nsplit; qq++) t += cluster.map_shared_rank(s_part, qq)[c];      // fixed order -> deterministic
-      if (dwf_part) dwf_part[(int64_t)b * CH + c] += t * att2[(int64_t)b * o1_stride + c];      // att2 term of d w_full (one owner per (b, c))
-      datt2[(int64_t)b * dcat_stride + c] = t * wf[c];
-      if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wf[c]);
+      const bool pf = c == c_pf;
+      const float wfc = pf ? wf_pf : wf[c];
+      if (dwf_part) dwf_part[(int64_t)b * CH + c] += t * (pf ? a2_pf : att2[(int64_t)b * o1_stride + c]);      // att2 term of d w_full (one owner per (b, c))
+      datt2[(int64_t)b * dcat_stride + c] = t * wfc;
+      if (datt2_bf) datt2_bf[(int64_t)b * dcat_stride + c] = __float2bfloat16_rn(t * wfc);
     }
     cluster.sync();
     ATT_TS(5, threadIdx.x == 0);

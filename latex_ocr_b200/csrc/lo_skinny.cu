@@ -53,6 +53,15 @@ __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict_
   const int kn = min(kc, K - k0);                            // multiple of 16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cpr = kn / 8;                                    // 16-byte chunks per row
+  // the bias is a parameter: fetched up front instead of after the MMA loop (one L2 round trip off the tail of the launch)
+  float bpre[2][2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int n = n0 + j * 8 + 2 * (lane & 3);
+    const bool has = bias && blockIdx.y == 0 && n < N;
+    bpre[j][0] = has ? bias[n] : 0.f;
+    bpre[j][1] = has ? bias[n + 1] : 0.f;
+  }
   if constexpr (TMA) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sk_smem + SK_SMEM);      // [0] weights, [1] activations
     if (tid == 0) {
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(128) skinny_mma_kernel(const bf16* __restrict_
   for (int j = 0; j < 2; j++) {
     const int n = n0 + j * 8 + 2 * t;
     if (n >= N) continue;
-    const float bx = (bias && blockIdx.y == 0) ? bias[n] : 0.f, by = (bias && blockIdx.y == 0) ? bias[n + 1] : 0.f;
+    const float bx = bpre[j][0], by = bpre[j][1];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int r = warp * 16 + g + h * 8;
