@@ -161,8 +161,9 @@ int lo_attention_forward_mask(const void* att1, const void* enc, int dt, const f
  * [B][alpha_stride] ; ctx / dctx_out [B][C] ; dgctx [B][dg_stride] ; dreg [B][dreg_stride] and sreg [B][sreg_stride] may be NULL ;
  * datt2 / dgp [B][dcat_stride] ; dwf_part (optional) [B][A] += sum_r de_r relu(att1_r + att2) (full_att.weight gradient).
  * d att1 and d enc are NOT produced here: they are hoisted out of the time loop (see lo_decoder_backward).
- * relu_mask (optional): the bits lo_attention_forward_mask stored; att1 is then NOT read (att2 is unused) and dwf_part is not
- * accumulated. */
+ * relu_mask (optional): the bits lo_attention_forward_mask stored; att1 is then NOT read, and dwf_part (optional) receives only the
+ * att2 term of the full_att.weight gradient, sum_r de_r [on] att2_a — the term that needs att1 itself, sum_r de_r [on] att1_ra, is
+ * added by lo_decoder_backward's single sweep over att1 after the time loop. */
 int lo_attention_backward(const void* att1, const void* enc, int dt, const float* att2, const float* gate, int64_t o1_stride,
                           const float* wf, const float* alpha, int64_t alpha_stride, const float* ctx, const float* dgctx,
                           int64_t dg_stride, const float* dreg, int64_t dreg_stride, const float* sreg, int64_t sreg_stride,
