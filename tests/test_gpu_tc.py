@@ -134,7 +134,7 @@ def test_tc_conv3x3_wgrad(N, H, W, Cin, Cout, pad):
 
 
 _SCHEDULE_OPTS = {"fuse_lstm": (0, 1), "dec_streams": (1, 2), "skinny_mma": (1, 0), "dec_fuse": (0, 1), "dec_fuse_bwd": (0, 1), "att_maskbits": (1, 0),
-                  "conv_persist": (1, 0), "wgrad256": (0, 1), "conv_mt2": (1, 0), "dec_cl": (0, 1), "dec_cl_bwd": (0, 1), "att_bwd_mma": (1, 0)}
+                  "conv_persist": (1, 0), "wgrad256": (0, 1), "conv_mt2": (1, 0), "dec_cl": (0, 1), "dec_cl_bwd": (0, 1), "att_bwd_mma": (1, 0), "skinny_tma": (1, 0)}
 
 
 @pytest.mark.parametrize("opt", sorted(_SCHEDULE_OPTS))
