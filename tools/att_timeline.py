@@ -1,4 +1,5 @@
-"""Per-CTA timeline of the attention step kernels (timing build: LO_LIB_DIR=_C_timing, built with -DLO_ATT_TIMING).
+"""(build the timing variant first: LO_LIB_DIR=_C_timing LO_NVCC_EXTRA=-DLO_ATT_TIMING python -m latex_ocr_b200.build)
+Per-CTA timeline of the attention step kernels (timing build: LO_LIB_DIR=_C_timing, built with -DLO_ATT_TIMING).
 Stamps (%globaltimer, ns): 0 entry, 1 consumer past griddepcontrol.wait, 2 consumer prologue done, 3 first stage landed,
 4 main loop done, 8 after the CTA barrier, 5 exit; producer: 6 first stage issued, 7 last stage issued."""
 import ctypes, os, sys

@@ -1,4 +1,5 @@
-"""Per-CTA timeline of the cluster-fused decoder step kernels (timing build: LO_LIB_DIR=_C_timing, -DLO_ATT_TIMING).  The stamps of the
+"""(build the timing variant first: LO_LIB_DIR=_C_timing LO_NVCC_EXTRA=-DLO_ATT_TIMING python -m latex_ocr_b200.build)
+Per-CTA timeline of the cluster-fused decoder step kernels (timing build: LO_LIB_DIR=_C_timing, -DLO_ATT_TIMING).  The stamps of the
 LAST launch of a decoder forward / backward pass (time loops only, attention switched off or on) are reported.
 Stamps: 0 entry, 1 ring prefill + operand loads issued, 2 past griddepcontrol.wait, 3 A operand landed, 4 phase boundary reached,
 9 cell done, 5 past the cluster barrier, 6 all-gather done, 7 main loop done, 8 exit."""

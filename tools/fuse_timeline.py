@@ -1,4 +1,5 @@
-"""Per-CTA timeline of the grid-barrier fused forward step kernel (dec_fuse=1; timing build LO_LIB_DIR=_C_timing, -DLO_ATT_TIMING),
+"""(build the timing variant first: LO_LIB_DIR=_C_timing LO_NVCC_EXTRA=-DLO_ATT_TIMING python -m latex_ocr_b200.build)
+Per-CTA timeline of the grid-barrier fused forward step kernel (dec_fuse=1; timing build LO_LIB_DIR=_C_timing, -DLO_ATT_TIMING),
 time loop only, attention switched off.  Stamps: 0 entry, 1 weights issued, 2 past griddepcontrol.wait, 3 A operand landed,
 4 cell done (before the grid barrier), 5 past the barrier, 6 A of phase 2 landed, 7 end."""
 import ctypes, os, sys
