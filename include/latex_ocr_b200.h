@@ -8,6 +8,15 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
  *   - stream-ordered on `stream` (a cudaStream_t passed as void*); no allocation, no synchronisation,
  *     no host-visible global state -> every call is CUDA-graph capturable;
+ *   - programmatic dependent launch: most kernels are launched so that they may become resident while the preceding
+ *     launch of the stream drains, and read their PARAMETER operands (weights, biases, projection tables — never
+ *     activations) before they wait for it.  A parameter must therefore not be produced by the launch enqueued
+ *     immediately before the call that consumes it (an optimiser step followed by anything else is fine: every
+ *     entry point enqueues more than one launch or waits first).  The stand-alone attention entry points
+ *     (lo_attention_forward / _forward_mask / _backward), whose early reads include activations (att1, enc; alpha,
+ *     ctx, gate of the forward pass), are launched WITHOUT that overlap unless lo_set_option("att_abi_pdl", 1) says the
+ *     caller guarantees those tensors are older than the preceding launch; lo_set_option("pdl", 0) turns the overlap
+ *     off everywhere;
  *   - return 0 on success, negative LO_E* otherwise (never throws); lo_last_error() gives the text;
  *   - dtype arguments are LO_F32 or LO_BF16 and name the STORAGE type of the "big" tensors
  *     (feature maps, conv/linear weight shadows, encoder_out, att1).  Small per-step state is fp32.
@@ -38,7 +47,11 @@ const char* lo_last_error(void);
 /* number of kernels launched through this library since load (bench.py's gpu_launches) */
 int64_t lo_launch_count(void);
 /* tuning knobs: "att_pipe" (1: TMA-pipelined attention kernels, 0: register-streaming), "att_policy_enc" /
- * "att_policy_att1" (L2 policy 0 normal, 1 evict_last, 2 evict_first), "att_nsplit" (0 = automatic) */
+ * "att_policy_att1" (L2 policy 0 normal, 1 evict_last, 2 evict_first), "att_nsplit" (0 = automatic), "pdl", "att_abi_pdl" (above);
+ * schedule variants, each parity-tested against the default (tests/test_gpu_tc.py): "att_maskbits", "att_bwd_mma",
+ * "skinny_mma", "skinny_tma", "fuse_lstm", "dec_streams", "dec_fuse", "dec_fuse_bwd", "dec_cl", "dec_cl_bwd", "conv_persist",
+ * "conv_mt2", "conv_mc", "wgrad256"; "dbg_skip" is a timing-dissection aid (results are garbage).  LO_OPTS=name=value,... in the
+ * environment sets them at load time (Python side). */
 int lo_set_option(const char* name, int value);
 /* current value of a tuning knob (-1: unknown name) */
 int lo_get_option(const char* name);

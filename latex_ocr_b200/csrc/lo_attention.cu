@@ -21,6 +21,7 @@ int g_opt_att_policy_enc = 1;    // 0 normal, 1 evict_last, 2 evict_first
 int g_opt_att_policy_att1 = 2;
 int g_opt_att_nsplit = 0;        // 0 = automatic
 int g_opt_att_cluster = 1;
+int g_opt_att_abi_pdl = 0;       // 1: the stand-alone attention entry points may use programmatic dependent launch too (bench probes)
 int g_opt_att_bwd_mma = 1;       // 1: 512-wide bf16 backward with both contractions on mma.sync (attention_bwd_mma_kernel)
 int g_opt_att_maskbits = 1;      // 1: the forward attention kernel stores the ReLU mask bits, the backward streams them instead of att1       // 1: the splits of one batch row form a thread-block cluster and combine through DSMEM
 
@@ -1176,9 +1177,15 @@ int att_pipe_splits(int B, int hint = 0) {
 // recorded in CUDA-graph kernel nodes, which a stream attribute is not
 static cudaAccessPolicyWindow g_att_window{};
 
-// launch with (optional) cluster dimension {ns,1,1} and the PDL attribute
+static inline bool att_pdl_ok(int abi) { return !abi || g_opt_att_abi_pdl; }
+
+// launch with (optional) cluster dimension {ns,1,1} and the PDL attribute.
+// pdl = false (stand-alone C entry points): these kernels read operands BEFORE griddepcontrol.wait — loop-invariant inputs in the
+// forward (att1, enc, full_att weight), forward-pass results in the backward (alpha, ctx, gate, att2, d reg).  Inside the decoder's
+// time loops those are at least two launches old; a caller of the C ABI may have produced them with the launch enqueued just before,
+// which would be allowed to overlap.  Without the attribute the launch is fully stream-ordered (the wait is a no-op).
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_att(void (*kernel)(KArgs...), dim3 grid, size_t smem, int cluster_x, cudaStream_t st, Args... args) {
+static cudaError_t launch_att(void (*kernel)(KArgs...), dim3 grid, size_t smem, int cluster_x, cudaStream_t st, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(AP_THREADS);
@@ -1191,7 +1198,7 @@ static cudaError_t launch_att(void (*kernel)(KArgs...), dim3 grid, size_t smem, 
     attr[n].val.accessPolicyWindow = g_att_window;
     n++;
   }
-  if (g_opt_pdl) {
+  if (g_opt_pdl && pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     n++;
@@ -1227,11 +1234,11 @@ static int fwd_launch_m(const AttFwdArgs& x, cudaStream_t st) {
   const int rpi = x.rows_per_img > 1 ? x.rows_per_img : 1;
   if (use_cluster(ns, x.R)) {
     const size_t smem = C::SMEM + (size_t)((x.R + ns - 1) / ns) * 4;
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT, MK>, dim3(ns, x.B), smem, ns, st, (const T*)x.att1, (const T*)x.enc,
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, true, ACT, MK>, dim3(ns, x.B), smem, ns, st, att_pdl_ok(x.abi), (const T*)x.att1, (const T*)x.enc,
                        x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx, x.gctx_bf, x.R, ns,
                        (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi, x.mask_out));
   } else {
-    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT, MK>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, (const T*)x.att1,
+    LO_CUDA(launch_att(attention_fwd_pipe_kernel<T, NVA, NVC, false, ACT, MK>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, att_pdl_ok(x.abi), (const T*)x.att1,
                        (const T*)x.enc, x.att2, x.att2_stride, x.wf, x.alpha, x.alpha_stride, x.ctx, x.gate_pre, x.gate_stride, x.gctx,
                        x.gctx_bf, x.R, ns, (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, rpi,
                        x.mask_out));
@@ -1291,9 +1298,9 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, x.att2, x.dwf_part
     const size_t smem_t = (size_t)ABM_SMEM + (size_t)att_rows_per_split(x.R, ns) * 8;      // + alpha / d reg of the CTA's rows
     if (use_cluster(ns, x.R)) {
-      LO_CUDA(launch_att(attention_bwd_mma_kernel<true>, dim3(ns, x.B), smem_t, ns, st, LO_BWDT_ARGS));
+      LO_CUDA(launch_att(attention_bwd_mma_kernel<true>, dim3(ns, x.B), smem_t, ns, st, att_pdl_ok(x.abi), LO_BWDT_ARGS));
     } else {
-      LO_CUDA(launch_att(attention_bwd_mma_kernel<false>, dim3(ns, x.B), smem_t, 1, st, LO_BWDT_ARGS));
+      LO_CUDA(launch_att(attention_bwd_mma_kernel<false>, dim3(ns, x.B), smem_t, 1, st, att_pdl_ok(x.abi), LO_BWDT_ARGS));
     }
 #undef LO_BWDT_ARGS
     LO_LAUNCH_OK();
@@ -1312,9 +1319,9 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
       x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns, (int*)x.work,           \
       (float*)((char*)x.work + 4096), g_opt_att_policy_enc, x.att2, x.dwf_part
     if (use_cluster(ns, x.R)) {
-      LO_CUDA(launch_att(attention_bwd_mask_kernel<T, NVA, NVC, true>, dim3(ns, x.B), (size_t)CM::SMEM, ns, st, LO_BWDM_ARGS));
+      LO_CUDA(launch_att(attention_bwd_mask_kernel<T, NVA, NVC, true>, dim3(ns, x.B), (size_t)CM::SMEM, ns, st, att_pdl_ok(x.abi), LO_BWDM_ARGS));
     } else {
-      LO_CUDA(launch_att(attention_bwd_mask_kernel<T, NVA, NVC, false>, dim3(ns, x.B), (size_t)CM::SMEM, 1, st, LO_BWDM_ARGS));
+      LO_CUDA(launch_att(attention_bwd_mask_kernel<T, NVA, NVC, false>, dim3(ns, x.B), (size_t)CM::SMEM, 1, st, att_pdl_ok(x.abi), LO_BWDM_ARGS));
     }
 #undef LO_BWDM_ARGS
     LO_LAUNCH_OK();
@@ -1325,9 +1332,9 @@ static int bwd_launch_a(const AttBwdArgs& x, cudaStream_t st) {
       x.dreg_stride, x.sreg, x.sreg_stride, x.de, x.datt2, x.dgp, x.dcat_stride, x.datt2_bf, x.dgp_bf, x.dctx_out, x.R, ns,       \
       (int*)x.work, (float*)((char*)x.work + 4096), g_opt_att_policy_enc, g_opt_att_policy_att1, x.dwf_part
   if (use_cluster(ns, x.R)) {
-    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NVA, NVC, true, ACT>, dim3(ns, x.B), (size_t)C::SMEM, ns, st, LO_BWD_ARGS));
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NVA, NVC, true, ACT>, dim3(ns, x.B), (size_t)C::SMEM, ns, st, att_pdl_ok(x.abi), LO_BWD_ARGS));
   } else {
-    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NVA, NVC, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, LO_BWD_ARGS));
+    LO_CUDA(launch_att(attention_bwd_pipe_kernel<T, NVA, NVC, false, ACT>, dim3(ns, x.B), (size_t)C::SMEM, 1, st, att_pdl_ok(x.abi), LO_BWD_ARGS));
   }
 #undef LO_BWD_ARGS
   LO_LAUNCH_OK();
@@ -1399,6 +1406,7 @@ extern "C" int lo_get_option(const char* name) {
   if (!strcmp(name, "att_pipe")) return lo::g_opt_att_pipe;
   if (!strcmp(name, "att_maskbits")) return lo::g_opt_att_maskbits;
   if (!strcmp(name, "att_bwd_mma")) return lo::g_opt_att_bwd_mma;
+  if (!strcmp(name, "att_abi_pdl")) return lo::g_opt_att_abi_pdl;
   if (!strcmp(name, "att_cluster")) return lo::g_opt_att_cluster;
   if (!strcmp(name, "pdl")) return lo::g_opt_pdl;
   if (!strcmp(name, "conv_persist")) return lo::g_opt_conv_persist;
@@ -1425,6 +1433,7 @@ extern "C" int lo_set_option(const char* name, int value) {
   else if (!strcmp(name, "att_cluster")) lo::g_opt_att_cluster = value;
   else if (!strcmp(name, "att_maskbits")) lo::g_opt_att_maskbits = value;
   else if (!strcmp(name, "att_bwd_mma")) lo::g_opt_att_bwd_mma = value;
+  else if (!strcmp(name, "att_abi_pdl")) lo::g_opt_att_abi_pdl = value;
   else if (!strcmp(name, "dbg_skip")) lo::g_opt_dbg_skip = value;
   else if (!strcmp(name, "conv_mc")) lo::g_opt_conv_mc = value;
   else if (!strcmp(name, "conv_persist")) lo::g_opt_conv_persist = value;

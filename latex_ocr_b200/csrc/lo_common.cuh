@@ -202,6 +202,7 @@ struct AttFwdArgs {
   int act;             // 0 ReLU score (torch flavour), 1 tanh (Genthial cell)
   int a_ch;            // channels of att1 / att2 / wf (0 = same as enc)
   uint8_t* mask_out;   // optional (ReLU score only): [B][R][A/8] bits (att1 + att2 > 0) of this step, for the backward
+  int abi = 0;         // 1: called through a stand-alone C entry point -> launched WITHOUT programmatic dependent launch (see launch_att)
 };
 struct AttBwdArgs {
   const void *att1, *enc;
@@ -218,6 +219,7 @@ struct AttBwdArgs {
   int a_ch;
   const uint8_t* mask_in;   // optional (ReLU score only): the forward's mask bits; the kernel then streams enc + 1 bit per att1
                             // element instead of enc + att1 (d w_full must then come from the post-loop sweep: dwf_part unused)
+  int abi = 0;         // as in AttFwdArgs
 };
 extern int g_opt_att_pipe;
 extern int g_opt_att_maskbits;

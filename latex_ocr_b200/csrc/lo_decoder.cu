@@ -918,11 +918,11 @@ static int32_t* work_dlen(const lo_decoder_args* a) { return (int32_t*)((char*)a
 static int attention_forward_launch(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride,
                                     const float* wf, float* alpha, int64_t alpha_stride, float* ctx, float* gate_pre,
                                     int64_t gate_stride, float* gctx, bf16* gctx_bf, int B, int R, int C, void* work, cudaStream_t st,
-                                    int rpi = 1, int nsplit_hint = 0, uint8_t* mask_out = nullptr) {
+                                    int rpi = 1, int nsplit_hint = 0, uint8_t* mask_out = nullptr, int abi = 0) {
   if (rpi < 1) rpi = 1;
   if (g_opt_att_pipe) {
     AttFwdArgs x{att1, enc, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, gctx_bf, B, R, work, rpi,
-                 nsplit_hint, 0, 0, mask_out};
+                 nsplit_hint, 0, 0, mask_out, abi};
     return attention_fwd_pipe(x, dt, C, st);
   }
   const int ns = att_splits(B);
@@ -1171,7 +1171,7 @@ int lo_attention_forward(const void* att1, const void* enc, int dt, const float*
   LO_CHECK_ARG(B > 0 && B <= 512 && R > 0, "B in 1..512, R > 0");
   LO_CHECK_ARG(att2_stride % 4 == 0, "att2 rows must be 16-byte aligned");
   return attention_forward_launch(att1, enc, dt, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, nullptr,
-                                  B, R, C, work, (cudaStream_t)stream);
+                                  B, R, C, work, (cudaStream_t)stream, 1, 0, nullptr, 1);
 }
 
 int lo_attention_forward_mask(const void* att1, const void* enc, int dt, const float* att2, int64_t att2_stride, const float* wf,
@@ -1183,7 +1183,7 @@ int lo_attention_forward_mask(const void* att1, const void* enc, int dt, const f
   LO_CHECK_ARG(att2_stride % 4 == 0, "att2 rows must be 16-byte aligned");
   LO_CHECK_ARG(!relu_mask_out || g_opt_att_pipe, "mask bits are written by the TMA-ring kernel (option att_pipe=1)");
   return attention_forward_launch(att1, enc, dt, att2, att2_stride, wf, alpha, alpha_stride, ctx, gate_pre, gate_stride, gctx, nullptr,
-                                  B, R, C, work, (cudaStream_t)stream, 1, 0, relu_mask_out);
+                                  B, R, C, work, (cudaStream_t)stream, 1, 0, relu_mask_out, 1);
 }
 
 int lo_attention_backward(const void* att1, const void* enc, int dt, const float* att2, const float* gate, int64_t o1_stride,
@@ -1197,6 +1197,7 @@ int lo_attention_backward(const void* att1, const void* enc, int dt, const float
   LO_CHECK_ARG(g_opt_att_pipe, "stand-alone attention backward runs on the TMA-ring kernel (option att_pipe=1)");
   AttBwdArgs x{att1, enc, att2, gate, o1_stride, wf, alpha, alpha_stride, ctx, dgctx, dg_stride, dreg, dreg_stride, sreg, sreg_stride,
                de, datt2, dgp, dcat_stride, nullptr, nullptr, dctx_out, B, R, work, dwf_part, 0, 0, 0, relu_mask};
+  x.abi = 1;
   return attention_bwd_pipe(x, dt, C, (cudaStream_t)stream);
 }
 

@@ -35,6 +35,7 @@ st = _lib.stream_ptr()
 dt = _lib.LO_BF16
 buf = torch.zeros(1024 * 16, dtype=torch.int64, device="cuda")
 _lib.check(L.lo_debug_buffer(_lib.ptr(buf)))
+_lib.set_option("att_abi_pdl", 1)       # static inputs: let the stand-alone entry points overlap like the time loop's launches do
 
 
 def fwd(s):
