@@ -1407,6 +1407,8 @@ extern "C" int lo_get_option(const char* name) {
   if (!strcmp(name, "att_maskbits")) return lo::g_opt_att_maskbits;
   if (!strcmp(name, "att_bwd_mma")) return lo::g_opt_att_bwd_mma;
   if (!strcmp(name, "att_abi_pdl")) return lo::g_opt_att_abi_pdl;
+  if (!strcmp(name, "dbg_skip")) return lo::g_opt_dbg_skip;
+  if (!strcmp(name, "conv_mc")) return lo::g_opt_conv_mc;
   if (!strcmp(name, "att_cluster")) return lo::g_opt_att_cluster;
   if (!strcmp(name, "pdl")) return lo::g_opt_pdl;
   if (!strcmp(name, "conv_persist")) return lo::g_opt_conv_persist;
