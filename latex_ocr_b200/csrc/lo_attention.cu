@@ -862,7 +862,9 @@ __global__ void __launch_bounds__(AP_THREADS, LO_ATT_MINB) attention_bwd_mask_ke
 
 // ------------------------------------------------------------------------------------------------------------------------------
 // [r2b] Tensor-core backward for the 512-wide torch flavour (bf16): the two contractions of the step run on mma.sync instead of
-// CUDA-core FMAs / predicated adds, which made attention_bwd_mask_kernel instruction-issue bound (0.54 of the HBM peak):
+// CUDA-core FMAs / predicated adds (2.5x fewer warp instructions).  Measured: the launch was NOT issue-bound — 17.35 vs 17.44 us
+// (run 60); what it loses it loses at its ends — but the tensor-core version frees the issue slots and,
+// with alpha / d reg staged in shared memory and the tail operands fetched up front, runs at 15.7 us:
 //   d[r]     = sum_c enc[r][c] * dctx[c]          A = 16 enc rows straight from the ring (ldmatrix), B = dctx split into bf16 hi+lo
 //                                                  (columns 0/1 of B, products exact, fp32 accumulation)
 //   datt2[a] = sum_r bit[r][a] * de[r]            A = mask bits expanded to bf16 {0, 2.0} with ONE shift + ONE and per register,
